@@ -1,0 +1,241 @@
+/*
+ * refrakt_b200 — C ABI of the B200-native fractal-flame render core.
+ *
+ * Drop-in boundary for the render path of untrioctium/refrakt. The reference has no
+ * FFI layer: its path sits behind the C++ methods of `struct flame`
+ * (src/flame.hpp:41-174), `struct flame_compiler` (src/variation_table.hpp:20-60) and
+ * the density / tonemap block inlined in the main loop (src/main.cpp:490-535). Every
+ * entry point below names the reference interface it replaces. INTEGRATION.md shows
+ * the binding a refrakt maintainer would add.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only. Pointers named *_dev are CUDA device pointers on
+ *    the current device; all others are host pointers.
+ *  - Functions returning int return 0 on success and a negative RFK_E_* code on
+ *    failure; functions returning a handle return NULL on failure. The message is
+ *    available from rfk_last_error() (thread-local), mirroring the reference's
+ *    "nullptr + message on stdout" convention (src/flame.cpp:196, :222-225).
+ *  - Like the reference (one thread owning the GL context, class-static buffers),
+ *    the library is not re-entrant: one host thread per process drives one device.
+ *  - There is no CPU fallback. Calls that need the GPU fail with RFK_E_CUDA when no
+ *    device is available; parsing and code generation work without one.
+ */
+#ifndef REFRAKT_B200_H
+#define REFRAKT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFK_ABI_VERSION 1
+
+enum {
+    RFK_OK = 0,
+    RFK_E_INVALID = -1, /* bad argument */
+    RFK_E_CUDA = -2,    /* CUDA / NVRTC failure, or no device */
+    RFK_E_STATE = -3,   /* call order: e.g. draw before warmup */
+    RFK_E_NOTFOUND = -4 /* unknown name or index */
+};
+
+typedef struct rfk_compiler rfk_compiler; /* flame_compiler, src/variation_table.hpp:20 */
+typedef struct rfk_flame rfk_flame;       /* flame, src/flame.hpp:41 */
+
+int rfk_abi_version(void);
+const char* rfk_last_error(void);
+
+/* ---- device plumbing (replaces the GL context + storage_buffer<T> RAII of src/buffer_objects.hpp) ---- */
+int rfk_set_device(int ordinal);
+int rfk_set_stream(void* cuda_stream); /* cudaStream_t; NULL = default stream */
+int rfk_synchronize(void);
+void* rfk_device_alloc(size_t bytes);  /* storage_buffer<T>{n}, buffer_objects.hpp:11-22 */
+int rfk_device_free(void* ptr_dev);
+int rfk_device_zero(void* ptr_dev, size_t bytes);                         /* storage_buffer::zero_out, :39-41 */
+int rfk_memcpy_to_device(void* dst_dev, const void* src, size_t bytes);   /* storage_buffer::update_all, :43-45 */
+int rfk_memcpy_to_host(void* dst, const void* src_dev, size_t bytes);     /* storage_buffer::get_*, :24-37 */
+uint64_t rfk_kernel_launch_count(void); /* kernels launched by this library since load */
+
+/* ---- global simulation parameters: flame::set_sim_parameters, src/flame.hpp:77, src/flame.cpp:105-158 ----
+ * total_particles / temporal_samples must be a multiple of 256 (the reference dispatches
+ * (P/TS)/256 workgroups, flame.cpp:263). Seeds one JSF32 state per particle slot with
+ * warmup_ctx(state, seed + slot) (src/util.hpp:90-95; the reference uses seed 0), on the
+ * device. shuffle_count is accepted for signature parity; the per-pass permutations are
+ * computed on chip. Invalidates the particle buffers of every live flame. */
+int rfk_set_sim_parameters(size_t total_particles, size_t temporal_samples, size_t shuffle_count, uint64_t seed);
+
+/* ---- flame_compiler: src/variation_table.hpp:20-60, src/variation_table.cpp:182-265 ---- */
+rfk_compiler* rfk_compiler_create(const char* variations_yaml_path); /* ctor, variation_table.cpp:182-215 */
+rfk_compiler* rfk_compiler_create_from_text(const char* yaml_text);
+int rfk_compiler_load_overlay(rfk_compiler* c, const char* yaml_path); /* extra / corrected definitions, same format */
+void rfk_compiler_destroy(rfk_compiler* c);
+int rfk_compiler_is_param(const rfk_compiler* c, const char* name);     /* variation_table.hpp:39 */
+int rfk_compiler_is_variation(const rfk_compiler* c, const char* name); /* variation_table.hpp:40 */
+int rfk_compiler_is_common(const rfk_compiler* c, const char* name);    /* variation_table.hpp:41 */
+int rfk_compiler_variation_count(const rfk_compiler* c);                /* variations().size(), :47 */
+const char* rfk_compiler_variation_name(const rfk_compiler* c, int index); /* alphabetical, as std::map iterates */
+/* get_parameters_for_variation, :44 — names joined by '\n' into buf; returns the count or a negative code */
+int rfk_compiler_get_parameters_for_variation(const rfk_compiler* c, const char* name, char* buf, size_t buf_len);
+const char* rfk_compiler_param_owner(const rfk_compiler* c, const char* param); /* :43 */
+
+/* ---- flame: load / destroy. flame::load_flame, src/flame.hpp:84, src/flame.cpp:160-226 ----
+ * NULL on an unreadable file, an unknown xform attribute, or generated kernels that do
+ * not compile (the reference: shader compile failure, flame.cpp:30). */
+rfk_flame* rfk_flame_load(const char* path, const rfk_compiler* c);
+rfk_flame* rfk_flame_load_string(const char* xml_text, const rfk_compiler* c);
+void rfk_flame_destroy(rfk_flame* f); /* ~flame, src/flame.hpp:91-93 */
+
+/* ---- flame: public genome fields, src/flame.hpp:44-60. Writing a field marks the flame as
+ * needing warmup (the UI does this by hand, src/main.cpp:335-369, :397-409). ---- */
+typedef struct rfk_flame_info {
+    uint32_t size[2];
+    float center[2];
+    float scale, rotate;
+    int32_t estimator_min, estimator_radius;
+    float estimator_curve;
+    float gamma, vibrancy, brightness;
+    int32_t num_xforms;      /* read-only */
+    int32_t has_final_xform; /* read-only */
+    int32_t param_count;     /* read-only: buffer_map["size"], src/flame.cpp:68 */
+} rfk_flame_info;
+
+/* flame_xform, src/flame.hpp:21-37. index -1 is the final xform (for_each_xform, :62-68). */
+typedef struct rfk_xform_info {
+    float affine[6];
+    int32_t has_post;
+    float post[6];
+    float weight, color, color_speed;
+    float rotation_frequency, opacity;
+    int32_t num_variations; /* read-only */
+    int32_t num_params;     /* read-only */
+} rfk_xform_info;
+
+int rfk_flame_get_info(const rfk_flame* f, rfk_flame_info* out);
+int rfk_flame_set_info(rfk_flame* f, const rfk_flame_info* in);
+int rfk_flame_get_xform(const rfk_flame* f, int index, rfk_xform_info* out);
+int rfk_flame_set_xform(rfk_flame* f, int index, const rfk_xform_info* in); /* has_post must keep its loaded value */
+/* variations / var_param maps of an xform (std::map order = alphabetical) */
+const char* rfk_flame_variation_name(const rfk_flame* f, int xform, int k);
+const char* rfk_flame_param_name(const rfk_flame* f, int xform, int k);
+int rfk_flame_get_variation(const rfk_flame* f, int xform, const char* name, float* out);
+int rfk_flame_set_variation(rfk_flame* f, int xform, const char* name, float value); /* existing names only: structure is fixed after load */
+int rfk_flame_get_param(const rfk_flame* f, int xform, const char* name, float* out);
+int rfk_flame_set_param(rfk_flame* f, int xform, const char* name, float value);
+int rfk_flame_get_palette(const rfk_flame* f, float* rgba_256x4);
+int rfk_flame_set_palette(rfk_flame* f, const float* rgba_256x4);
+
+/* ---- flame: parameter buffer and generated code ---- */
+const char* rfk_flame_buffer_map_json(const rfk_flame* f); /* buffer_map_.dump(), src/flame.hpp:130-132 */
+int rfk_flame_copy_params(const rfk_flame* f, float* out_1024); /* copy_flame_data_to_buffer, src/flame.cpp:73-103 */
+const char* rfk_flame_glsl_source(const rfk_flame* f); /* flame_compiler::compile_flame_xforms, variation_table.cpp:217-265 */
+const char* rfk_flame_cuda_source(const rfk_flame* f); /* the translation unit handed to NVRTC */
+/* sm_100a cubin of the generated kernels; *size receives the byte count, buf may be NULL to query. Needs no GPU. */
+int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size);
+
+/* Options of the generated kernels (no reference counterpart). Changing them rebuilds the module. */
+typedef struct rfk_kernel_options {
+    int32_t fast_math;      /* SFU intrinsics (--use_fast_math); default 0: 1-2 ulp library functions */
+    int32_t fmad;           /* FMA contraction; default 1 */
+    int32_t per_lane_xform; /* 1: every particle picks its own xform (divergent). default 0: one pick per warp + on-chip re-deal */
+    int32_t warp_aggregate; /* 1: match_any de-duplication of same-bin updates inside a warp */
+    int32_t deterministic;  /* 1: fixed-point integer accumulation, bit-identical histograms run to run */
+    int32_t count_xforms;   /* 1: count xform selections (rfk_flame_xform_counts) */
+    int32_t min_blocks;     /* __launch_bounds__ minBlocksPerSM, 0 = unset */
+} rfk_kernel_options;
+int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* out);
+int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* in);
+/* registers / static shared memory / resident CTAs per SM of "rfk_warm" or "rfk_draw" */
+int rfk_flame_kernel_info(rfk_flame* f, const char* kernel, int* regs, int* smem_bytes, int* blocks_per_sm);
+
+/* ---- flame: run. src/flame.hpp:86-89 ---- */
+int rfk_flame_needs_warmup(const rfk_flame* f); /* flame::needs_warmup, :86 */
+/* flame::warmup, src/flame.cpp:228-281: uploads the current field values, builds the per-temporal-sample
+ * parameter blocks (animate.tpl.glsl), re-seeds the particles from the Hammersley set and runs one first-run
+ * pass plus num_passes undrawn iterations. Does not clear any histogram. */
+int rfk_flame_warmup(rfk_flame* f, size_t num_passes, float tss_width);
+/* flame::draw_to_bins, src/flame.cpp:283-330: num_iter iterations of every particle, accumulated in place into
+ * the caller's histogram bins_dev (bins_len float4 = RGB + density; height = bins_len / bins_width, :290).
+ * Returns the number of samples binned by this call, or a negative code. Blocks on the counter read-back. */
+int64_t rfk_flame_draw_to_bins(rfk_flame* f, float* bins_dev, size_t bins_len, size_t bins_width, int num_iter);
+/* Same without the read-back; rfk_flame_binned_total() returns the count since the last warmup. */
+int rfk_flame_draw_to_bins_async(rfk_flame* f, float* bins_dev, size_t bins_len, size_t bins_width, int num_iter);
+int64_t rfk_flame_binned_total(rfk_flame* f);
+int rfk_flame_reset_animation(rfk_flame* f); /* flame::reset_animation, src/flame.hpp:95 */
+/* per-xform selection counts since the last warmup (count_xforms option); the reference's read-out is
+ * src/main.cpp:595-611 */
+int rfk_flame_xform_counts(rfk_flame* f, uint64_t* out, int n);
+/* screen-space affine of draw_to_bins, src/flame.cpp:289-296 */
+int rfk_flame_screen_affine(const rfk_flame* f, size_t bins_width, size_t bins_height, float out[6]);
+/* per-frame animation step of the main loop, src/main.cpp:383-395: rotates every xform with a non-zero
+ * rotation_frequency by degrees * rotation_frequency */
+int rfk_flame_rotate_xforms(rfk_flame* f, float degrees);
+
+/* ---- affine helpers: flame::rotate_affine / scale_affine / translate_affine, src/flame.hpp:97-128 ---- */
+void rfk_rotate_affine(const float a[6], float deg, float out[6]);
+void rfk_scale_affine(const float a[6], float scale, float out[6]);
+void rfk_translate_affine(const float a[6], const float t[2], float out[6]);
+
+/* ---- density estimation + tonemap: the block inlined at src/main.cpp:490-535 ----
+ * estimator_radius is clamped to 100 (main.cpp:502); scale_constant is 10^-exponent with exponent 4 in the
+ * reference (main.cpp:228, :528). Images are row-major, row 0 = screen row 0 (= PNG row 0). */
+typedef struct rfk_post_params {
+    int32_t estimator_radius, estimator_min;
+    float estimator_curve;
+    float gamma, brightness, vibrancy;
+    float scale_constant;
+} rfk_post_params;
+int rfk_flame_post_params(const rfk_flame* f, rfk_post_params* out); /* the uniforms main.cpp:502-509, :526-531 would set */
+/* density_vert.glsl + density_frag.glsl, main.cpp:490-515: histogram -> float4 image */
+int rfk_density_estimate(const float* bins_dev, float* image_dev, size_t width, size_t height, const rfk_post_params* p);
+/* tonemap.glsl, main.cpp:522-535: float4 image -> float4 image (alpha = 1); rgba8_dev optional */
+int rfk_tonemap(const float* image_in_dev, float* image_out_dev, uint8_t* rgba8_dev, size_t width, size_t height, const rfk_post_params* p);
+/* both in one kernel; either output may be NULL */
+int rfk_density_tonemap(const float* bins_dev, float* image_out_dev, uint8_t* rgba8_dev, size_t width, size_t height, const rfk_post_params* p);
+/* 2x2 box average of a float4 image: out is out_width x out_height, in is twice that in each dimension */
+int rfk_downsample2x(const float* image_in_dev, float* image_out_dev, size_t out_width, size_t out_height);
+
+/* ---- seeding kernels (src/flame.cpp:105-158 moved to the device) ---- */
+int rfk_seed_rng_states(uint32_t* states_dev, size_t count, uint32_t seed_base); /* jsf32::warmup_ctx, src/util.hpp:90-95 */
+int rfk_make_sample_points(float* points_dev, uint32_t count);                   /* make_sample_points, src/hammersley.cpp:29-48 */
+int rfk_make_shuffle_buffers(uint32_t* out_dev, uint32_t size, uint32_t count, uint64_t seed); /* src/shuffle_buffers.cpp:9-52 */
+int rfk_copy_rng_states(uint32_t* out, size_t first, size_t count); /* the global states, to host */
+
+/* ---- end to end with host buffers: what one iteration of the main loop does for a still
+ * (src/main.cpp:403-535): warmup, draw_to_bins until `target_binned` samples are in the histogram
+ * (the `accumulated < quality * W * H` rule of :411), density estimation, tonemap, read-back
+ * (texture::get_pixels, src/buffer_objects.hpp:113-119). The histogram lives in library-owned
+ * device memory. ---- */
+typedef struct rfk_frame_request {
+    uint32_t width, height;    /* histogram = image size (supersampling 1, main.cpp:195) */
+    uint32_t warmup_passes;    /* 16, main.cpp:263 */
+    uint32_t drawing_passes;   /* iterations per draw_to_bins call: 128, main.cpp:264 */
+    float tss_width;           /* 1.2/60, main.cpp:237 */
+    uint64_t target_binned;    /* stop once this many samples are binned (quality * W * H, main.cpp:411); 0 = use max_draw_calls only */
+    uint32_t max_draw_calls;   /* upper bound on draw_to_bins calls; 0 = unlimited */
+    float scale_constant_exp;  /* 4, main.cpp:228 */
+} rfk_frame_request;
+typedef struct rfk_frame_stats {
+    uint64_t iterations;   /* chaos-game iterations run (warmup excluded) */
+    uint64_t binned;       /* samples that landed in the histogram */
+    uint32_t draw_calls;
+    float ms_warmup, ms_draw, ms_post, ms_readback; /* CUDA-event times of the stages */
+} rfk_frame_stats;
+int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_out, float* image_out /* optional float4 */,
+                     rfk_frame_stats* stats);
+
+/* ---- test hooks: the generated device functions on host-supplied vectors ---- */
+/* one dispatch(v, xid) per element (variation_table.cpp:222-263). xyz: n x 3 in, xid: n, rng: n x 4 in/out,
+ * fp: 1024 floats or NULL for the flame's current values, out: n x 4 (x, y, colour, opacity) */
+int rfk_flame_single_step(rfk_flame* f, int n, const float* xyz, const int* xid, uint32_t* rng, const float* fp, int first_run, float* out);
+/* get_xform_id(ratio) per element (xform_select.tpl.glsl) */
+int rfk_flame_select_xform(rfk_flame* f, int n, const float* ratio, const float* fp, int* out);
+/* flame.glsl:78-84 per element: xyzw n x 4 (x, y, colour, opacity) -> bin index (-1 = rejected) and palette index */
+int rfk_flame_bucket_index(rfk_flame* f, int n, const float* xyzw, const float ss_affine[6], int width, int height, int* idx_out, int* palette_out);
+/* animate.tpl.glsl: the temporal_samples x param_count blocks, to host */
+int rfk_flame_animate(rfk_flame* f, float tss_width, int temporal_samples, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REFRAKT_B200_H */

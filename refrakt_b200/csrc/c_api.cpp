@@ -1,0 +1,622 @@
+// extern "C" surface of include/refrakt_b200.h over the C++ host classes.
+#include "../../include/refrakt_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "flame.hpp"
+#include "flame_device.hpp"
+#include "static_kernels.cuh"
+#include "textutil.hpp"
+#include "variation_table.hpp"
+
+using namespace rfk;
+
+namespace {
+
+thread_local std::string t_error;
+thread_local std::string t_scratch;
+
+int fail(int code, const std::string& msg) {
+    t_error = msg;
+    return code;
+}
+
+template <typename F>
+int guarded(F&& body) {
+    try {
+        return (int)body();
+    } catch (const std::invalid_argument& e) {
+        return fail(RFK_E_INVALID, e.what());
+    } catch (const std::out_of_range& e) {
+        return fail(RFK_E_NOTFOUND, e.what());
+    } catch (const std::exception& e) {
+        return fail(RFK_E_CUDA, e.what());
+    }
+}
+
+flame* F(rfk_flame* f) { return reinterpret_cast<flame*>(f); }
+const flame* F(const rfk_flame* f) { return reinterpret_cast<const flame*>(f); }
+flame_compiler* C(rfk_compiler* c) { return reinterpret_cast<flame_compiler*>(c); }
+const flame_compiler* C(const rfk_compiler* c) { return reinterpret_cast<const flame_compiler*>(c); }
+
+void cuda_ok(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+flame_xform* xform_at(flame* f, int index) {
+    if (index == -1) return f->final_xform ? &f->final_xform.value() : nullptr;
+    if (index < 0 || index >= (int)f->xforms.size()) return nullptr;
+    return &f->xforms[index];
+}
+const flame_xform* xform_at(const flame* f, int index) { return xform_at(const_cast<flame*>(f), index); }
+
+kernels::density_params to_density(const rfk_post_params& p, size_t W, size_t H) {
+    kernels::density_params d{};
+    d.W = (int)W;
+    d.H = (int)H;
+    d.estimator_radius = p.estimator_radius > 100 ? 100 : (p.estimator_radius < 0 ? 0 : p.estimator_radius);  // main.cpp:502
+    d.estimator_min = p.estimator_min < 0 ? 0 : p.estimator_min;
+    d.estimator_curve = p.estimator_curve;
+    d.gamma = p.gamma;
+    d.brightness = p.brightness;
+    d.vibrancy = p.vibrancy;
+    d.scale_constant = p.scale_constant;
+    return d;
+}
+
+// thresholds table lives on the device for the duration of one call
+struct threshold_table {
+    float* dev = nullptr;
+    explicit threshold_table(const kernels::density_params& d) {
+        const int R = d.estimator_radius > d.estimator_min ? d.estimator_radius : d.estimator_min;
+        std::vector<float> host(R + 2, 0.0f);
+        kernels::density_thresholds(host.data(), d.estimator_radius, d.estimator_min, d.estimator_curve);
+        cuda_ok(cudaMalloc(&dev, host.size() * sizeof(float)), "cudaMalloc(thresholds)");
+        cuda_ok(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, current_stream()), "upload thresholds");
+        cuda_ok(cudaStreamSynchronize(current_stream()), "upload thresholds");
+    }
+    ~threshold_table() { cudaFree(dev); }
+};
+
+int run_post(const float* in, float* out_f4, uint8_t* out_rgba8, size_t W, size_t H, const rfk_post_params* p, bool density, bool tonemap) {
+    if (!in || !p || W == 0 || H == 0 || W > 0x3fffffff || H > 0x3fffffff) throw std::invalid_argument("post: bad image arguments");
+    if (!out_f4 && !out_rgba8) throw std::invalid_argument("post: no output buffer");
+    auto d = to_density(*p, W, H);
+    threshold_table t(d);
+    kernels::density_tonemap(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out_f4), reinterpret_cast<uchar4*>(out_rgba8), d, t.dev, density, tonemap, current_stream());
+    count_launch(1);
+    cuda_ok(cudaGetLastError(), "density_tonemap launch");
+    cuda_ok(cudaStreamSynchronize(current_stream()), "density_tonemap");
+    return RFK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rfk_abi_version(void) { return RFK_ABI_VERSION; }
+const char* rfk_last_error(void) { return t_error.c_str(); }
+
+int rfk_set_device(int ordinal) {
+    return guarded([&]() -> int { cuda_ok(cudaSetDevice(ordinal), "cudaSetDevice"); return RFK_OK; });
+}
+int rfk_set_stream(void* cuda_stream) { set_current_stream(reinterpret_cast<cudaStream_t>(cuda_stream)); return RFK_OK; }
+int rfk_synchronize(void) {
+    return guarded([&]() -> int { cuda_ok(cudaStreamSynchronize(current_stream()), "cudaStreamSynchronize"); return RFK_OK; });
+}
+void* rfk_device_alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(RFK_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+int rfk_device_free(void* p) {
+    return guarded([&]() -> int { cuda_ok(cudaFree(p), "cudaFree"); return RFK_OK; });
+}
+int rfk_device_zero(void* p, size_t bytes) {
+    return guarded([&]() -> int { cuda_ok(cudaMemsetAsync(p, 0, bytes, current_stream()), "cudaMemsetAsync"); return RFK_OK; });
+}
+int rfk_memcpy_to_device(void* dst, const void* src, size_t bytes) {
+    return guarded([&]() -> int {
+        cuda_ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, current_stream()), "cudaMemcpy H2D");
+        cuda_ok(cudaStreamSynchronize(current_stream()), "cudaMemcpy H2D");
+        return RFK_OK;
+    });
+}
+int rfk_memcpy_to_host(void* dst, const void* src, size_t bytes) {
+    return guarded([&]() -> int {
+        cuda_ok(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, current_stream()), "cudaMemcpy D2H");
+        cuda_ok(cudaStreamSynchronize(current_stream()), "cudaMemcpy D2H");
+        return RFK_OK;
+    });
+}
+uint64_t rfk_kernel_launch_count(void) { return kernel_launch_count(); }
+
+int rfk_set_sim_parameters(size_t total_particles, size_t temporal_samples, size_t shuffle_count, uint64_t seed) {
+    return guarded([&]() -> int { flame::set_sim_parameters(total_particles, temporal_samples, shuffle_count, seed); return RFK_OK; });
+}
+
+// ---- compiler ----
+rfk_compiler* rfk_compiler_create(const char* path) {
+    try {
+        if (!path) throw std::invalid_argument("rfk_compiler_create: null path");
+        return reinterpret_cast<rfk_compiler*>(new flame_compiler(path));
+    } catch (const std::exception& e) { fail(RFK_E_INVALID, e.what()); return nullptr; }
+}
+rfk_compiler* rfk_compiler_create_from_text(const char* text) {
+    try {
+        if (!text) throw std::invalid_argument("rfk_compiler_create_from_text: null text");
+        return reinterpret_cast<rfk_compiler*>(new flame_compiler(flame_compiler::from_text(text)));
+    } catch (const std::exception& e) { fail(RFK_E_INVALID, e.what()); return nullptr; }
+}
+int rfk_compiler_load_overlay(rfk_compiler* c, const char* path) {
+    return guarded([&]() -> int {
+        if (!c || !path) throw std::invalid_argument("rfk_compiler_load_overlay: null argument");
+        bool ok = false;
+        std::string text = read_file(path, &ok);
+        if (!ok) throw std::invalid_argument(std::string("cannot read ") + path);
+        C(c)->load_overlay_text(text);
+        return RFK_OK;
+    });
+}
+void rfk_compiler_destroy(rfk_compiler* c) { delete C(c); }
+int rfk_compiler_is_param(const rfk_compiler* c, const char* n) { return c && n && C(c)->is_param(n); }
+int rfk_compiler_is_variation(const rfk_compiler* c, const char* n) { return c && n && C(c)->is_variation(n); }
+int rfk_compiler_is_common(const rfk_compiler* c, const char* n) { return c && n && C(c)->is_common(n); }
+int rfk_compiler_variation_count(const rfk_compiler* c) { return c ? (int)C(c)->variations().size() : 0; }
+const char* rfk_compiler_variation_name(const rfk_compiler* c, int index) {
+    if (!c || index < 0 || index >= (int)C(c)->variations().size()) return nullptr;
+    auto it = C(c)->variations().begin();
+    std::advance(it, index);
+    return it->first.c_str();
+}
+int rfk_compiler_get_parameters_for_variation(const rfk_compiler* c, const char* name, char* buf, size_t buf_len) {
+    return guarded([&]() -> int {
+        if (!c || !name) throw std::invalid_argument("null argument");
+        if (!C(c)->is_variation(name)) return fail(RFK_E_NOTFOUND, std::string("unknown variation ") + name);
+        const auto& params = C(c)->get_parameters_for_variation(name);
+        std::string joined;
+        for (size_t i = 0; i < params.size(); i++) joined += (i ? "\n" : "") + params[i];
+        if (buf && buf_len) {
+            std::strncpy(buf, joined.c_str(), buf_len - 1);
+            buf[buf_len - 1] = '\0';
+        }
+        return (int)params.size();
+    });
+}
+const char* rfk_compiler_param_owner(const rfk_compiler* c, const char* param) {
+    if (!c || !param || !C(c)->is_param(param)) return nullptr;
+    t_scratch = C(c)->param_owner(param);
+    return t_scratch.c_str();
+}
+
+// ---- flame ----
+rfk_flame* rfk_flame_load(const char* path, const rfk_compiler* c) {
+    if (!path || !c) { fail(RFK_E_INVALID, "rfk_flame_load: null argument"); return nullptr; }
+    try {
+        auto f = flame::load_flame(path, *C(c));
+        if (!f) { fail(RFK_E_INVALID, flame::last_error()); return nullptr; }
+        return reinterpret_cast<rfk_flame*>(f.release());
+    } catch (const std::exception& e) { fail(RFK_E_INVALID, e.what()); return nullptr; }
+}
+rfk_flame* rfk_flame_load_string(const char* xml_text, const rfk_compiler* c) {
+    if (!xml_text || !c) { fail(RFK_E_INVALID, "rfk_flame_load_string: null argument"); return nullptr; }
+    try {
+        auto f = flame::load_flame_string(xml_text, "<string>", *C(c));
+        if (!f) { fail(RFK_E_INVALID, flame::last_error()); return nullptr; }
+        return reinterpret_cast<rfk_flame*>(f.release());
+    } catch (const std::exception& e) { fail(RFK_E_INVALID, e.what()); return nullptr; }
+}
+void rfk_flame_destroy(rfk_flame* f) { delete F(f); }
+
+int rfk_flame_get_info(const rfk_flame* f, rfk_flame_info* o) {
+    if (!f || !o) return fail(RFK_E_INVALID, "null argument");
+    const flame* fl = F(f);
+    o->size[0] = fl->size[0]; o->size[1] = fl->size[1];
+    o->center[0] = fl->center[0]; o->center[1] = fl->center[1];
+    o->scale = fl->scale; o->rotate = fl->rotate;
+    o->estimator_min = fl->estimator_min; o->estimator_radius = fl->estimator_radius; o->estimator_curve = fl->estimator_curve;
+    o->gamma = fl->gamma; o->vibrancy = fl->vibrancy; o->brightness = fl->brightness;
+    o->num_xforms = (int)fl->xforms.size();
+    o->has_final_xform = fl->final_xform ? 1 : 0;
+    o->param_count = fl->buffer_map().size;
+    return RFK_OK;
+}
+int rfk_flame_set_info(rfk_flame* f, const rfk_flame_info* i) {
+    if (!f || !i) return fail(RFK_E_INVALID, "null argument");
+    flame* fl = F(f);
+    fl->size = {i->size[0], i->size[1]};
+    fl->center = {i->center[0], i->center[1]};
+    fl->scale = i->scale; fl->rotate = i->rotate;
+    fl->estimator_min = i->estimator_min; fl->estimator_radius = i->estimator_radius; fl->estimator_curve = i->estimator_curve;
+    fl->gamma = i->gamma; fl->vibrancy = i->vibrancy; fl->brightness = i->brightness;
+    return RFK_OK;  // none of these feed the particle state: no re-warmup (main.cpp:324-333)
+}
+int rfk_flame_get_xform(const rfk_flame* f, int index, rfk_xform_info* o) {
+    if (!f || !o) return fail(RFK_E_INVALID, "null argument");
+    const flame_xform* x = xform_at(F(f), index);
+    if (!x) return fail(RFK_E_NOTFOUND, "no xform " + std::to_string(index));
+    for (int k = 0; k < 6; k++) { o->affine[k] = x->affine[k]; o->post[k] = x->post ? (*x->post)[k] : 0.0f; }
+    o->has_post = x->post ? 1 : 0;
+    o->weight = x->weight; o->color = x->color; o->color_speed = x->color_speed;
+    o->rotation_frequency = x->rotation_frequency; o->opacity = x->opacity;
+    o->num_variations = (int)x->variations.size();
+    o->num_params = (int)x->var_param.size();
+    return RFK_OK;
+}
+int rfk_flame_set_xform(rfk_flame* f, int index, const rfk_xform_info* i) {
+    if (!f || !i) return fail(RFK_E_INVALID, "null argument");
+    flame_xform* x = xform_at(F(f), index);
+    if (!x) return fail(RFK_E_NOTFOUND, "no xform " + std::to_string(index));
+    if ((i->has_post != 0) != x->post.has_value()) return fail(RFK_E_INVALID, "has_post cannot change after load (the generated kernel depends on it)");
+    for (int k = 0; k < 6; k++) x->affine[k] = i->affine[k];
+    if (x->post) for (int k = 0; k < 6; k++) (*x->post)[k] = i->post[k];
+    x->weight = i->weight; x->color = i->color; x->color_speed = i->color_speed;
+    x->rotation_frequency = i->rotation_frequency; x->opacity = i->opacity;
+    F(f)->mark_dirty();
+    return RFK_OK;
+}
+static const char* nth_key(const std::map<std::string, float>& m, int k) {
+    if (k < 0 || k >= (int)m.size()) return nullptr;
+    auto it = m.begin();
+    std::advance(it, k);
+    return it->first.c_str();
+}
+const char* rfk_flame_variation_name(const rfk_flame* f, int xform, int k) {
+    const flame_xform* x = f ? xform_at(F(f), xform) : nullptr;
+    return x ? nth_key(x->variations, k) : nullptr;
+}
+const char* rfk_flame_param_name(const rfk_flame* f, int xform, int k) {
+    const flame_xform* x = f ? xform_at(F(f), xform) : nullptr;
+    return x ? nth_key(x->var_param, k) : nullptr;
+}
+static int map_get(const std::map<std::string, float>& m, const char* name, float* out) {
+    auto it = m.find(name);
+    if (it == m.end()) return fail(RFK_E_NOTFOUND, std::string("no entry named ") + name);
+    *out = it->second;
+    return RFK_OK;
+}
+static int map_set(std::map<std::string, float>& m, const char* name, float v) {
+    auto it = m.find(name);
+    if (it == m.end()) return fail(RFK_E_NOTFOUND, std::string("no entry named ") + name + " (the structure of a flame is fixed after load)");
+    it->second = v;
+    return RFK_OK;
+}
+int rfk_flame_get_variation(const rfk_flame* f, int xform, const char* name, float* out) {
+    const flame_xform* x = (f && name && out) ? xform_at(F(f), xform) : nullptr;
+    return x ? map_get(x->variations, name, out) : fail(RFK_E_NOTFOUND, "no such xform");
+}
+int rfk_flame_set_variation(rfk_flame* f, int xform, const char* name, float v) {
+    flame_xform* x = (f && name) ? xform_at(F(f), xform) : nullptr;
+    if (!x) return fail(RFK_E_NOTFOUND, "no such xform");
+    int r = map_set(x->variations, name, v);
+    if (r == RFK_OK) F(f)->mark_dirty();
+    return r;
+}
+int rfk_flame_get_param(const rfk_flame* f, int xform, const char* name, float* out) {
+    const flame_xform* x = (f && name && out) ? xform_at(F(f), xform) : nullptr;
+    return x ? map_get(x->var_param, name, out) : fail(RFK_E_NOTFOUND, "no such xform");
+}
+int rfk_flame_set_param(rfk_flame* f, int xform, const char* name, float v) {
+    flame_xform* x = (f && name) ? xform_at(F(f), xform) : nullptr;
+    if (!x) return fail(RFK_E_NOTFOUND, "no such xform");
+    int r = map_set(x->var_param, name, v);
+    if (r == RFK_OK) F(f)->mark_dirty();
+    return r;
+}
+int rfk_flame_get_palette(const rfk_flame* f, float* rgba) {
+    if (!f || !rgba) return fail(RFK_E_INVALID, "null argument");
+    std::memcpy(rgba, F(f)->palette.data(), 256 * 4 * sizeof(float));
+    return RFK_OK;
+}
+int rfk_flame_set_palette(rfk_flame* f, const float* rgba) {
+    if (!f || !rgba) return fail(RFK_E_INVALID, "null argument");
+    std::memcpy(F(f)->palette.data(), rgba, 256 * 4 * sizeof(float));
+    F(f)->mark_dirty();
+    return RFK_OK;
+}
+
+const char* rfk_flame_buffer_map_json(const rfk_flame* f) {
+    if (!f) return nullptr;
+    t_scratch = F(f)->buffer_map().dump_json();
+    return t_scratch.c_str();
+}
+int rfk_flame_copy_params(const rfk_flame* f, float* out) {
+    if (!f || !out) return fail(RFK_E_INVALID, "null argument");
+    auto buf = F(f)->copy_flame_data_to_buffer();
+    std::memcpy(out, buf.data(), sizeof(float) * flame::PARAM_BUFFER);
+    return RFK_OK;
+}
+const char* rfk_flame_glsl_source(const rfk_flame* f) { return f ? F(f)->glsl_source().c_str() : nullptr; }
+const char* rfk_flame_cuda_source(const rfk_flame* f) { return f ? F(f)->cuda_source().c_str() : nullptr; }
+int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size) {
+    return guarded([&]() -> int {
+        if (!f || !size) throw std::invalid_argument("null argument");
+        const auto& image = F(f)->cubin();
+        *size = image.size();
+        if (buf) {
+            if (buf_len < image.size()) throw std::invalid_argument("cubin buffer too small");
+            std::memcpy(buf, image.data(), image.size());
+        }
+        return RFK_OK;
+    });
+}
+
+int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* o) {
+    if (!f || !o) return fail(RFK_E_INVALID, "null argument");
+    const auto& k = F(f)->options();
+    *o = rfk_kernel_options{k.fast_math, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks};
+    return RFK_OK;
+}
+int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
+    if (!f || !i) return fail(RFK_E_INVALID, "null argument");
+    kernel_options k;
+    k.fast_math = i->fast_math != 0; k.fmad = i->fmad != 0; k.per_lane_xform = i->per_lane_xform != 0;
+    k.warp_aggregate = i->warp_aggregate != 0; k.deterministic = i->deterministic != 0; k.count_xforms = i->count_xforms != 0;
+    k.min_blocks = i->min_blocks;
+    if (k.count_xforms && F(f)->xforms.size() > 62) return fail(RFK_E_INVALID, "count_xforms supports at most 62 xforms");
+    if (!F(f)->set_options(k)) return fail(RFK_E_CUDA, flame::last_error());
+    return RFK_OK;
+}
+int rfk_flame_kernel_info(rfk_flame* f, const char* kernel, int* regs, int* smem, int* blocks) {
+    return guarded([&]() -> int {
+        if (!f || !kernel || !regs || !smem || !blocks) throw std::invalid_argument("null argument");
+        flame_kernel_info(*F(f), kernel, regs, smem, blocks);
+        return RFK_OK;
+    });
+}
+
+int rfk_flame_needs_warmup(const rfk_flame* f) { return f ? (F(f)->needs_warmup() ? 1 : 0) : fail(RFK_E_INVALID, "null flame"); }
+int rfk_flame_warmup(rfk_flame* f, size_t num_passes, float tss_width) {
+    return guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        if (num_passes > 0x7fffffff) throw std::invalid_argument("too many passes");
+        F(f)->warmup(num_passes, tss_width);
+        return RFK_OK;
+    });
+}
+int64_t rfk_flame_draw_to_bins(rfk_flame* f, float* bins, size_t bins_len, size_t bins_width, int num_iter) {
+    int64_t result = 0;
+    int rc = guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        if (num_iter < 0) throw std::invalid_argument("negative iteration count");
+        if (F(f)->needs_warmup()) return fail(RFK_E_STATE, "draw_to_bins: warmup() has not been run for the current parameters");
+        result = (int64_t)F(f)->draw_to_bins(bins, bins_len, bins_width, num_iter);
+        return RFK_OK;
+    });
+    return rc == RFK_OK ? result : rc;
+}
+int rfk_flame_draw_to_bins_async(rfk_flame* f, float* bins, size_t bins_len, size_t bins_width, int num_iter) {
+    return guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        if (num_iter < 0) throw std::invalid_argument("negative iteration count");
+        if (F(f)->needs_warmup()) return fail(RFK_E_STATE, "draw_to_bins: warmup() has not been run for the current parameters");
+        F(f)->draw_to_bins_async(bins, bins_len, bins_width, num_iter);
+        return RFK_OK;
+    });
+}
+int64_t rfk_flame_binned_total(rfk_flame* f) {
+    int64_t result = 0;
+    int rc = guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        result = (int64_t)F(f)->binned_total();
+        return RFK_OK;
+    });
+    return rc == RFK_OK ? result : rc;
+}
+int rfk_flame_reset_animation(rfk_flame* f) {
+    if (!f) return fail(RFK_E_INVALID, "null flame");
+    F(f)->reset_animation();
+    return RFK_OK;
+}
+int rfk_flame_xform_counts(rfk_flame* f, uint64_t* out, int n) {
+    return guarded([&]() -> int {
+        if (!f || !out || n < 0 || n > 62) throw std::invalid_argument("bad argument");
+        unsigned long long raw[64] = {0};
+        flame_read_counters(*F(f), raw, 64);
+        for (int i = 0; i < n; i++) out[i] = raw[1 + i];
+        return RFK_OK;
+    });
+}
+int rfk_flame_screen_affine(const rfk_flame* f, size_t W, size_t H, float out[6]) {
+    if (!f || !out) return fail(RFK_E_INVALID, "null argument");
+    auto a = F(f)->screen_space_affine(W, H);
+    for (int i = 0; i < 6; i++) out[i] = a[i];
+    return RFK_OK;
+}
+int rfk_flame_rotate_xforms(rfk_flame* f, float degrees) {
+    if (!f) return fail(RFK_E_INVALID, "null flame");
+    flame* fl = F(f);
+    for (auto& x : fl->xforms)
+        if (x.rotation_frequency != 0.0f) x.affine = flame::rotate_affine(x.affine, degrees * x.rotation_frequency);
+    if (fl->final_xform) {
+        auto& fx = fl->final_xform.value();
+        if (fx.rotation_frequency != 0.0f) fx.affine = flame::rotate_affine(fx.affine, degrees * fx.rotation_frequency);
+    }
+    fl->mark_dirty();
+    return RFK_OK;
+}
+
+void rfk_rotate_affine(const float a[6], float deg, float out[6]) {
+    flame_xform::affine_t in{a[0], a[1], a[2], a[3], a[4], a[5]};
+    auto r = flame::rotate_affine(in, deg);
+    for (int i = 0; i < 6; i++) out[i] = r[i];
+}
+void rfk_scale_affine(const float a[6], float scale, float out[6]) {
+    flame_xform::affine_t in{a[0], a[1], a[2], a[3], a[4], a[5]};
+    auto r = flame::scale_affine(in, scale);
+    for (int i = 0; i < 6; i++) out[i] = r[i];
+}
+void rfk_translate_affine(const float a[6], const float t[2], float out[6]) {
+    flame_xform::affine_t in{a[0], a[1], a[2], a[3], a[4], a[5]};
+    auto r = flame::translate_affine(in, {t[0], t[1]});
+    for (int i = 0; i < 6; i++) out[i] = r[i];
+}
+
+// ---- post ----
+int rfk_flame_post_params(const rfk_flame* f, rfk_post_params* o) {
+    if (!f || !o) return fail(RFK_E_INVALID, "null argument");
+    const flame* fl = F(f);
+    o->estimator_radius = fl->estimator_radius > 100 ? 100 : fl->estimator_radius;
+    o->estimator_min = fl->estimator_min;
+    o->estimator_curve = fl->estimator_curve;
+    o->gamma = fl->gamma; o->brightness = fl->brightness; o->vibrancy = fl->vibrancy;
+    o->scale_constant = (float)(1.0 / std::pow(10.0, 4.0));  // main.cpp:228, :528
+    return RFK_OK;
+}
+int rfk_density_estimate(const float* bins, float* image, size_t W, size_t H, const rfk_post_params* p) {
+    return guarded([&]() -> int { return run_post(bins, image, nullptr, W, H, p, true, false); });
+}
+int rfk_tonemap(const float* in, float* out, uint8_t* rgba8, size_t W, size_t H, const rfk_post_params* p) {
+    return guarded([&]() -> int { return run_post(in, out, rgba8, W, H, p, false, true); });
+}
+int rfk_density_tonemap(const float* bins, float* out, uint8_t* rgba8, size_t W, size_t H, const rfk_post_params* p) {
+    return guarded([&]() -> int { return run_post(bins, out, rgba8, W, H, p, true, true); });
+}
+int rfk_downsample2x(const float* in, float* out, size_t W, size_t H) {
+    return guarded([&]() -> int {
+        if (!in || !out || !W || !H) throw std::invalid_argument("bad argument");
+        kernels::downsample2x(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), (int)W, (int)H, current_stream());
+        count_launch(1);
+        cuda_ok(cudaGetLastError(), "downsample2x");
+        return RFK_OK;
+    });
+}
+
+// ---- seeding ----
+int rfk_seed_rng_states(uint32_t* states, size_t count, uint32_t seed_base) {
+    return guarded([&]() -> int {
+        if (!states) throw std::invalid_argument("null argument");
+        kernels::seed_rng_states(reinterpret_cast<uint4*>(states), count, seed_base, current_stream());
+        count_launch(1);
+        cuda_ok(cudaGetLastError(), "seed_rng_states");
+        return RFK_OK;
+    });
+}
+int rfk_make_sample_points(float* points, uint32_t count) {
+    return guarded([&]() -> int {
+        if (!points) throw std::invalid_argument("null argument");
+        kernels::make_sample_points(reinterpret_cast<float4*>(points), count, current_stream());
+        count_launch(1);
+        cuda_ok(cudaGetLastError(), "make_sample_points");
+        return RFK_OK;
+    });
+}
+int rfk_make_shuffle_buffers(uint32_t* out, uint32_t size, uint32_t count, uint64_t seed) {
+    return guarded([&]() -> int {
+        if (!out) throw std::invalid_argument("null argument");
+        kernels::make_shuffle_buffers(out, size, count, seed, current_stream());
+        count_launch(1);
+        cuda_ok(cudaGetLastError(), "make_shuffle_buffers");
+        return RFK_OK;
+    });
+}
+int rfk_copy_rng_states(uint32_t* out, size_t first, size_t count) {
+    return guarded([&]() -> int {
+        if (!out) throw std::invalid_argument("null argument");
+        if (!sim_rng_states() || first + count > sim_total_particles()) throw std::invalid_argument("range outside the particle RNG states");
+        cuda_ok(cudaMemcpyAsync(out, sim_rng_states() + first, count * sizeof(uint4), cudaMemcpyDeviceToHost, current_stream()), "copy rng states");
+        cuda_ok(cudaStreamSynchronize(current_stream()), "copy rng states");
+        return RFK_OK;
+    });
+}
+
+// ---- end to end ----
+int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_out, float* image_out, rfk_frame_stats* stats) {
+    return guarded([&]() -> int {
+        if (!f || !req || (!rgba8_out && !image_out)) throw std::invalid_argument("rfk_render_frame: null argument");
+        if (!req->width || !req->height) throw std::invalid_argument("rfk_render_frame: empty image");
+        if (!req->target_binned && !req->max_draw_calls) throw std::invalid_argument("rfk_render_frame: neither target_binned nor max_draw_calls given");
+        flame* fl = F(f);
+        const size_t W = req->width, H = req->height, n = W * H;
+        cudaStream_t s = current_stream();
+
+        struct buffers {
+            float4* bins = nullptr; float4* image = nullptr; uchar4* rgba8 = nullptr;
+            cudaEvent_t ev[5] = {};
+            ~buffers() { cudaFree(bins); cudaFree(image); cudaFree(rgba8); for (auto e : ev) if (e) cudaEventDestroy(e); }
+        } b;
+        cuda_ok(cudaMalloc(&b.bins, n * sizeof(float4)), "cudaMalloc(bins)");
+        if (image_out) cuda_ok(cudaMalloc(&b.image, n * sizeof(float4)), "cudaMalloc(image)");
+        if (rgba8_out) cuda_ok(cudaMalloc(&b.rgba8, n * sizeof(uchar4)), "cudaMalloc(rgba8)");
+        for (auto& e : b.ev) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
+
+        cuda_ok(cudaEventRecord(b.ev[0], s), "event");
+        fl->warmup(req->warmup_passes, req->tss_width);
+        cuda_ok(cudaMemsetAsync(b.bins, 0, n * sizeof(float4), s), "clear bins");  // bins.zero_out(), main.cpp:406
+        cuda_ok(cudaEventRecord(b.ev[1], s), "event");
+
+        uint64_t binned = 0, iterations = 0;
+        uint32_t calls = 0;
+        while ((req->max_draw_calls == 0 || calls < req->max_draw_calls) && (req->target_binned == 0 || binned < req->target_binned)) {
+            size_t got = fl->draw_to_bins(reinterpret_cast<float*>(b.bins), n, W, (int)req->drawing_passes);
+            binned += got;
+            iterations += (uint64_t)req->drawing_passes * sim_total_particles();
+            calls++;
+            if (req->target_binned && got == 0 && calls >= 4 && binned == 0) throw std::runtime_error("rfk_render_frame: nothing lands in the histogram");
+        }
+        cuda_ok(cudaEventRecord(b.ev[2], s), "event");
+
+        rfk_post_params pp;
+        rfk_flame_post_params(f, &pp);
+        pp.scale_constant = (float)(1.0 / std::pow(10.0, (double)req->scale_constant_exp));
+        auto d = to_density(pp, W, H);
+        threshold_table t(d);
+        kernels::density_tonemap(b.bins, b.image, b.rgba8, d, t.dev, true, true, s);
+        count_launch(1);
+        cuda_ok(cudaGetLastError(), "density_tonemap launch");
+        cuda_ok(cudaEventRecord(b.ev[3], s), "event");
+        if (rgba8_out) cuda_ok(cudaMemcpyAsync(rgba8_out, b.rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, s), "read back rgba8");
+        if (image_out) cuda_ok(cudaMemcpyAsync(image_out, b.image, n * sizeof(float4), cudaMemcpyDeviceToHost, s), "read back image");
+        cuda_ok(cudaEventRecord(b.ev[4], s), "event");
+        cuda_ok(cudaStreamSynchronize(s), "rfk_render_frame");
+        if (stats) {
+            stats->iterations = iterations; stats->binned = binned; stats->draw_calls = calls;
+            cudaEventElapsedTime(&stats->ms_warmup, b.ev[0], b.ev[1]);
+            cudaEventElapsedTime(&stats->ms_draw, b.ev[1], b.ev[2]);
+            cudaEventElapsedTime(&stats->ms_post, b.ev[2], b.ev[3]);
+            cudaEventElapsedTime(&stats->ms_readback, b.ev[3], b.ev[4]);
+        }
+        return RFK_OK;
+    });
+}
+
+// ---- test hooks ----
+int rfk_flame_single_step(rfk_flame* f, int n, const float* xyz, const int* xid, uint32_t* rng, const float* fp, int first_run, float* out) {
+    return guarded([&]() -> int {
+        if (!f || n < 0 || (n && (!xyz || !xid || !rng || !out))) throw std::invalid_argument("rfk_flame_single_step: bad argument");
+        if (n == 0) return RFK_OK;
+        flame_single_step(*F(f), n, xyz, xid, rng, fp, first_run, out);
+        return RFK_OK;
+    });
+}
+int rfk_flame_select_xform(rfk_flame* f, int n, const float* ratio, const float* fp, int* out) {
+    return guarded([&]() -> int {
+        if (!f || n < 0 || (n && (!ratio || !out))) throw std::invalid_argument("rfk_flame_select_xform: bad argument");
+        if (n == 0) return RFK_OK;
+        flame_select_xform(*F(f), n, ratio, fp, out);
+        return RFK_OK;
+    });
+}
+int rfk_flame_bucket_index(rfk_flame* f, int n, const float* xyzw, const float ss[6], int W, int H, int* idx, int* pal) {
+    return guarded([&]() -> int {
+        if (!f || n < 0 || !ss || W <= 0 || H <= 0 || (n && (!xyzw || !idx || !pal))) throw std::invalid_argument("rfk_flame_bucket_index: bad argument");
+        if (n == 0) return RFK_OK;
+        flame_bucket_index(*F(f), n, xyzw, ss, W, H, idx, pal);
+        return RFK_OK;
+    });
+}
+int rfk_flame_animate(rfk_flame* f, float tss_width, int temporal_samples, float* out) {
+    return guarded([&]() -> int {
+        if (!f || !out || temporal_samples <= 0) throw std::invalid_argument("rfk_flame_animate: bad argument");
+        flame_animate_host(*F(f), tss_width, temporal_samples, out);
+        return RFK_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// Chaos-game kernels for one genome (sm_100a, compiled by NVRTC together with the
+// generated dispatch()/get_xform_id()). Replaces shaders/flame.glsl:41-90 and the
+// per-pass dispatch loops of src/flame.cpp:252-280 and :317-325.
+//
+// The reference runs ONE iteration per dispatch and moves the particle, its RNG
+// state, two shuffle indices and a histogram read-modify-write through global memory
+// every time (~104 B per iteration). Here a thread keeps its particle and its RNG in
+// registers for all `num_iter` iterations of a call; HBM sees one float4 + one uint4
+// load and store per particle per call, plus the histogram reductions.
+//
+// Divergence: the reference picks one xform per 256-thread workgroup per pass and
+// relies on its shuffle-buffer permutations to mix particles between workgroups.
+// Same idea at warp granularity: lane 0 of every warp draws the xform for the warp
+// (no divergence inside dispatch()), and after every iteration the CTA re-deals its
+// particles across warps through shared memory with a fresh bijection of [0, BLOCK),
+// computed on chip (the shuffle buffers of src/shuffle_buffers.cpp, moved on chip).
+//
+// Expects these macros from the host (flame_device.cpp): RFK_BLOCK, RFK_LOG2_BLOCK,
+// RFK_TOTAL_PARAMS, RFK_NUM_XFORMS, RFK_HAS_FINAL, RFK_LAUNCH_BOUNDS and the
+// option macros RFK_PER_LANE_XFORM, RFK_WARP_AGGREGATE, RFK_DETERMINISTIC,
+// RFK_COUNT_XFORMS (each 0 or 1).
+
+using namespace rfk_glsl;
+
+struct rfk_iter_params {
+    float4* particles;                  // [P] (x, y, colour, 0): pos_in/pos_out of buffers.glsl:1-9
+    uint4* rng;                         // [P] JSF32 state per thread slot (random.glsl:1-4)
+    const float* fp_inflated;           // [TS * RFK_TOTAL_PARAMS] (buffers.glsl:26-29)
+    const float4* palette;              // [256] (buffers.glsl:16-19)
+    float4* bins;                       // [W * H] RGB + density (buffers.glsl:21-24)
+    unsigned long long* fixed_bins;     // [W * H * 4] fixed-point accumulators (deterministic mode)
+    unsigned long long* counters;       // [0] binned samples (buffers.glsl:31-34), [1 + i] picks of xform i
+    float ss_affine[6];                 // flame.glsl:22
+    int bin_w, bin_h;                   // flame.glsl:17
+    int num_iter;
+    int ppt;                            // particles per temporal sample
+    int first_run;                      // flame.glsl:13
+    unsigned int deal_seed;             // key of this call's re-deal permutations
+    int hammersley_bits;                // log2 of the sample-point count (src/hammersley.cpp:37-42)
+    float hammersley_inv_max;
+};
+
+#define RFK_FIXED_SCALE 16777216.0f  // 2^24
+
+__device__ __forceinline__ unsigned int rfk_hash32(unsigned int h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+// A bijection of [0, RFK_BLOCK): odd multiplier, xor-shift, odd multiplier.
+__device__ __forceinline__ unsigned int rfk_deal_slot(unsigned int tid, unsigned int key) {
+    const unsigned int mask = RFK_BLOCK - 1;
+    unsigned int j = (tid * (key | 1u) + (key >> 8)) & mask;
+    j ^= j >> (RFK_LOG2_BLOCK / 2);
+    j = (j * ((key >> 16) | 1u) + (key >> 24)) & mask;
+    return j;
+}
+
+// src/hammersley.cpp:29-48 for point `i` (z = w = 0)
+__device__ __forceinline__ float2 rfk_sample_point(unsigned int i, int bits, float inv_max) {
+    unsigned int flipped = bits ? (__brev(i) >> (32 - bits)) : 0u;
+    float fx = (float)i * inv_max;
+    float fy = (float)flipped * inv_max;
+    return make_float2((float)((double)fx * 2.0 - 1.0), (float)((double)fy * 2.0 - 1.0));
+}
+
+// flame.glsl:78-84: screen affine, floor, bounds and opacity test, row flip.
+// Returns the bin index or -1. Non-finite positions never bin (the reference leaves
+// ivec2(floor(NaN)) undefined).
+__device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const float* ss, int W, int H) {
+    float px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
+    float py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
+    float fx = floorf(px), fy = floorf(py);
+    if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)W && fy < (float)H && w > 0.0f)) return -1;
+    return (H - (int)fy - 1) * W + (int)fx;
+}
+
+__device__ __forceinline__ unsigned int rfk_palette_index(float z) {
+    float c = ceilf(z * 255.0f);
+    unsigned int u = c > 0.0f ? (unsigned int)c : 0u;  // uint(negative) is undefined in GLSL; clamp to 0
+    return u < 255u ? u : 255u;
+}
+
+__device__ __forceinline__ void rfk_red_add_v4(float4* addr, float r, float g, float b, float a) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(r), "f"(g), "f"(b), "f"(a) : "memory");
+}
+
+#if RFK_WARP_AGGREGATE
+// Sums `v` over the lanes of `peers` (lanes that hit the same bin); the lowest lane
+// of each group ends up with the group total. All lanes of `mask` must call.
+__device__ __forceinline__ float4 rfk_reduce_peers(unsigned int mask, unsigned int peers, float4 v, int lane) {
+    int rel_pos = __popc(peers & ((1u << lane) - 1u));
+    peers &= (0xfffffffeu << lane);
+    while (__any_sync(mask, peers)) {
+        int next = __ffs(peers);
+        int src = next ? next - 1 : lane;
+        float tx = __shfl_sync(mask, v.x, src), ty = __shfl_sync(mask, v.y, src);
+        float tz = __shfl_sync(mask, v.z, src), tw = __shfl_sync(mask, v.w, src);
+        if (next) { v.x += tx; v.y += ty; v.z += tz; v.w += tw; }
+        unsigned int done = rel_pos & 1;
+        peers &= ~__ballot_sync(mask, done);
+        rel_pos >>= 1;
+    }
+    return v;
+}
+#endif
+
+template <bool DRAW>
+__device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
+    __shared__ float fp[RFK_TOTAL_PARAMS + 1];
+    __shared__ float4 pal[256];
+    __shared__ float ex_x[2][RFK_BLOCK], ex_y[2][RFK_BLOCK], ex_c[2][RFK_BLOCK];
+#if RFK_COUNT_XFORMS
+    __shared__ unsigned int xcount[RFK_NUM_XFORMS + 1];
+#endif
+
+    const unsigned int tid = threadIdx.x;
+    const unsigned int lane = tid & 31u;
+    const unsigned int blocks_per_ts = (unsigned int)p.ppt / RFK_BLOCK;
+    const unsigned int ts = blockIdx.x / blocks_per_ts;                  // gl_WorkGroupID.y
+    const size_t slot = (size_t)blockIdx.x * RFK_BLOCK + tid;            // ts * ppt + gl_GlobalInvocationID.x
+
+    for (int i = tid; i < RFK_TOTAL_PARAMS; i += RFK_BLOCK) fp[i] = p.fp_inflated[(size_t)ts * RFK_TOTAL_PARAMS + i];
+    if (DRAW) for (int i = tid; i < 256; i += RFK_BLOCK) pal[i] = p.palette[i];
+#if RFK_COUNT_XFORMS
+    if (tid <= RFK_NUM_XFORMS) xcount[tid] = 0;
+#endif
+
+    rfk_rng rs = p.rng[slot];
+    float x, y, c;
+    __syncthreads();
+
+    unsigned int binned = 0;
+    int parity = 0;
+
+    auto pick_xform = [&]() -> int {
+#if RFK_PER_LANE_XFORM
+        return get_xform_id(rfk_randf(rs), fp);
+#else
+        float u = 0.0f;
+        if (lane == 0) u = rfk_randf(rs);  // flame.glsl:51-53: the first thread of the group burns one draw
+        u = __shfl_sync(0xffffffffu, u, 0);
+        return get_xform_id(u, fp);
+#endif
+    };
+    auto deal = [&](int it) {
+        unsigned int key = rfk_hash32(p.deal_seed ^ (blockIdx.x * 0x9E3779B9u) ^ ((unsigned int)it * 0x7FEB352Du));
+        unsigned int j = rfk_deal_slot(tid, key);
+        ex_x[parity][j] = x; ex_y[parity][j] = y; ex_c[parity][j] = c;
+        __syncthreads();
+        x = ex_x[parity][tid]; y = ex_y[parity][tid]; c = ex_c[parity][tid];
+        parity ^= 1;
+    };
+
+    if (!DRAW && p.first_run) {
+        // flame.glsl:58-65: every temporal sample starts from the same Hammersley set, jittered
+        const unsigned int gid = (blockIdx.x % blocks_per_ts) * RFK_BLOCK + tid;
+        int xid = pick_xform();
+        float2 s = rfk_sample_point(gid, p.hammersley_bits, p.hammersley_inv_max);
+        float r0 = rfk_randf(rs);
+        float r1 = rfk_randf(rs);
+        vec2 sc = sincos(sqrtf(r1));
+        float m = r0 * .1f * PI * 2.0f;
+        vec4 r = dispatch<true>(vec3(s.x + m * sc.x, s.y + m * sc.y, 0.0f), xid, fp, rs);
+        x = r.x; y = r.y; c = r.z;
+        deal(-1);
+    } else {
+        float4 st = p.particles[slot];
+        x = st.x; y = st.y; c = st.z;
+    }
+
+    for (int it = 0; it < p.num_iter; ++it) {
+        const int xid = pick_xform();
+#if RFK_COUNT_XFORMS
+  #if RFK_PER_LANE_XFORM
+        atomicAdd(&xcount[xid], 1u);
+  #else
+        if (lane == 0) atomicAdd(&xcount[xid], 32u);
+  #endif
+#endif
+        vec4 r = dispatch<false>(vec3(x, y, c), xid, fp, rs);
+        x = r.x; y = r.y; c = r.z;  // flame.glsl:72
+
+        if (DRAW) {
+            float fx = r.x, fy = r.y, fc = r.z, fw = r.w;
+#if RFK_HAS_FINAL
+            {   // src/flame.cpp:23: result = dispatch(result.xyz, -1) * vec4(1, 1, 1, result.w)
+                vec4 q = dispatch<false>(vec3(r.x, r.y, r.z), -1, fp, rs);
+                fx = q.x; fy = q.y; fc = q.z; fw = q.w * r.w;
+            }
+#endif
+            const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h);
+#if RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC
+            const unsigned int hit = __ballot_sync(0xffffffffu, idx >= 0);
+            if (idx >= 0) {
+                float4 col = pal[rfk_palette_index(fc)];
+                float4 v = make_float4(col.x, col.y, col.z, fw);
+                unsigned int peers = __match_any_sync(hit, idx);
+                v = rfk_reduce_peers(hit, peers, v, lane);
+                if ((int)lane == __ffs(peers) - 1) rfk_red_add_v4(p.bins + idx, v.x, v.y, v.z, v.w);
+                binned++;
+            }
+#else
+            if (idx >= 0) {
+                float4 col = pal[rfk_palette_index(fc)];
+  #if RFK_DETERMINISTIC
+                unsigned long long* b = p.fixed_bins + (size_t)idx * 4;
+                atomicAdd(b + 0, (unsigned long long)__float2ll_rn(col.x * RFK_FIXED_SCALE));
+                atomicAdd(b + 1, (unsigned long long)__float2ll_rn(col.y * RFK_FIXED_SCALE));
+                atomicAdd(b + 2, (unsigned long long)__float2ll_rn(col.z * RFK_FIXED_SCALE));
+                atomicAdd(b + 3, (unsigned long long)__float2ll_rn(fw * RFK_FIXED_SCALE));
+  #else
+                rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);
+  #endif
+                binned++;
+            }
+#endif
+        }
+#if !RFK_PER_LANE_XFORM
+        deal(it);
+#endif
+    }
+
+    p.particles[slot] = make_float4(x, y, c, 0.0f);
+    p.rng[slot] = rs;  // flame.glsl:89
+
+    if (DRAW) {
+        // flame.glsl:85 does one same-address atomic per sample; one per warp here
+        for (int o = 16; o > 0; o >>= 1) binned += __shfl_xor_sync(0xffffffffu, binned, o);
+        if (lane == 0 && binned) atomicAdd(p.counters, (unsigned long long)binned);
+    }
+#if RFK_COUNT_XFORMS
+    __syncthreads();
+    if (tid < RFK_NUM_XFORMS && xcount[tid]) atomicAdd(p.counters + 1 + tid, (unsigned long long)xcount[tid]);
+#endif
+}
+
+extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_warm(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<false>(p); }
+extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_draw(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<true>(p); }
+
+// Test hook: one dispatch(v, xid) per thread on caller-supplied particles, RNG states
+// and parameter block — the single-step level of the parity contract.
+extern "C" __global__ void rfk_single_step(int n, const float* __restrict__ xyz, const int* __restrict__ xid, uint4* rng,
+                                           const float* __restrict__ fp, int first_run, float4* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rfk_rng rs = rng[i];
+    vec3 v(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    vec4 r = first_run ? dispatch<true>(v, xid[i], fp, rs) : dispatch<false>(v, xid[i], fp, rs);
+    out[i] = make_float4(r.x, r.y, r.z, r.w);
+    rng[i] = rs;
+}
+
+// Test hook: xform selection for caller-supplied ratios (xform_select.tpl.glsl).
+extern "C" __global__ void rfk_select_xform(int n, const float* __restrict__ ratio, const float* __restrict__ fp, int* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = get_xform_id(ratio[i], fp);
+}
+
+struct rfk_bucket_params { float ss_affine[6]; int bin_w, bin_h; };
+
+// Test hook: the bucket index of flame.glsl:78-84 for caller-supplied (x, y, w) and colour.
+extern "C" __global__ void rfk_bucket_index(int n, const float* __restrict__ xyzw, const __grid_constant__ rfk_bucket_params bp,
+                                            int* idx_out, int* pal_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    idx_out[i] = rfk_bin_index(xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 3], bp.ss_affine, bp.bin_w, bp.bin_h);
+    pal_out[i] = (int)rfk_palette_index(xyzw[4 * i + 2]);
+}

@@ -1,0 +1,133 @@
+// Device prelude of every generated chaos-game module (compiled by NVRTC for sm_100a).
+// It gives the variation snippets of variations.yaml — which are GLSL — the types and
+// built-ins they use (vec2/vec3/vec4, sincos, 2-argument atan, mix, mod2, ...), with
+// the semantics of shaders/include/math.glsl:1-22, and the JSF32 generator of
+// shaders/include/random.glsl:29-41.
+namespace rfk_glsl {
+
+typedef unsigned int uint;
+typedef uint4 rfk_rng;  // (a, b, c, d) = local_random_state.xyzw (random.glsl:19-23)
+
+struct vec2 {
+    float x, y;
+    vec2() = default;
+    __device__ __forceinline__ vec2(float a, float b) : x(a), y(b) {}
+    __device__ __forceinline__ explicit vec2(float a) : x(a), y(a) {}
+    __device__ __forceinline__ vec2 yx() const { return vec2(y, x); }
+    __device__ __forceinline__ vec2& operator+=(vec2 o) { x += o.x; y += o.y; return *this; }
+    __device__ __forceinline__ vec2& operator-=(vec2 o) { x -= o.x; y -= o.y; return *this; }
+    __device__ __forceinline__ vec2& operator*=(vec2 o) { x *= o.x; y *= o.y; return *this; }
+    __device__ __forceinline__ vec2& operator/=(vec2 o) { x /= o.x; y /= o.y; return *this; }
+    __device__ __forceinline__ vec2& operator+=(float s) { x += s; y += s; return *this; }
+    __device__ __forceinline__ vec2& operator-=(float s) { x -= s; y -= s; return *this; }
+    __device__ __forceinline__ vec2& operator*=(float s) { x *= s; y *= s; return *this; }
+    __device__ __forceinline__ vec2& operator/=(float s) { x /= s; y /= s; return *this; }
+};
+
+struct ivec2 {
+    int x, y;
+    ivec2() = default;
+    __device__ __forceinline__ ivec2(int a, int b) : x(a), y(b) {}
+};
+
+// v.xy must be assignable and alias v.x / v.y (the affine line of every xform writes it)
+struct vec3 {
+    union {
+        struct { float x, y; };
+        vec2 xy;
+    };
+    float z;
+    vec3() = default;
+    __device__ __forceinline__ vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+    __device__ __forceinline__ vec3(vec2 a, float c) : x(a.x), y(a.y), z(c) {}
+};
+
+struct vec4 {
+    float x, y, z, w;
+    vec4() = default;
+    __device__ __forceinline__ vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
+    __device__ __forceinline__ vec4(vec2 a, float c, float d) : x(a.x), y(a.y), z(c), w(d) {}
+};
+
+#define RFK_BINOP(op)                                                                                       \
+    __device__ __forceinline__ vec2 operator op(vec2 a, vec2 b) { return vec2(a.x op b.x, a.y op b.y); }   \
+    __device__ __forceinline__ vec2 operator op(vec2 a, float s) { return vec2(a.x op s, a.y op s); }      \
+    __device__ __forceinline__ vec2 operator op(float s, vec2 a) { return vec2(s op a.x, s op a.y); }
+RFK_BINOP(+)
+RFK_BINOP(-)
+RFK_BINOP(*)
+RFK_BINOP(/)
+#undef RFK_BINOP
+__device__ __forceinline__ vec2 operator-(vec2 a) { return vec2(-a.x, -a.y); }
+
+// math.glsl:1-4
+static constexpr float PI = 3.141592653589793f;
+static constexpr float PI_2 = PI / 2.0f;  // used by some variations only
+static constexpr float EPS = (1e-10f);
+
+__device__ __forceinline__ float sin(float v) { return ::sinf(v); }
+__device__ __forceinline__ float cos(float v) { return ::cosf(v); }
+__device__ __forceinline__ float tan(float v) { return ::tanf(v); }
+__device__ __forceinline__ float sinh(float v) { return ::sinhf(v); }
+__device__ __forceinline__ float cosh(float v) { return ::coshf(v); }
+__device__ __forceinline__ float exp(float v) { return ::expf(v); }
+__device__ __forceinline__ float log(float v) { return ::logf(v); }
+__device__ __forceinline__ float sqrt(float v) { return ::sqrtf(v); }
+__device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
+__device__ __forceinline__ float atan(float a, float b) { return ::atan2f(a, b); }
+__device__ __forceinline__ float atan(float a) { return ::atanf(a); }
+__device__ __forceinline__ float acos(float v) { return ::acosf(v); }
+__device__ __forceinline__ float asin(float v) { return ::asinf(v); }
+__device__ __forceinline__ float floor(float v) { return ::floorf(v); }
+__device__ __forceinline__ float ceil(float v) { return ::ceilf(v); }
+__device__ __forceinline__ float trunc(float v) { return ::truncf(v); }
+// GLSL round(): the tie direction is the implementation's choice; nearest-even (one FRND)
+__device__ __forceinline__ float round(float v) { return ::rintf(v); }
+__device__ __forceinline__ float abs(float v) { return ::fabsf(v); }
+__device__ __forceinline__ int abs(int v) { return v < 0 ? -v : v; }
+__device__ __forceinline__ float fma(float a, float b, float c) { return ::fmaf(a, b, c); }
+__device__ __forceinline__ float min(float a, float b) { return ::fminf(a, b); }
+__device__ __forceinline__ float max(float a, float b) { return ::fmaxf(a, b); }
+__device__ __forceinline__ int min(int a, int b) { return a < b ? a : b; }
+__device__ __forceinline__ int max(int a, int b) { return a > b ? a : b; }
+__device__ __forceinline__ float clamp(float v, float lo, float hi) { return ::fminf(::fmaxf(v, lo), hi); }
+__device__ __forceinline__ float mix(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float sign(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+__device__ __forceinline__ float fract(float v) { return v - ::floorf(v); }
+__device__ __forceinline__ float mod(float a, float b) { return a - b * ::floorf(a / b); }
+__device__ __forceinline__ float dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float length(vec2 v) { return ::sqrtf(v.x * v.x + v.y * v.y); }
+
+__device__ __forceinline__ vec2 sin(vec2 v) { return vec2(::sinf(v.x), ::sinf(v.y)); }
+__device__ __forceinline__ vec2 cos(vec2 v) { return vec2(::cosf(v.x), ::cosf(v.y)); }
+__device__ __forceinline__ vec2 abs(vec2 v) { return vec2(::fabsf(v.x), ::fabsf(v.y)); }
+__device__ __forceinline__ vec2 mix(vec2 a, vec2 b, float t) { return vec2(mix(a.x, b.x, t), mix(a.y, b.y, t)); }
+
+// math.glsl:6-22
+__device__ __forceinline__ vec2 sincos(float v) {
+    float s, c;
+    ::sincosf(v, &s, &c);
+    return vec2(s, c);
+}
+__device__ __forceinline__ vec2 sinhcosh(float v) { return vec2(::sinhf(v), ::coshf(v)); }
+__device__ __forceinline__ float mod2(float x, float y) { return x - y * ::truncf(x / y); }
+__device__ __forceinline__ float log10(float x) { return ::logf(x) * 0.434294481903251827651128918916f; }
+__device__ __forceinline__ bool badval(float x) { return (x != x) || (x > 1e10f) || (x < -1e10f); }
+
+// random.glsl:29-41. The device generator returns `a` after the update (the host
+// one in src/util.hpp:81-88 returns `d`); randf is float(u)/4294967295.0f, and that
+// divisor rounds to 2^32 in binary32, so the quotient is an exact scaling.
+__device__ __forceinline__ uint rfk_rot32(uint x, int k) { return (x << k) | (x >> (32 - k)); }
+__device__ __forceinline__ uint rfk_ranval(rfk_rng& s) {
+    uint e = s.x - rfk_rot32(s.y, 27);
+    s.x = s.y ^ rfk_rot32(s.z, 17);
+    s.y = s.z + s.w;
+    s.z = s.w + e;
+    s.w = e + s.x;
+    return s.x;
+}
+__device__ __forceinline__ float rfk_randf(rfk_rng& s) {
+    return ::fminf(::fmaxf(__uint2float_rn(rfk_ranval(s)) / 4294967295.0f, 0.0f), 1.0f);
+}
+
+}  // namespace rfk_glsl

@@ -1,0 +1,168 @@
+// Host-side flame object: genome model, flam3 parser, parameter-buffer layout and
+// the warmup / draw_to_bins entry points. Same names, argument meaning and error
+// behaviour as the reference's `struct flame` (src/flame.hpp:21-174, src/flame.cpp),
+// with the OpenGL compute path replaced by sm_100a CUDA kernels.
+#pragma once
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+namespace rfk {
+
+class flame_compiler;
+struct flame_device;  // CUDA-side state (flame_device.cpp)
+
+// src/flame.hpp:21-37 (motion_info is parsed nowhere in the reference and is omitted)
+struct flame_xform {
+    using affine_t = std::array<float, 6>;
+
+    affine_t affine{};
+    std::optional<affine_t> post;
+    std::map<std::string, float> variations;
+    std::map<std::string, float> var_param;
+
+    float weight = 0;
+    float color = 0;
+    float color_speed = 0;
+
+    float rotation_frequency = 0;
+    float opacity = 0;
+};
+
+// Float-slot layout of one xform inside fp[] (src/flame.cpp:39-60).
+struct xform_slots {
+    int start = 0, end = 0, size = 0;
+    int weight = 0;
+    std::array<int, 6> affine{};
+    bool has_post = false;
+    std::array<int, 6> post{};
+    std::map<std::string, int> variations;
+    std::map<std::string, int> param;
+    int color = 0, color_speed = 0, opacity = 0, rotation_frequency = 0;
+};
+
+// The reference keeps this as nlohmann::json (src/flame.cpp:33-71); same content.
+struct buffer_map_t {
+    std::vector<xform_slots> xforms;
+    std::optional<xform_slots> final_xform;
+    int size = 0;
+    std::string dump_json() const;
+};
+
+// Options of the generated chaos-game kernel (no reference counterpart: the GLSL
+// path has a single mode).
+struct kernel_options {
+    bool fast_math = false;       // SFU intrinsics instead of the 1-2 ulp library calls
+    bool fmad = true;             // allow FMA contraction of a*b+c
+    bool per_lane_xform = false;  // every particle picks its own xform (divergent); default one pick per warp
+    bool warp_aggregate = false;  // match_any de-duplication of same-bin updates inside a warp
+    bool deterministic = false;   // fixed-point (integer) accumulation: bit-identical histograms
+    bool count_xforms = false;    // per-xform selection counters
+    int min_blocks = 0;           // __launch_bounds__ second argument, 0 = compiler's choice
+    bool operator==(const kernel_options&) const = default;
+};
+
+struct flame {
+    static constexpr int BLOCK_WIDTH = 256;     // src/flame.cpp:15
+    static constexpr int PARAM_BUFFER = 1024;   // src/flame.hpp:166, shaders/flame.glsl:27
+
+    std::vector<flame_xform> xforms;
+    std::array<std::array<float, 4>, 256> palette{};
+
+    std::array<unsigned int, 2> size{};
+    std::array<float, 2> center{};
+    float scale = 0;
+    float rotate = 0;
+
+    std::optional<flame_xform> final_xform;
+
+    int estimator_min = 0;
+    int estimator_radius = 0;
+    float estimator_curve = 0;
+
+    float gamma = 0;
+    float vibrancy = 0;
+    float brightness = 0;
+
+    template <typename Func>
+    void for_each_xform(Func&& func) {
+        int idx = 0;
+        for (auto& x : xforms) func(idx++, x);
+        if (final_xform) func(-1, final_xform.value());
+    }
+
+    // src/flame.hpp:77, src/flame.cpp:105-158. `seed` offsets the particle RNG seeds
+    // (reference: seed = particle index, i.e. seed 0); shuffle_count is kept for
+    // signature parity (the re-deal permutations are computed on chip).
+    static void set_sim_parameters(std::size_t total_particles, std::size_t temporal_samples, std::size_t shuffle_count,
+                                   std::uint64_t seed = 0);
+
+    // src/flame.hpp:84, src/flame.cpp:160-226. nullptr on an unknown xform attribute,
+    // unreadable file or a kernel that fails to compile; message in last_error().
+    static std::unique_ptr<flame> load_flame(const std::string& path, const flame_compiler& vt);
+    static std::unique_ptr<flame> load_flame_string(const std::string& xml_text, const std::string& origin, const flame_compiler& vt);
+    static const std::string& last_error();
+
+    bool needs_warmup() const;                                 // src/flame.hpp:86
+    void warmup(std::size_t num_passes, float tss_width);      // src/flame.cpp:228-281
+    // bins: DEVICE pointer to bins_len float4 (RGB + density), accumulated in place.
+    // Returns the number of samples binned by this call (src/flame.cpp:283-330).
+    std::size_t draw_to_bins(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter);
+    // Same without the blocking counter read-back; collect with binned_total().
+    void draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter);
+    std::uint64_t binned_total();  // all draw calls since the last warmup
+    void reset_animation();                                    // src/flame.cpp:332-336
+
+    ~flame();
+
+    // src/flame.hpp:97-128
+    static flame_xform::affine_t rotate_affine(const flame_xform::affine_t& a, float deg);
+    static flame_xform::affine_t scale_affine(const flame_xform::affine_t& a, float scale);
+    static flame_xform::affine_t translate_affine(const flame_xform::affine_t& a, const std::array<float, 2>& t);
+    // src/flame.cpp:289-296
+    flame_xform::affine_t screen_space_affine(std::size_t bins_width, std::size_t bins_height) const;
+
+    // src/flame.cpp:33-71 and :73-103
+    void make_shader_buffer_map();
+    std::array<float, PARAM_BUFFER> copy_flame_data_to_buffer() const;
+    const buffer_map_t& buffer_map() const { return buffer_map_; }
+
+    // generated text: reference-identical GLSL body and the CUDA translation unit
+    const std::string& glsl_source() const { return glsl_source_; }
+    const std::string& cuda_source() const { return cuda_source_; }
+    const kernel_options& options() const { return options_; }
+    // Rebuilds the CUDA module with new options (the structure of the genome is fixed
+    // after load, only values change without a rebuild: src/flame.hpp, main.cpp:335-369).
+    bool set_options(const kernel_options& opt);
+    // sm_100a cubin of the generated kernels (compiled on first use; needs no GPU)
+    const std::vector<char>& cubin();
+
+    flame_device* device() { return device_.get(); }
+    std::unique_ptr<flame_device>& device_slot() { return device_; }
+    void mark_dirty() { needs_update_ = true; }
+
+private:
+    flame();
+    bool do_common_init(const flame_compiler& fc);  // src/flame.cpp:17-31
+    friend class flame_compiler;
+    friend struct flame_device;
+
+    buffer_map_t buffer_map_;
+    std::string glsl_source_;
+    std::string cuda_body_;    // generated dispatch()/get_xform_id() in the CUDA dialect
+    std::string cuda_source_;  // prelude + options + body + kernels
+    kernel_options options_;
+    std::vector<char> cubin_;
+    std::unique_ptr<flame_device> device_;
+    bool needs_update_ = true;
+    void rebuild_cuda_source();
+};
+
+void set_last_error(const std::string& msg);
+
+}  // namespace rfk

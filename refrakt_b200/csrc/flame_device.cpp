@@ -1,0 +1,536 @@
+// CUDA side of the flame object: NVRTC build of the generated kernels, device
+// buffers, warmup / draw_to_bins launches. Replaces the GL half of src/flame.cpp
+// (do_common_init :17-31, set_sim_parameters :105-158, warmup :228-281,
+// draw_to_bins :283-330) — there is no CPU fallback: every entry point here throws
+// when no CUDA device / driver is available.
+#include "flame_device.hpp"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <cstring>
+#include <mutex>
+#include <set>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "static_kernels.cuh"
+#include "variation_table.hpp"
+
+namespace rfk {
+
+namespace embedded {
+extern const char* const device_prelude;
+extern const char* const chaos_kernels;
+}  // namespace embedded
+
+// ---------------------------------------------------------------------------------
+// driver entry points (resolved through the runtime, so the library has no link-time
+// dependency on libcuda and loads on a machine without a GPU)
+// ---------------------------------------------------------------------------------
+namespace {
+
+struct driver_api {
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+};
+
+void cuda_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+const driver_api& driver() {
+    static driver_api api = [] {
+        driver_api a;
+        cuda_check(cudaFree(nullptr), "CUDA initialisation (is a GPU visible?)");
+        auto get = [](const char* name, auto& fn) {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            cuda_check(cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q), name);
+            if (!p || q != cudaDriverEntryPointSuccess) throw std::runtime_error(std::string("driver entry point not found: ") + name);
+            fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(p);
+        };
+        get("cuModuleLoadData", a.ModuleLoadData);
+        get("cuModuleUnload", a.ModuleUnload);
+        get("cuModuleGetFunction", a.ModuleGetFunction);
+        get("cuLaunchKernel", a.LaunchKernel);
+        get("cuFuncGetAttribute", a.FuncGetAttribute);
+        get("cuOccupancyMaxActiveBlocksPerMultiprocessor", a.OccupancyMaxActiveBlocksPerMultiprocessor);
+        get("cuGetErrorString", a.GetErrorString);
+        return a;
+    }();
+    return api;
+}
+
+void cu_check(CUresult r, const char* what) {
+    if (r == CUDA_SUCCESS) return;
+    const char* msg = nullptr;
+    driver().GetErrorString(r, &msg);
+    throw std::runtime_error(std::string(what) + ": " + (msg ? msg : "unknown driver error"));
+}
+
+// global simulation state: class-static in the reference (src/flame.hpp:150-156)
+struct sim_state {
+    std::size_t total_particles = 0, temporal_samples = 0, shuffle_count = 0;
+    std::uint64_t seed = 0;
+    uint4* rng = nullptr;
+    std::uint64_t generation = 0;  // bumped by set_sim_parameters: invalidates per-flame buffers (flame.cpp:153-157)
+    cudaStream_t stream = nullptr;
+    std::uint64_t launches = 0;
+};
+sim_state g_sim;
+std::set<flame*> g_active_flames;  // src/flame.hpp:173
+
+std::mutex g_cache_mutex;
+std::unordered_map<std::string, std::vector<char>> g_cubin_cache;  // source text -> cubin
+
+}  // namespace
+
+cudaStream_t current_stream() { return g_sim.stream; }
+void set_current_stream(cudaStream_t s) { g_sim.stream = s; }
+std::uint64_t kernel_launch_count() { return g_sim.launches; }
+void count_launch(unsigned n) { g_sim.launches += n; }
+
+// ---------------------------------------------------------------------------------
+// NVRTC
+// ---------------------------------------------------------------------------------
+std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out) {
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mutex);
+        auto it = g_cubin_cache.find(source + (opt.fast_math ? "#F" : "") + (opt.fmad ? "" : "#M"));
+        if (it != g_cubin_cache.end()) return it->second;
+    }
+    nvrtcProgram prog;
+    if (nvrtcCreateProgram(&prog, source.c_str(), "rfk_chaos_game.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+        throw std::runtime_error("nvrtcCreateProgram failed");
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--generate-line-info"};
+    if (opt.fast_math) opts.push_back("--use_fast_math");
+    if (!opt.fmad) opts.push_back("--fmad=false");
+    nvrtcResult res = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    std::size_t log_size = 0;
+    nvrtcGetProgramLogSize(prog, &log_size);
+    std::string log(log_size, '\0');
+    if (log_size) nvrtcGetProgramLog(prog, log.data());
+    if (log_out) *log_out = log;
+    if (res != NVRTC_SUCCESS) {
+        nvrtcDestroyProgram(&prog);
+        throw std::runtime_error("kernel compilation failed:\n" + log);
+    }
+    std::size_t size = 0;
+    nvrtcGetCUBINSize(prog, &size);
+    std::vector<char> cubin(size);
+    nvrtcGetCUBIN(prog, cubin.data());
+    nvrtcDestroyProgram(&prog);
+    std::lock_guard<std::mutex> lock(g_cache_mutex);
+    g_cubin_cache[source + (opt.fast_math ? "#F" : "") + (opt.fmad ? "" : "#M")] = cubin;
+    return cubin;
+}
+
+// ---------------------------------------------------------------------------------
+// flame: construction, codegen products
+// ---------------------------------------------------------------------------------
+struct rfk_iter_params_host {  // must match rfk_iter_params in chaos_kernels.cuh
+    float4* particles;
+    uint4* rng;
+    const float* fp_inflated;
+    const float4* palette;
+    float4* bins;
+    unsigned long long* fixed_bins;
+    unsigned long long* counters;
+    float ss_affine[6];
+    int bin_w, bin_h;
+    int num_iter;
+    int ppt;
+    int first_run;
+    unsigned int deal_seed;
+    int hammersley_bits;
+    float hammersley_inv_max;
+};
+
+struct flame_device {
+    CUmodule module = nullptr;
+    CUfunction warm = nullptr, draw = nullptr, single_step = nullptr, select_xform = nullptr, bucket_index = nullptr;
+    float4* particles = nullptr;
+    float* fp = nullptr;
+    float* fp_inflated = nullptr;
+    float4* palette = nullptr;
+    unsigned long long* counters = nullptr;  // [0] binned, [1..] per-xform picks
+    unsigned long long* fixed_bins = nullptr;
+    std::size_t fixed_len = 0;
+    kernels::animate_xform* anim = nullptr;
+    int anim_count = 0;
+    std::uint64_t sim_generation = ~0ull;
+    unsigned int deal_counter = 0x5EED0001u;
+    std::uint64_t binned_reported = 0;
+    bool warmed = false;
+
+    ~flame_device() {
+        if (module) driver().ModuleUnload(module);
+        cudaFree(particles); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
+        cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
+    }
+};
+
+flame::flame() { g_active_flames.insert(this); }
+flame::~flame() { g_active_flames.erase(this); }
+
+void flame::rebuild_cuda_source() {
+    const int n = (int)xforms.size();
+    std::string s;
+    s += "// generated by refrakt_b200 for one genome: options, prelude, dispatch, kernels\n";
+    s += "#define RFK_BLOCK " + std::to_string(BLOCK_WIDTH) + "\n";
+    int log2b = 0;
+    while ((1 << log2b) < BLOCK_WIDTH) log2b++;
+    s += "#define RFK_LOG2_BLOCK " + std::to_string(log2b) + "\n";
+    s += "#define RFK_TOTAL_PARAMS " + std::to_string(buffer_map_.size) + "\n";
+    s += "#define RFK_NUM_XFORMS " + std::to_string(n) + "\n";
+    s += "#define RFK_HAS_FINAL " + std::to_string(final_xform ? 1 : 0) + "\n";
+    s += "#define RFK_PER_LANE_XFORM " + std::to_string(options_.per_lane_xform ? 1 : 0) + "\n";
+    s += "#define RFK_WARP_AGGREGATE " + std::to_string(options_.warp_aggregate ? 1 : 0) + "\n";
+    s += "#define RFK_DETERMINISTIC " + std::to_string(options_.deterministic ? 1 : 0) + "\n";
+    s += "#define RFK_COUNT_XFORMS " + std::to_string(options_.count_xforms ? 1 : 0) + "\n";
+    if (options_.min_blocks > 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(options_.min_blocks) + ")\n";
+    else s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK)\n";
+    s += embedded::device_prelude;
+    s += "\nnamespace rfk_glsl {\n#define randf() rfk_randf(rs)\n";
+    s += cuda_body_;
+    s += "#undef randf\n}  // namespace rfk_glsl\n\n";
+    s += embedded::chaos_kernels;
+    cuda_source_ = std::move(s);
+    cubin_.clear();
+    if (device_) device_.reset();  // module must be rebuilt
+}
+
+bool flame::do_common_init(const flame_compiler& fc) {
+    make_shader_buffer_map();
+    if (buffer_map_.size > PARAM_BUFFER) {
+        set_last_error("flame needs " + std::to_string(buffer_map_.size) + " parameter slots; the parameter buffer holds " + std::to_string(PARAM_BUFFER));
+        return false;
+    }
+    try {
+        glsl_source_ = fc.compile_flame_xforms(*this);
+        cuda_body_ = fc.compile_flame_cuda(*this);
+    } catch (const std::exception& e) {
+        set_last_error(std::string("flame compiler: ") + e.what());
+        return false;
+    }
+    rebuild_cuda_source();
+    reset_animation();
+    try {
+        cubin();  // the reference fails the load when the shader does not compile (flame.cpp:30)
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return false;
+    }
+    return true;
+}
+
+bool flame::set_options(const kernel_options& opt) {
+    if (opt == options_) return true;
+    kernel_options old = options_;
+    options_ = opt;
+    rebuild_cuda_source();
+    try {
+        cubin();
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        options_ = old;
+        rebuild_cuda_source();
+        return false;
+    }
+    needs_update_ = true;
+    return true;
+}
+
+const std::vector<char>& flame::cubin() {
+    if (cubin_.empty()) cubin_ = compile_cubin(cuda_source_, options_, nullptr);
+    return cubin_;
+}
+
+void flame::reset_animation() { needs_update_ = true; }
+
+// ---------------------------------------------------------------------------------
+// simulation parameters
+// ---------------------------------------------------------------------------------
+void flame::set_sim_parameters(std::size_t total_particles, std::size_t temporal_samples, std::size_t shuffle_count, std::uint64_t seed) {
+    if (temporal_samples == 0 || total_particles == 0) throw std::invalid_argument("set_sim_parameters: particle and temporal sample counts must be positive");
+    if (total_particles % temporal_samples != 0 || (total_particles / temporal_samples) % BLOCK_WIDTH != 0)
+        throw std::invalid_argument("set_sim_parameters: particles per temporal sample must be a multiple of " + std::to_string(BLOCK_WIDTH));
+    if (total_particles / BLOCK_WIDTH > 0x7fffffffull) throw std::invalid_argument("set_sim_parameters: too many particles");
+    driver();
+    if (g_sim.rng) cuda_check(cudaFree(g_sim.rng), "cudaFree(rng)");
+    g_sim.rng = nullptr;
+    cuda_check(cudaMalloc(&g_sim.rng, total_particles * sizeof(uint4)), "cudaMalloc(rng states)");
+    g_sim.total_particles = total_particles;
+    g_sim.temporal_samples = temporal_samples;
+    g_sim.shuffle_count = shuffle_count;
+    g_sim.seed = seed;
+    g_sim.generation++;
+    kernels::seed_rng_states(g_sim.rng, total_particles, (std::uint32_t)seed, g_sim.stream);
+    count_launch(1);
+    cuda_check(cudaGetLastError(), "seed_rng_states");
+    // invalidate existing flames
+    for (auto* f : g_active_flames)
+        if (f->device()) f->device()->sim_generation = ~0ull;
+}
+
+std::size_t sim_total_particles() { return g_sim.total_particles; }
+std::size_t sim_temporal_samples() { return g_sim.temporal_samples; }
+const uint4* sim_rng_states() { return g_sim.rng; }
+
+// ---------------------------------------------------------------------------------
+// device state
+// ---------------------------------------------------------------------------------
+static void ensure_module(flame& f) {
+    if (!f.device_slot()) f.device_slot() = std::make_unique<flame_device>();
+    flame_device& d = *f.device();
+    if (d.module) return;
+    const auto& api = driver();
+    const auto& image = f.cubin();
+    cu_check(api.ModuleLoadData(&d.module, image.data()), "cuModuleLoadData");
+    cu_check(api.ModuleGetFunction(&d.warm, d.module, "rfk_warm"), "rfk_warm");
+    cu_check(api.ModuleGetFunction(&d.draw, d.module, "rfk_draw"), "rfk_draw");
+    cu_check(api.ModuleGetFunction(&d.single_step, d.module, "rfk_single_step"), "rfk_single_step");
+    cu_check(api.ModuleGetFunction(&d.select_xform, d.module, "rfk_select_xform"), "rfk_select_xform");
+    cu_check(api.ModuleGetFunction(&d.bucket_index, d.module, "rfk_bucket_index"), "rfk_bucket_index");
+}
+
+static void ensure_buffers(flame& f) {
+    ensure_module(f);
+    flame_device& d = *f.device();
+    if (g_sim.total_particles == 0) throw std::runtime_error("set_sim_parameters has not been called");
+    const int total_params = f.buffer_map().size;
+    if (!d.fp) {
+        cuda_check(cudaMalloc(&d.fp, flame::PARAM_BUFFER * sizeof(float)), "cudaMalloc(fp)");
+        cuda_check(cudaMalloc(&d.palette, 256 * sizeof(float4)), "cudaMalloc(palette)");
+        cuda_check(cudaMalloc(&d.counters, 64 * sizeof(unsigned long long)), "cudaMalloc(counters)");
+        std::vector<kernels::animate_xform> ax;
+        auto add = [&](const xform_slots& m) {
+            kernels::animate_xform a;
+            for (int i = 0; i < 6; i++) a.affine[i] = m.affine[i];
+            a.rotation_frequency = m.rotation_frequency;
+            ax.push_back(a);
+        };
+        for (auto& m : f.buffer_map().xforms) add(m);
+        if (f.buffer_map().final_xform) add(*f.buffer_map().final_xform);
+        d.anim_count = (int)ax.size();
+        cuda_check(cudaMalloc(&d.anim, ax.size() * sizeof(kernels::animate_xform)), "cudaMalloc(animate table)");
+        cuda_check(cudaMemcpyAsync(d.anim, ax.data(), ax.size() * sizeof(kernels::animate_xform), cudaMemcpyHostToDevice, g_sim.stream), "upload animate table");
+        cuda_check(cudaStreamSynchronize(g_sim.stream), "upload animate table");
+    }
+    if (d.sim_generation != g_sim.generation) {
+        cudaFree(d.particles); d.particles = nullptr;
+        cudaFree(d.fp_inflated); d.fp_inflated = nullptr;
+        cuda_check(cudaMalloc(&d.particles, g_sim.total_particles * sizeof(float4)), "cudaMalloc(particles)");
+        cuda_check(cudaMalloc(&d.fp_inflated, g_sim.temporal_samples * (std::size_t)total_params * sizeof(float)), "cudaMalloc(fp_inflated)");
+        d.sim_generation = g_sim.generation;
+        d.warmed = false;
+    }
+}
+
+bool flame::needs_warmup() const {
+    return needs_update_ || !device_ || !device_->particles || !device_->fp_inflated || device_->sim_generation != g_sim.generation || !device_->warmed;
+}
+
+static void launch(CUfunction fn, unsigned grid, unsigned block, void** args) {
+    cu_check(driver().LaunchKernel(fn, grid, 1, 1, block, 1, 1, 0, (CUstream)g_sim.stream, args, nullptr), "cuLaunchKernel");
+    count_launch(1);
+}
+
+static rfk_iter_params_host base_params(flame& f) {
+    flame_device& d = *f.device();
+    rfk_iter_params_host p{};
+    p.particles = d.particles;
+    p.rng = g_sim.rng;
+    p.fp_inflated = d.fp_inflated;
+    p.palette = d.palette;
+    p.counters = d.counters;
+    p.ppt = (int)(g_sim.total_particles / g_sim.temporal_samples);
+    // src/hammersley.cpp:33-42
+    std::uint32_t count = (std::uint32_t)p.ppt, max = count;
+    if (count % 2 != 0) { max = count - 1; max |= max >> 1; max |= max >> 2; max |= max >> 4; max |= max >> 8; max |= max >> 16; max++; }
+    p.hammersley_inv_max = 1.0f / max;
+    p.hammersley_bits = 0;
+    for (std::uint32_t v = max; v >>= 1;) p.hammersley_bits++;
+    p.deal_seed = d.deal_counter;
+    d.deal_counter = d.deal_counter * 1664525u + 1013904223u;
+    return p;
+}
+
+void flame::warmup(std::size_t num_passes, float tss_width) {
+    ensure_buffers(*this);
+    flame_device& d = *device_;
+    needs_update_ = false;
+
+    auto buf = copy_flame_data_to_buffer();
+    cuda_check(cudaMemcpyAsync(d.fp, buf.data(), PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
+    cuda_check(cudaMemcpyAsync(d.palette, palette.data(), 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
+    cuda_check(cudaMemsetAsync(d.counters, 0, 64 * sizeof(unsigned long long), g_sim.stream), "clear counters");
+    // the host arrays above are stack / member storage: finish the copies before returning control
+    kernels::animate(d.fp, d.fp_inflated, buffer_map_.size, (int)g_sim.temporal_samples, tss_width, d.anim, d.anim_count, g_sim.stream);
+    count_launch(1);
+
+    rfk_iter_params_host p = base_params(*this);
+    p.first_run = 1;
+    p.num_iter = (int)num_passes;
+    void* args[] = {&p};
+    launch(d.warm, (unsigned)(g_sim.total_particles / BLOCK_WIDTH), BLOCK_WIDTH, args);
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "warmup");
+    d.binned_reported = 0;
+    d.warmed = true;
+}
+
+void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter) {
+    if (needs_warmup()) throw std::runtime_error("draw_to_bins: warmup() has not been run for the current parameters");
+    if (!bins || bins_width == 0 || bins_len < bins_width) throw std::invalid_argument("draw_to_bins: bad bins buffer");
+    flame_device& d = *device_;
+    const std::size_t W = bins_width, H = bins_len / bins_width;  // flame.cpp:290
+    if (W > 0x7fffffff / 4 || H > 0x7fffffff / 4 || W * H > 0x7fffffffull) throw std::invalid_argument("draw_to_bins: histogram too large for 32-bit bin indices");
+
+    rfk_iter_params_host p = base_params(*this);
+    auto ss = screen_space_affine(W, H);
+    for (int i = 0; i < 6; i++) p.ss_affine[i] = ss[i];
+    p.bin_w = (int)W;
+    p.bin_h = (int)H;
+    p.bins = reinterpret_cast<float4*>(bins);
+    p.num_iter = num_iter;
+    p.first_run = 0;
+
+    if (options_.deterministic) {
+        if (d.fixed_len != W * H) {
+            cudaFree(d.fixed_bins); d.fixed_bins = nullptr;
+            cuda_check(cudaMalloc(&d.fixed_bins, W * H * 4 * sizeof(unsigned long long)), "cudaMalloc(fixed-point bins)");
+            d.fixed_len = W * H;
+        }
+        cuda_check(cudaMemsetAsync(d.fixed_bins, 0, W * H * 4 * sizeof(unsigned long long), g_sim.stream), "clear fixed-point bins");
+        p.fixed_bins = d.fixed_bins;
+    }
+    void* args[] = {&p};
+    launch(d.draw, (unsigned)(g_sim.total_particles / BLOCK_WIDTH), BLOCK_WIDTH, args);
+    if (options_.deterministic) {
+        kernels::fixed_to_float(d.fixed_bins, p.bins, W * H, g_sim.stream);
+        count_launch(1);
+    }
+}
+
+std::uint64_t flame::binned_total() {
+    if (!device_ || !device_->counters) return 0;
+    unsigned long long total = 0;
+    cuda_check(cudaMemcpyAsync(&total, device_->counters, sizeof(total), cudaMemcpyDeviceToHost, g_sim.stream), "read binned counter");
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "read binned counter");
+    return total;
+}
+
+std::size_t flame::draw_to_bins(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter) {
+    draw_to_bins_async(bins, bins_len, bins_width, num_iter);
+    std::uint64_t total = binned_total();  // blocks, like counters_.get_one(0) at flame.cpp:329
+    std::uint64_t delta = total - device_->binned_reported;
+    device_->binned_reported = total;
+    return (std::size_t)delta;
+}
+
+// ---------------------------------------------------------------------------------
+// test hooks (device work on host-supplied vectors)
+// ---------------------------------------------------------------------------------
+namespace {
+template <typename T>
+struct dev_buf {
+    T* p = nullptr;
+    std::size_t n = 0;
+    explicit dev_buf(std::size_t count) : n(count) { cuda_check(cudaMalloc(&p, (count ? count : 1) * sizeof(T)), "cudaMalloc(test buffer)"); }
+    ~dev_buf() { cudaFree(p); }
+    void upload(const T* h) { cuda_check(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice), "upload"); }
+    void download(T* h) { cuda_check(cudaMemcpy(h, p, n * sizeof(T), cudaMemcpyDeviceToHost), "download"); }
+};
+}  // namespace
+
+void flame_single_step(flame& f, int n, const float* xyz, const int* xid, std::uint32_t* rng, const float* fp, int first_run, float* out) {
+    ensure_module(f);
+    dev_buf<float> d_xyz(3 * (std::size_t)n), d_fp(flame::PARAM_BUFFER), d_out(4 * (std::size_t)n);
+    dev_buf<int> d_xid(n);
+    dev_buf<std::uint32_t> d_rng(4 * (std::size_t)n);
+    d_xyz.upload(xyz); d_xid.upload(xid); d_rng.upload(rng);
+    std::array<float, flame::PARAM_BUFFER> own;
+    if (!fp) { own = f.copy_flame_data_to_buffer(); fp = own.data(); }
+    d_fp.upload(fp);
+    float4* outp = reinterpret_cast<float4*>(d_out.p);
+    uint4* rngp = reinterpret_cast<uint4*>(d_rng.p);
+    void* args[] = {&n, &d_xyz.p, &d_xid.p, &rngp, &d_fp.p, &first_run, &outp};
+    launch(f.device()->single_step, (unsigned)((n + 127) / 128), 128, args);
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "rfk_single_step");
+    d_out.download(out); d_rng.download(rng);
+}
+
+void flame_select_xform(flame& f, int n, const float* ratio, const float* fp, int* out) {
+    ensure_module(f);
+    dev_buf<float> d_ratio(n), d_fp(flame::PARAM_BUFFER);
+    dev_buf<int> d_out(n);
+    d_ratio.upload(ratio);
+    std::array<float, flame::PARAM_BUFFER> own;
+    if (!fp) { own = f.copy_flame_data_to_buffer(); fp = own.data(); }
+    d_fp.upload(fp);
+    void* args[] = {&n, &d_ratio.p, &d_fp.p, &d_out.p};
+    launch(f.device()->select_xform, (unsigned)((n + 127) / 128), 128, args);
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "rfk_select_xform");
+    d_out.download(out);
+}
+
+void flame_bucket_index(flame& f, int n, const float* xyzw, const float ss_affine[6], int W, int H, int* idx_out, int* pal_out) {
+    ensure_module(f);
+    dev_buf<float> d_in(4 * (std::size_t)n);
+    dev_buf<int> d_idx(n), d_pal(n);
+    d_in.upload(xyzw);
+    struct { float ss[6]; int w, h; } bp;
+    for (int i = 0; i < 6; i++) bp.ss[i] = ss_affine[i];
+    bp.w = W; bp.h = H;
+    void* args[] = {&n, &d_in.p, &bp, &d_idx.p, &d_pal.p};
+    launch(f.device()->bucket_index, (unsigned)((n + 127) / 128), 128, args);
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "rfk_bucket_index");
+    d_idx.download(idx_out); d_pal.download(pal_out);
+}
+
+void flame_animate_host(flame& f, float tss_width, int temporal_samples, float* out) {
+    ensure_module(f);
+    const int total = f.buffer_map().size;
+    dev_buf<float> d_fp(flame::PARAM_BUFFER), d_out((std::size_t)temporal_samples * total);
+    auto buf = f.copy_flame_data_to_buffer();
+    d_fp.upload(buf.data());
+    std::vector<kernels::animate_xform> ax;
+    auto add = [&](const xform_slots& m) {
+        kernels::animate_xform a;
+        for (int i = 0; i < 6; i++) a.affine[i] = m.affine[i];
+        a.rotation_frequency = m.rotation_frequency;
+        ax.push_back(a);
+    };
+    for (auto& m : f.buffer_map().xforms) add(m);
+    if (f.buffer_map().final_xform) add(*f.buffer_map().final_xform);
+    dev_buf<kernels::animate_xform> d_ax(ax.size());
+    d_ax.upload(ax.data());
+    kernels::animate(d_fp.p, d_out.p, total, temporal_samples, tss_width, d_ax.p, (int)ax.size(), g_sim.stream);
+    count_launch(1);
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "animate");
+    d_out.download(out);
+}
+
+void flame_kernel_info(flame& f, const char* kernel, int* regs, int* smem_bytes, int* blocks_per_sm) {
+    ensure_module(f);
+    CUfunction fn = nullptr;
+    cu_check(driver().ModuleGetFunction(&fn, f.device()->module, kernel), kernel);
+    cu_check(driver().FuncGetAttribute(regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn), "regs");
+    cu_check(driver().FuncGetAttribute(smem_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, fn), "smem");
+    cu_check(driver().OccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, flame::BLOCK_WIDTH, 0), "occupancy");
+}
+
+void flame_read_counters(flame& f, unsigned long long* out, int n) {
+    if (!f.device() || !f.device()->counters) { std::memset(out, 0, n * sizeof(*out)); return; }
+    cuda_check(cudaMemcpyAsync(out, f.device()->counters, (std::size_t)(n < 64 ? n : 64) * sizeof(*out), cudaMemcpyDeviceToHost, g_sim.stream), "read counters");
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "read counters");
+}
+
+}  // namespace rfk

@@ -1,0 +1,33 @@
+// Device-side helpers shared between flame_device.cpp and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "flame.hpp"
+
+namespace rfk {
+
+cudaStream_t current_stream();
+void set_current_stream(cudaStream_t s);
+std::uint64_t kernel_launch_count();  // kernels launched by this library since load
+void count_launch(unsigned n);
+
+std::size_t sim_total_particles();
+std::size_t sim_temporal_samples();
+const uint4* sim_rng_states();
+
+// NVRTC: CUDA source -> sm_100a cubin (no GPU needed). Throws with the compile log on failure.
+std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out);
+
+// test hooks: run the generated device functions on host-supplied vectors
+void flame_single_step(flame& f, int n, const float* xyz, const int* xid, std::uint32_t* rng, const float* fp, int first_run, float* out);
+void flame_select_xform(flame& f, int n, const float* ratio, const float* fp, int* out);
+void flame_bucket_index(flame& f, int n, const float* xyzw, const float ss_affine[6], int W, int H, int* idx_out, int* pal_out);
+void flame_animate_host(flame& f, float tss_width, int temporal_samples, float* out);
+void flame_kernel_info(flame& f, const char* kernel, int* regs, int* smem_bytes, int* blocks_per_sm);
+void flame_read_counters(flame& f, unsigned long long* out, int n);
+
+}  // namespace rfk

@@ -1,0 +1,304 @@
+// Genome-independent device kernels: RNG seeding, sample points, shuffle buffers,
+// temporal-sample parameter inflation, density estimation + tonemap.
+#include "static_kernels.cuh"
+
+#include <cmath>
+
+namespace rfk::kernels {
+
+namespace {
+
+__device__ __forceinline__ unsigned int rot32(unsigned int x, int k) { return (x << k) | (x >> (32 - k)); }
+
+__global__ void seed_rng_kernel(uint4* states, size_t count, unsigned int seed_base) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned int seed = seed_base + (unsigned int)i;
+    unsigned int a = 0xf1ea5eedu, b = seed, c = seed, d = seed;
+    for (int k = 0; k < 20; k++) {
+        unsigned int e = a - rot32(b, 27);
+        a = b ^ rot32(c, 17);
+        b = c + d;
+        c = d + e;
+        d = e + a;
+    }
+    states[i] = make_uint4(a, b, c, d);
+}
+
+__global__ void sample_points_kernel(float4* out, unsigned int count, int bits, float inv_max) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned int flipped = bits ? (__brev(i) >> (32 - bits)) : 0u;
+    float fx = (float)i * inv_max;
+    float fy = (float)flipped * inv_max;
+    out[i] = make_float4((float)((double)fx * 2.0 - 1.0), (float)((double)fy * 2.0 - 1.0), 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ unsigned int hash32(unsigned int h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    return h;
+}
+
+// One permutation per blockIdx.y: a 4-round Feistel network on `bits` bits (a bijection
+// of [0, 2^bits)) cycle-walked into [0, size). Replaces std::shuffle + mt19937_64.
+__global__ void shuffle_kernel(unsigned int* out, unsigned int size, int bits, unsigned long long seed) {
+    unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    const unsigned int perm = blockIdx.y;
+    const int half_lo = bits / 2, half_hi = bits - half_lo;
+    const unsigned int mask_lo = (1u << half_lo) - 1u, mask_hi = (1u << half_hi) - 1u;
+    const unsigned int k0 = hash32((unsigned int)seed ^ (perm * 0x9E3779B9u)), k1 = hash32((unsigned int)(seed >> 32) + perm);
+    unsigned int v = i;
+    do {
+        unsigned int lo = v & mask_lo, hi = v >> half_lo;
+        for (int r = 0; r < 4; r++) {
+            // (lo: half_lo bits, hi: half_hi bits) -> (hi', lo') with widths swapped back every two rounds
+            unsigned int f = hash32(hi ^ k0 ^ (r * 0x632BE5ABu)) + k1;
+            unsigned int nlo = (lo ^ f) & mask_lo;
+            unsigned int g = hash32(nlo + k1 * (r + 1u)) ^ k0;
+            unsigned int nhi = (hi ^ g) & mask_hi;
+            lo = nlo; hi = nhi;
+        }
+        v = (hi << half_lo) | lo;
+    } while (v >= size);
+    out[(size_t)perm * size + i] = v;
+}
+
+__global__ void animate_kernel(const float* __restrict__ fp, float* __restrict__ fp_inflated, int total_params, int temporal_samples,
+                               float temporal_sample_width, const animate_xform* __restrict__ xf, int num_xforms) {
+    const float rads_per_second = 0.31415926535f;  // animate.tpl.glsl:16
+    int ts = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ts >= temporal_samples) return;
+    int half_width = temporal_samples / 2;
+    int sample_pos = ts - half_width;
+    float dt = sample_pos / float(half_width) * temporal_sample_width;
+    float* dst = fp_inflated + (size_t)ts * total_params;
+    for (int i = 0; i < total_params; i++) dst[i] = fp[i];
+    for (int k = 0; k < num_xforms; k++) {
+        const animate_xform x = xf[k];
+        float ang = rads_per_second * dt * fp[x.rotation_frequency];
+        float sino = sinf(ang), coso = cosf(ang);
+        float a = fp[x.affine[0]], b = fp[x.affine[1]], c = fp[x.affine[2]], d = fp[x.affine[3]];
+        dst[x.affine[0]] = a * coso + c * sino;
+        dst[x.affine[1]] = b * coso + d * sino;
+        dst[x.affine[2]] = c * coso - a * sino;
+        dst[x.affine[3]] = d * coso - b * sino;
+    }
+}
+
+__global__ void fixed_to_float_kernel(const unsigned long long* __restrict__ fixed, float4* bins, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double s = 1.0 / 16777216.0;
+    float4 b = bins[i];
+    b.x += (float)((double)fixed[4 * i + 0] * s);
+    b.y += (float)((double)fixed[4 * i + 1] * s);
+    b.z += (float)((double)fixed[4 * i + 2] * s);
+    b.w += (float)((double)fixed[4 * i + 3] * s);
+    bins[i] = b;
+}
+
+__global__ void downsample2x_kernel(const float4* __restrict__ in, float4* __restrict__ out, int W, int H) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float4* r0 = in + (size_t)(2 * y) * (2 * W) + 2 * x;
+    const float4* r1 = r0 + 2 * W;
+    float4 a = r0[0], b = r0[1], c = r1[0], d = r1[1];
+    out[(size_t)y * W + x] = make_float4((a.x + b.x + c.x + d.x) * 0.25f, (a.y + b.y + c.y + d.y) * 0.25f,
+                                         (a.z + b.z + c.z + d.z) * 0.25f, (a.w + b.w + c.w + d.w) * 0.25f);
+}
+
+// density_vert.glsl:35-44
+__device__ __forceinline__ int estimator_radius_of(float density, const density_params& p) {
+    int r = (int)((float)p.estimator_radius / powf(density, p.estimator_curve));
+    r = min(p.estimator_radius, r);
+    return max(p.estimator_min, r);
+}
+
+// tonemap.glsl:25-36; an empty pixel (alpha 0) is 0 * (0/0) in the reference — defined as black here
+__device__ __forceinline__ float4 tonemap_pixel(float4 color, const density_params& p) {
+    if (!(color.w > 0.0f)) return make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    float s = .5f * p.brightness * logf(1.0f + color.w * p.scale_constant) * 0.434294481903251827651128918916f / color.w;
+    color.x *= s; color.y *= s; color.z *= s; color.w *= s;
+    float inv_gamma = 1.0f / p.gamma;
+    float z = powf(color.w, inv_gamma);
+    float gamma_factor = z / color.w;
+    float v = p.vibrancy;
+    auto chan = [&](float ch) {
+        float m = powf(ch, inv_gamma) * (1.0f - v) + (gamma_factor * ch) * v;
+        return fminf(fmaxf(m, 0.0f), 1.0f);
+    };
+    return make_float4(chan(color.x), chan(color.y), chan(color.z), 1.0f);
+}
+
+constexpr int DE_TILE_W = 32, DE_ROWS_PER_WARP = 4, DE_WARPS = 8, DE_TILE_H = DE_ROWS_PER_WARP * DE_WARPS;
+
+// Gather form of the reference's point-sprite splat. A warp owns 4 output rows x 32
+// columns and keeps their float4 sums in registers (no atomics, fixed summation order).
+// Source bin (bx, by) with radius r lands on out[cy + m][bx - 1 + i], cy = H-1-by,
+// i, m in [-r, r], weight (1 - n(i)^2 - n(m)^2) * (2/pi) / r^2 when that is >= 0, with
+// n(k) = 2k/(2r+1) + 1/(2r+1)^2; r == 0 copies the bin to out[cy][bx-1].
+// The warp scans the source rows within the maximum radius; a bin is a candidate only if
+// its density is below the threshold of the smallest radius that could reach the warp's
+// rows, so dense regions (radius 0 everywhere) cost one 4-byte load per scanned bin.
+template <bool DENSITY, bool TONEMAP>
+__global__ void __launch_bounds__(DE_WARPS * 32) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
+                                                                       uchar4* __restrict__ out_rgba8, const density_params p,
+                                                                       const float* __restrict__ thresholds) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ox = blockIdx.x * DE_TILE_W + lane;
+    const int oy0 = blockIdx.y * DE_TILE_H + warp * DE_ROWS_PER_WARP;
+    const int W = p.W, H = p.H;
+
+    float4 acc[DE_ROWS_PER_WARP];
+#pragma unroll
+    for (int k = 0; k < DE_ROWS_PER_WARP; k++) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (DENSITY) {
+        const int R = max(p.estimator_radius, p.estimator_min);
+        // radius-0 sources: out[cy][ox] takes bin (ox + 1, cy)
+        if (p.estimator_min == 0) {
+#pragma unroll
+            for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
+                int cy = oy0 + k, bx = ox + 1;
+                if (cy < H && bx < W) {
+                    float4 c = __ldg(bins + (size_t)(H - 1 - cy) * W + bx);
+                    if (c.w != 0.0f && estimator_radius_of(c.w, p) == 0) acc[k] = c;
+                }
+            }
+        }
+        // radius >= 1 sources
+        if (R >= 1) {
+            const int bx_first = blockIdx.x * DE_TILE_W + 1 - R;  // leftmost source column that can reach the tile
+            const int span = DE_TILE_W + 2 * R;
+            const float t_any = thresholds[1];
+            for (int cy = max(0, oy0 - R); cy <= min(H - 1, oy0 + DE_ROWS_PER_WARP - 1 + R); cy++) {
+                // smallest |m| between this source row and the warp's rows
+                int dy = cy < oy0 ? oy0 - cy : (cy > oy0 + DE_ROWS_PER_WARP - 1 ? cy - (oy0 + DE_ROWS_PER_WARP - 1) : 0);
+                const float t_row = dy <= 1 ? t_any : thresholds[dy];
+                const float4* row = bins + (size_t)(H - 1 - cy) * W;
+                for (int c0 = 0; c0 < span; c0 += 32) {
+                    int bx = bx_first + c0 + lane;
+                    float d = 0.0f;
+                    if (c0 + lane < span && bx >= 0 && bx < W) d = __ldg(&row[bx].w);
+                    unsigned int cand = __ballot_sync(0xffffffffu, d != 0.0f && d <= t_row);
+                    if (!cand) continue;
+                    // candidates: exact radius and colour, then every lane accumulates its column
+                    float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int r = 0;
+                    if (cand & (1u << lane)) {
+                        col = __ldg(&row[bx]);
+                        r = estimator_radius_of(d, p);
+                    }
+                    while (cand) {
+                        int src = __ffs(cand) - 1;
+                        cand &= cand - 1;
+                        int sr = __shfl_sync(0xffffffffu, r, src);
+                        if (sr < 1 || sr < dy) continue;  // warp-uniform
+                        float sx = __shfl_sync(0xffffffffu, col.x, src), sy = __shfl_sync(0xffffffffu, col.y, src);
+                        float sz = __shfl_sync(0xffffffffu, col.z, src), sw = __shfl_sync(0xffffffffu, col.w, src);
+                        int sbx = bx_first + c0 + src;
+                        int i = ox - sbx + 1;
+                        if (i < -sr || i > sr) continue;  // per lane
+                        float S = (float)(2 * sr + 1);
+                        float bias = 1.0f / (S * S);
+                        float ni = 2.0f * (float)i / S + bias;
+                        float norm = 0.63661977236f / (float)(sr * sr);  // density_vert.glsl:62
+#pragma unroll
+                        for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
+                            int m = oy0 + k - cy;
+                            if (m < -sr || m > sr) continue;
+                            float nm = 2.0f * (float)m / S + bias;
+                            float dist = ni * ni + nm * nm;
+                            if (dist > 1.0f) continue;  // density_frag.glsl:17
+                            float wgt = (1.0f - dist) * norm;
+                            acc[k].x += sx * wgt; acc[k].y += sy * wgt; acc[k].z += sz * wgt; acc[k].w += sw * wgt;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
+            int cy = oy0 + k;
+            if (cy < H && ox < W) acc[k] = __ldg(bins + (size_t)cy * W + ox);  // tonemap only: input is already an image
+        }
+    }
+
+    if (ox >= W) return;
+#pragma unroll
+    for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
+        int cy = oy0 + k;
+        if (cy >= H) continue;
+        float4 v = TONEMAP ? tonemap_pixel(acc[k], p) : acc[k];
+        size_t o = (size_t)cy * W + ox;
+        if (out_f4) out_f4[o] = v;
+        if (out_rgba8) out_rgba8[o] = make_uchar4((unsigned char)rintf(fminf(fmaxf(v.x, 0.f), 1.f) * 255.0f), (unsigned char)rintf(fminf(fmaxf(v.y, 0.f), 1.f) * 255.0f),
+                                                  (unsigned char)rintf(fminf(fmaxf(v.z, 0.f), 1.f) * 255.0f), (unsigned char)rintf(fminf(fmaxf(v.w, 0.f), 1.f) * 255.0f));
+    }
+}
+
+}  // namespace
+
+void seed_rng_states(uint4* states, std::size_t count, std::uint32_t seed_base, cudaStream_t s) {
+    if (!count) return;
+    seed_rng_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(states, count, seed_base);
+}
+
+void make_sample_points(float4* out, std::uint32_t count, cudaStream_t s) {
+    if (!count) return;
+    // src/hammersley.cpp:33-42
+    std::uint32_t max = count;
+    if (count % 2 != 0) { max = count - 1; max |= max >> 1; max |= max >> 2; max |= max >> 4; max |= max >> 8; max |= max >> 16; max++; }
+    float inv_max = 1.0f / max;
+    int bits = 0;
+    for (std::uint32_t v = max; v >>= 1;) bits++;
+    sample_points_kernel<<<(count + 255) / 256, 256, 0, s>>>(out, count, bits, inv_max);
+}
+
+void make_shuffle_buffers(std::uint32_t* out, std::uint32_t size, std::uint32_t count, std::uint64_t seed, cudaStream_t s) {
+    if (!size || !count) return;
+    int bits = 2;
+    while ((1ull << bits) < size) bits++;
+    dim3 grid((size + 255) / 256, count);
+    shuffle_kernel<<<grid, 256, 0, s>>>(out, size, bits, seed);
+}
+
+void animate(const float* fp, float* fp_inflated, int total_params, int temporal_samples, float temporal_sample_width,
+             const animate_xform* xforms_dev, int num_xforms, cudaStream_t s) {
+    animate_kernel<<<(temporal_samples + 31) / 32, 32, 0, s>>>(fp, fp_inflated, total_params, temporal_samples, temporal_sample_width, xforms_dev, num_xforms);
+}
+
+void density_thresholds(float* host_out, int estimator_radius, int estimator_min, float estimator_curve) {
+    const int R = estimator_radius > estimator_min ? estimator_radius : estimator_min;
+    host_out[0] = INFINITY;
+    for (int k = 1; k <= R; k++) {
+        // radius >= k  <=>  k <= estimator_min  or  estimator_radius / d^curve >= k
+        if (k <= estimator_min || !(estimator_curve > 0.0f)) { host_out[k] = INFINITY; continue; }
+        if (k > estimator_radius) { host_out[k] = 0.0f; continue; }
+        double t = std::pow((double)estimator_radius / (double)k, 1.0 / (double)estimator_curve);
+        host_out[k] = (float)(t * (1.0 + 1e-3));
+    }
+}
+
+void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, const density_params& p, const float* thresholds_dev,
+                     bool do_density, bool do_tonemap, cudaStream_t s) {
+    dim3 grid((p.W + DE_TILE_W - 1) / DE_TILE_W, (p.H + DE_TILE_H - 1) / DE_TILE_H);
+    dim3 block(DE_WARPS * 32);
+    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p, thresholds_dev);
+    else if (do_density) density_tonemap_kernel<true, false><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p, thresholds_dev);
+    else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p, thresholds_dev);
+}
+
+void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s) {
+    if (!count) return;
+    fixed_to_float_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(fixed, bins, count);
+}
+
+void downsample2x(const float4* in, float4* out, int W, int H, cudaStream_t s) {
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+    downsample2x_kernel<<<grid, block, 0, s>>>(in, out, W, H);
+}
+
+}  // namespace rfk::kernels

@@ -1,0 +1,44 @@
+// Launchers of the genome-independent kernels (static_kernels.cu, built by nvcc for sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace rfk::kernels {
+
+// src/flame.cpp:132-149 + src/util.hpp:90-95: states[i] = warmup_ctx(seed_base + i)
+void seed_rng_states(uint4* states, std::size_t count, std::uint32_t seed_base, cudaStream_t s);
+
+// src/hammersley.cpp:29-48 as a kernel (test/ABI surface; the chaos kernel computes its point inline)
+void make_sample_points(float4* out, std::uint32_t count, cudaStream_t s);
+
+// src/shuffle_buffers.cpp:9-52 as a kernel: `count` permutations of [0, size), reproducible from `seed`
+void make_shuffle_buffers(std::uint32_t* out, std::uint32_t size, std::uint32_t count, std::uint64_t seed, cudaStream_t s);
+
+struct animate_xform { int affine[6]; int rotation_frequency; };
+// shaders/templates/animate.tpl.glsl:18-96: per-temporal-sample parameter blocks
+void animate(const float* fp, float* fp_inflated, int total_params, int temporal_samples, float temporal_sample_width,
+             const animate_xform* xforms_dev, int num_xforms, cudaStream_t s);
+
+struct density_params {
+    int W, H;
+    int estimator_radius, estimator_min;  // density_vert.glsl:3-4 (radius already clamped to <= 100, main.cpp:502)
+    float estimator_curve;
+    float gamma, brightness, vibrancy, scale_constant;  // tonemap.glsl:13-16 (scale_constant = 10^-4, main.cpp:528)
+};
+// Density estimation (density_vert.glsl:26-63 + density_frag.glsl:9-19 + main.cpp:490-515) and/or tonemap
+// (tonemap.glsl:18-39) in one pass. out_f4 / out_rgba8 may each be null. thresholds: device array
+// [estimator_radius + 1] from density_thresholds().
+void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, const density_params& p, const float* thresholds_dev,
+                     bool do_density, bool do_tonemap, cudaStream_t s);
+// density d can only have radius >= k when d <= thresholds[k] (conservative; the kernel re-derives the exact radius)
+void density_thresholds(float* host_out, int estimator_radius, int estimator_min, float estimator_curve);
+
+// deterministic mode: bins += fixed * 2^-24, one thread per bin
+void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s);
+
+// 2x2 box average of a float4 image (config 3: 2x supersampled histogram -> image); W, H are the OUTPUT dims
+void downsample2x(const float4* in, float4* out, int W, int H, cudaStream_t s);
+
+}  // namespace rfk::kernels

@@ -1,0 +1,360 @@
+#include "variation_table.hpp"
+
+#include <stack>
+#include <stdexcept>
+
+#include "textutil.hpp"
+#include "yaml_lite.hpp"
+
+namespace rfk {
+
+namespace {
+
+std::string slot_str(int slot) { return "fp[" + std::to_string(slot) + "]"; }  // variation_table.cpp:21
+
+using adj_desc_t = std::map<std::string, std::set<std::string>>;
+
+// Depth-first post-order over the precalc dependency graph (variation_table.cpp:25-47).
+void order_recurse(const std::string& vertex, const adj_desc_t& adj, std::map<std::string, bool>& visited, std::stack<std::string>& stack) {
+    visited[vertex] = true;
+    for (const auto& con : adj.at(vertex))
+        if (!visited[con]) order_recurse(con, adj, visited, stack);
+    stack.push(vertex);
+}
+
+std::stack<std::string> get_ordering(const adj_desc_t& adj) {
+    std::stack<std::string> ordering;
+    std::map<std::string, bool> visited;
+    for (auto& [k, v] : adj) visited[k] = false;
+    for (auto& [v, a] : adj)
+        if (!visited[v]) order_recurse(v, adj, visited, ordering);
+    return ordering;
+}
+
+// $cCR -> affine slot C*2+R (variation_table.cpp:49-60); $pCR likewise for post (:62-73).
+void resolve_coefs(std::string& src, const std::array<int, 6>& slots, char prefix) {
+    for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 2; r++) {
+            std::string name = std::string(1, prefix) + std::to_string(c) + std::to_string(r);
+            src = replace_macro(src, name, slot_str(slots[c * 2 + r]));
+        }
+}
+
+bool is_linear_only(const flame_xform& x) {  // variation_table.cpp:85-87
+    return !x.post && x.variations.size() == 1 && x.variations.begin()->first == "linear";
+}
+
+// The reference's two "optimizers" (variation_table.cpp:78-169): returns {inlined, text}.
+std::pair<bool, std::string> make_xform_text(const flame_xform& x, const xform_slots& xmap, const flame_compiler& vt) {
+    if (is_linear_only(x)) {
+        std::string src = "$weight * vec2(fma($c00, v.x, fma($c10, v.y, $c20)), fma($c01, v.x, fma($c11, v.y, $c21)))";
+        src = replace_macro(src, "weight", slot_str(xmap.variations.at("linear")));
+        resolve_coefs(src, xmap.affine, 'c');
+        return {true, src};
+    }
+
+    std::string xform_result;
+    bool first_var = true;
+    std::string affine = "\tv.xy = vec2(fma($c00, v.x, fma($c10, v.y, $c20)), fma($c01, v.x, fma($c11, v.y, $c21)));\n";
+
+    for (auto& [var_name, weight] : x.variations) {
+        const auto& vd = vt.variation(var_name);
+        const std::string wslot = slot_str(xmap.variations.at(var_name));
+        std::string var_src;
+        var_src += "// variation: " + var_name + "\n";
+        if (!vd.source.empty()) var_src += replace_macro(vd.source, "weight", wslot) + "\n";
+
+        std::string weight_str = vd.flags.count("no_weight_mul") ? "" : "$weight *";
+
+        if (vd.flags.count("pre_xform")) {
+            affine += replace_macro(("v.xy += " + weight_str) + vd.result + ";", "weight", wslot) + "\n";
+        } else {
+            var_src += replace_macro((first_var ? "vec2 result = " + weight_str : "result += " + weight_str) + vd.result + ";", "weight", wslot) + "\n";
+            xform_result += var_src;
+            first_var = false;
+        }
+    }
+
+    for (auto& [p_name, val] : x.var_param) xform_result = replace_macro(xform_result, p_name, slot_str(xmap.param.at(p_name)));
+
+    // precalc macros in dependency order (variation_table.cpp:130-147)
+    auto macros = find_macros(xform_result);
+    std::erase_if(macros, [&vt](const std::string& name) { return !vt.is_common(name); });
+
+    adj_desc_t macro_adj;
+    for (auto& m : macros) {
+        auto deps = find_macros(vt.common(m));
+        for (auto& d : deps)
+            if (vt.is_common(d) && !macro_adj.count(d)) macro_adj[d] = find_macros(vt.common(m));
+        macro_adj[m] = find_macros(vt.common(m));
+    }
+
+    auto order = get_ordering(macro_adj);
+    while (order.size()) {
+        xform_result = "float " + order.top() + " = " + vt.common(order.top()) + ";\n" + xform_result;
+        order.pop();
+    }
+
+    xform_result = affine + xform_result;
+    resolve_coefs(xform_result, xmap.affine, 'c');
+
+    if (x.post) {
+        xform_result += "\tresult = vec2(fma($p00, result.x, fma($p10, result.y, $p20)), fma($p01, result.x, fma($p11, result.y, $p21)));\n";
+        resolve_coefs(xform_result, xmap.post, 'p');
+    }
+
+    xform_result = replace_all(xform_result, "\n", "\n\t");
+    xform_result = replace_all(xform_result, "$", "");
+    return {false, xform_result};
+}
+
+void default_replace_macros(std::string& str) {  // variation_table.cpp:174-180
+    str = replace_macro(str, "x", "v.x");
+    str = replace_macro(str, "y", "v.y");
+    str = replace_macro(str, "v", "v.xy");
+    str = replace_macro(str, "result", "result");
+}
+
+std::string xform_select_text(const buffer_map_t& map, bool cuda) {  // shaders/templates/xform_select.tpl.glsl
+    std::string s = cuda ? "__device__ __forceinline__ int get_xform_id(float ratio, const float* __restrict__ fp) {\n\n"
+                         : "int get_xform_id(float ratio) {\n\n";
+    const int n = (int)map.xforms.size();
+    for (int i = 0; i < n; i++) {
+        const std::string w = slot_str(map.xforms[i].weight);
+        if (i == 0) {
+            s += "\tfloat sum = " + w + ";\n\tif(sum >= ratio) return 0;\n";
+        } else if (i == n - 1) {
+            s += "\treturn " + std::to_string(i) + ";\n";
+        } else {
+            s += "\tsum += " + w + ";\n\tif(sum >= ratio) return " + std::to_string(i) + ";\n";
+        }
+    }
+    // a one-xform genome leaves the template without a final return; every pick is xform 0
+    if (cuda && n <= 1) s += "\treturn 0;\n";
+    s += "}";
+    return s;
+}
+
+enum class dialect { glsl, cuda };
+
+std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
+    const auto& buf_map = f.buffer_map();
+    std::string disp_func = d == dialect::glsl
+        ? std::string("vec4 dispatch(vec3 v, int xform){\n").append("switch(xform){\n")
+        : std::string("template <bool first_run>\n__device__ __forceinline__ vec4 dispatch(vec3 v, int xform, const float* __restrict__ fp, rfk_rng& rs){\n").append("switch(xform){\n");
+    int rf_counter = 0;
+
+    for (int i = -1; i < (int)f.xforms.size(); i++) {
+        if (i == -1 && !f.final_xform) continue;
+        const auto& xform = (i == -1) ? f.final_xform.value() : f.xforms.at(i);
+        const auto& xmap = (i == -1) ? buf_map.final_xform.value() : buf_map.xforms.at(i);
+
+        auto [inlined, xform_src] = make_xform_text(xform, xmap, vt);
+
+        std::string dispatch_invoke = "return vec4(" + std::string(inlined ? xform_src : "result") + ", mix(((first_run)? randf(): v.z), " +
+                                      slot_str(xmap.color) + ", " + slot_str(xmap.color_speed) + "), " + slot_str(xmap.opacity) + ");\n";
+        if (!inlined) dispatch_invoke = xform_src + dispatch_invoke;
+
+        if (d == dialect::cuda) {
+            dispatch_invoke = suffix_float_literals(dispatch_invoke);
+            dispatch_invoke = swizzles_to_calls(dispatch_invoke);
+            dispatch_invoke = sequence_randf(dispatch_invoke, rf_counter);
+        }
+
+        if (i + 1 == (int)f.xforms.size()) disp_func += "default: {\n" + dispatch_invoke + "\n}}\n";
+        else disp_func += "case " + std::to_string(i) + ": {\n" + dispatch_invoke + "\n}\n";
+    }
+    if (f.xforms.empty()) disp_func += "default: { return vec4(v.xy, v.z, 0.0" + std::string(d == dialect::cuda ? "f" : "") + "); }}\n";
+
+    std::string xid_func = xform_select_text(buf_map, d == dialect::cuda);
+
+    disp_func = replace_all(disp_func, "\n", "\n\t");
+    disp_func += "\n}";
+    if (d == dialect::cuda) return xid_func + "\n" + disp_func + "\n";
+    return xid_func + disp_func;
+}
+
+inline bool ident_char(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_'; }
+inline bool digit(char c) { return c >= '0' && c <= '9'; }
+
+}  // namespace
+
+// GLSL floating literals are single precision; unsuffixed they would be doubles in CUDA.
+std::string suffix_float_literals(const std::string& s) {
+    std::string out;
+    out.reserve(s.size() + 64);
+    std::size_t i = 0;
+    while (i < s.size()) {
+        char c = s[i];
+        // line comments pass through untouched
+        if (c == '/' && i + 1 < s.size() && s[i + 1] == '/') {
+            std::size_t nl = s.find('\n', i);
+            if (nl == std::string::npos) nl = s.size();
+            out.append(s, i, nl - i);
+            i = nl;
+            continue;
+        }
+        bool starts_number = (digit(c) || (c == '.' && i + 1 < s.size() && digit(s[i + 1]))) && (i == 0 || !ident_char(s[i - 1])) &&
+                             !(i > 0 && s[i - 1] == '.' && c != '.');
+        if (!starts_number) {
+            out += c;
+            i++;
+            continue;
+        }
+        std::size_t j = i;
+        bool is_float = false;
+        while (j < s.size() && digit(s[j])) j++;
+        if (j < s.size() && s[j] == '.') {
+            is_float = true;
+            j++;
+            while (j < s.size() && digit(s[j])) j++;
+        }
+        if (j < s.size() && (s[j] == 'e' || s[j] == 'E')) {
+            std::size_t k = j + 1;
+            if (k < s.size() && (s[k] == '+' || s[k] == '-')) k++;
+            if (k < s.size() && digit(s[k])) {
+                is_float = true;
+                while (k < s.size() && digit(s[k])) k++;
+                j = k;
+            }
+        }
+        out.append(s, i, j - i);
+        if (is_float) {
+            if (j < s.size() && (s[j] == 'f' || s[j] == 'F')) { out += 'f'; j++; }
+            else if (j + 1 < s.size() && (s[j] == 'l' || s[j] == 'L') && (s[j + 1] == 'f' || s[j + 1] == 'F')) { j += 2; }  // GLSL double suffix
+            else out += 'f';
+        }
+        i = j;
+    }
+    return out;
+}
+
+// `.yx` / `.xy` on an rvalue cannot be a data member in C++: they become calls. `v.xy`
+// (the particle position, an lvalue) stays a member of the CUDA-side vec3.
+std::string swizzles_to_calls(const std::string& s) {
+    std::string out;
+    out.reserve(s.size() + 16);
+    for (std::size_t i = 0; i < s.size(); i++) {
+        if (s[i] == '.' && i + 2 < s.size() && s[i + 1] == 'y' && s[i + 2] == 'x' && (i + 3 == s.size() || !ident_char(s[i + 3])) && i > 0 &&
+            (ident_char(s[i - 1]) || s[i - 1] == ')' || s[i - 1] == ']')) {
+            out += ".yx()";
+            i += 2;
+            continue;
+        }
+        out += s[i];
+    }
+    return out;
+}
+
+// GLSL leaves the evaluation order of operands unspecified; so does C++. A statement
+// that draws two or more random numbers gets its draws hoisted into declarations, in
+// textual order, so that every implementation consumes the stream identically.
+// Statements containing `?` keep their draws in place (a draw under a conditional
+// must stay conditional).
+std::string sequence_randf(const std::string& body, int& counter) {
+    static const std::string call = "randf()";
+    std::string out;
+    std::size_t start = 0;
+    auto flush = [&](std::size_t end) {  // [start, end) is one statement chunk, delimiter included
+        std::string chunk = body.substr(start, end - start);
+        std::size_t n = 0;
+        for (std::size_t p = chunk.find(call); p != std::string::npos; p = chunk.find(call, p + call.size())) n++;
+        if (n >= 2 && chunk.find('?') == std::string::npos) {
+            std::string decl = "float ";
+            std::string rewritten;
+            std::size_t p = 0, k = 0;
+            for (;;) {
+                std::size_t q = chunk.find(call, p);
+                if (q == std::string::npos) { rewritten.append(chunk, p, std::string::npos); break; }
+                rewritten.append(chunk, p, q - p);
+                std::string name = "_rf" + std::to_string(counter++);
+                rewritten += name;
+                decl += (k++ ? ", " : "") + name + " = randf()";
+                p = q + call.size();
+            }
+            // keep leading whitespace / comment lines in front of the declaration
+            std::size_t ins = 0;
+            for (;;) {
+                while (ins < rewritten.size() && (rewritten[ins] == ' ' || rewritten[ins] == '\t' || rewritten[ins] == '\n')) ins++;
+                if (rewritten.compare(ins, 2, "//") == 0) {
+                    std::size_t nl = rewritten.find('\n', ins);
+                    if (nl == std::string::npos) break;
+                    ins = nl + 1;
+                } else break;
+            }
+            out += rewritten.substr(0, ins) + decl + "; " + rewritten.substr(ins);
+        } else {
+            out += chunk;
+        }
+        start = end;
+    };
+    for (std::size_t i = 0; i < body.size(); i++) {
+        char c = body[i];
+        if (c == '/' && i + 1 < body.size() && body[i + 1] == '/') {  // skip comment text
+            std::size_t nl = body.find('\n', i);
+            if (nl == std::string::npos) break;
+            i = nl;
+            continue;
+        }
+        if (c == ';' || c == '{' || c == '}') flush(i + 1);
+    }
+    flush(body.size());
+    return out;
+}
+
+void flame_compiler::load_text(const std::string& yaml_text) {
+    auto defs = yaml::parse(yaml_text);
+
+    if (const auto* variations = defs.find("variations"); variations && variations->is_map()) {
+        for (auto& [name, def] : variations->entries) {
+            const auto* src_n = def.find("src");
+            const auto* res_n = def.find("result");
+            std::string src = src_n ? src_n->as_string("") : "";
+            default_replace_macros(src);
+            std::string result = res_n ? res_n->as_string("") : "";
+            default_replace_macros(result);
+
+            auto& var = vars_[name];
+            var = variation_definition{};
+            var.source = src;
+            var.result = result;
+
+            if (const auto* param = def.find("param"); param && param->is_map())
+                for (auto& [pname, unused] : param->entries) {
+                    var.param.push_back(pname);
+                    param_owners_[pname] = name;
+                }
+            if (const auto* flags = def.find("flags"); flags)
+                for (auto& item : flags->items) var.flags.insert(item.as_string());
+        }
+    }
+
+    if (const auto* common = defs.find("common"); common && common->is_map()) {
+        for (auto& [name, val] : common->entries) {
+            std::string src = val.as_string();
+            default_replace_macros(src);
+            common_[name] = src;
+        }
+    }
+}
+
+flame_compiler::flame_compiler(const std::string& path) {
+    bool ok = false;
+    std::string text = read_file(path, &ok);
+    if (!ok) throw std::runtime_error("flame_compiler: cannot read " + path);
+    load_text(text);
+}
+
+flame_compiler flame_compiler::from_text(const std::string& yaml_text) {
+    flame_compiler c{empty_tag{}};
+    c.load_text(yaml_text);
+    return c;
+}
+
+void flame_compiler::load_overlay_text(const std::string& yaml_text) { load_text(yaml_text); }
+
+std::string flame_compiler::compile_flame_xforms(const flame& f) const { return emit(f, *this, dialect::glsl); }
+
+std::string flame_compiler::compile_flame_cuda(const flame& f) const { return emit(f, *this, dialect::cuda); }
+
+}  // namespace rfk
