@@ -1,0 +1,29 @@
+// TEST INFRASTRUCTURE. C wrappers over reference code compiled from /root/reference
+// (see Makefile): make_sample_points (src/hammersley.cpp:29) and jsf32::warmup_ctx
+// (src/util.hpp:90). Used only to pin the oracle's restatement of those functions.
+#include <array>
+#include <cstdint>
+#include <vector>
+
+#include "util.hpp"  // the reference's header: jsf32
+
+std::vector<std::array<float, 4>> make_sample_points(std::uint32_t count);  // hammersley.cpp
+
+extern "C" {
+void ref_make_sample_points(std::uint32_t count, float* out) {
+    auto pts = make_sample_points(count);
+    for (std::uint32_t i = 0; i < count; i++)
+        for (int k = 0; k < 4; k++) out[4 * i + k] = pts[i][k];
+}
+void ref_jsf32_warmup(std::uint32_t seed, std::uint32_t* out4) {
+    jsf32::ctx c;
+    jsf32::warmup_ctx(c, seed);
+    out4[0] = c.a; out4[1] = c.b; out4[2] = c.c; out4[3] = c.d;
+}
+std::uint32_t ref_jsf32_ranval(std::uint32_t* state4) {
+    jsf32::ctx c{state4[0], state4[1], state4[2], state4[3]};
+    std::uint32_t r = jsf32::ranval(c);
+    state4[0] = c.a; state4[1] = c.b; state4[2] = c.c; state4[3] = c.d;
+    return r;
+}
+}

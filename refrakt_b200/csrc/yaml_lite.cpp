@@ -122,10 +122,11 @@ struct parser {
         std::size_t pending_blank = 0;
         while (pos < lines.size()) {
             const line& l = lines[pos];
-            std::string raw = rstrip(l.raw);
+            std::string raw = l.raw;  // literal blocks keep trailing spaces
+            while (!raw.empty() && raw.back() == '\r') raw.pop_back();
             std::size_t lead = 0;
             while (lead < raw.size() && raw[lead] == ' ') lead++;
-            bool blank = lead == raw.size();
+            bool blank = rstrip(raw).empty();
             if (blank) { pending_blank++; pos++; continue; }
             if (block_indent < 0) {
                 if ((int)lead <= parent_indent) break;

@@ -1,0 +1,168 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same
+seeded inputs. Thresholds are the ones BASELINE.md §5 states."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_PER_XFORM = 100_000
+
+
+def _inputs(seed, n, spread=1.0):
+    rng = np.random.default_rng(seed)
+    xyz = np.concatenate([rng.normal(0.0, spread, (n, 2)), rng.random((n, 1))], axis=1).astype(np.float32)
+    states = rng.integers(0, 2**32, (n, 4), dtype=np.uint64).astype(np.uint32)
+    return xyz, states
+
+
+def _rel_err(got, want):
+    d = np.linalg.norm(got[:, :2].astype(np.float64) - want[:, :2].astype(np.float64), axis=1)
+    return d / np.maximum(1.0, np.linalg.norm(want[:, :2].astype(np.float64), axis=1))
+
+
+def _nudge(xyz, k):
+    """inputs moved by k ulp in x and y"""
+    out = xyz.copy()
+    for _ in range(abs(k)):
+        out[:, :2] = np.nextafter(out[:, :2], np.float32(np.inf if k > 0 else -np.inf))
+    return out
+
+
+@pytest.mark.parametrize("xid", list(range(-1, 10)))
+def test_single_step_matches_oracle(gpu_ready, flame, oracle, xid):
+    """dispatch(v, xid): xy within 1e-5 relative, colour within 1e-5, opacity equal, RNG state bit-exact.
+    >= 99.9 % of vectors pass outright; every outlier passes against the oracle evaluated at an input
+    nudged by <= 2 ulp (discontinuous variations: rectangles, julia, julian)."""
+    xyz, states = _inputs(1000 + xid, N_PER_XFORM)
+    ids = np.full(N_PER_XFORM, xid, dtype=np.int32)
+    got, got_rng = flame.single_step(xyz, ids, states)
+    want, want_rng = oracle.single_step(xyz, ids, states)
+    assert np.array_equal(got_rng, want_rng)
+    finite = np.isfinite(want).all(axis=1)
+    assert finite.mean() > 0.999
+    assert np.array_equal(np.isfinite(got).all(axis=1), finite) or np.mean(np.isfinite(got).all(axis=1) == finite) > 0.9999
+    err = _rel_err(got, want)
+    bad = finite & ~(err <= 1e-5)
+    assert np.abs(got[finite, 2] - want[finite, 2]).max() <= 1e-5
+    assert np.array_equal(got[finite, 3], want[finite, 3])
+    assert bad.mean() <= 1e-3, "xform %d: %.4f%% of vectors outside 1e-5" % (xid, 100 * bad.mean())
+    if bad.any():
+        idx = np.nonzero(bad)[0]
+        best = np.full(idx.size, np.inf)
+        for k in (-2, -1, 1, 2):
+            alt, _ = oracle.single_step(_nudge(xyz[idx], k), ids[idx], states[idx])
+            best = np.minimum(best, _rel_err(got[idx], alt))
+        assert (best <= 1e-5).all(), "xform %d: %d outliers not explained by a 2-ulp nudge (worst %g)" % (xid, (best > 1e-5).sum(), best.max())
+
+
+def test_single_step_first_run_colour(gpu_ready, flame, oracle):
+    """first_run: the colour coordinate comes from randf() (variation_table.cpp:242)."""
+    xyz, states = _inputs(77, 20000)
+    ids = np.random.default_rng(5).integers(0, 10, 20000).astype(np.int32)
+    got, got_rng = flame.single_step(xyz, ids, states, first_run=True)
+    want, want_rng = oracle.single_step(xyz, ids, states, first_run=True)
+    assert np.array_equal(got_rng, want_rng)
+    finite = np.isfinite(want).all(axis=1)
+    assert np.abs(got[finite, 2] - want[finite, 2]).max() <= 1e-5
+    assert (_rel_err(got, want)[finite] <= 1e-5).mean() >= 0.999
+
+
+def test_single_step_custom_params(gpu_ready, flame, oracle):
+    """a caller-supplied fp[] block (one temporal sample's rotated affines) instead of the flame's own"""
+    fp = oracle.animate(8, 1.2 / 60)[1]
+    fp1024 = np.zeros(1024, dtype=np.float32)
+    fp1024[: fp.size] = fp
+    xyz, states = _inputs(31, 30000)
+    ids = np.random.default_rng(6).integers(-1, 10, 30000).astype(np.int32)
+    got, got_rng = flame.single_step(xyz, ids, states, fp=fp1024)
+    want, want_rng = oracle.single_step(xyz, ids, states, fp=fp1024)
+    assert np.array_equal(got_rng, want_rng)
+    finite = np.isfinite(want).all(axis=1)
+    assert (_rel_err(got, want)[finite] <= 1e-5).mean() >= 0.999
+
+
+def test_single_step_empty(gpu_ready, flame):
+    out, rng = flame.single_step(np.zeros((0, 3), np.float32), np.zeros(0, np.int32), np.zeros((0, 4), np.uint32))
+    assert out.shape == (0, 4) and rng.shape == (0, 4)
+
+
+def test_select_xform_bit_exact(gpu_ready, flame, oracle):
+    """get_xform_id: cumulative `sum >= ratio` in binary32, last xform is the fall-through"""
+    rng = np.random.default_rng(3)
+    fp = oracle.params()
+    cum = np.cumsum(fp[[0, 13, 30, 43, 59, 76, 92, 110, 125]].astype(np.float32), dtype=np.float32)
+    edge = np.concatenate([cum, np.nextafter(cum, np.float32(0)), np.nextafter(cum, np.float32(2)), [0.0, 1.0]]).astype(np.float32)
+    ratio = np.concatenate([rng.random(200000).astype(np.float32), edge])
+    got = flame.select_xform(ratio)
+    want = oracle.select_xform(ratio)
+    assert np.array_equal(got, want)
+    assert set(np.unique(got)) == set(range(10))
+
+
+@pytest.mark.parametrize("W,H", [(1280, 720), (3840, 2160), (15360, 8640), (7, 5)])
+def test_bucket_index_bit_exact(gpu_ready, flame, oracle, oracle_mod, W, H):
+    """(x, y, w) -> bin index incl. bounds test, opacity test and row flip; palette index — bit-exact"""
+    rng = np.random.default_rng(W)
+    n = 300000
+    xyzw = np.zeros((n, 4), dtype=np.float32)
+    xyzw[:, :2] = rng.normal(0, 1.6, (n, 2))
+    xyzw[:, 2] = rng.random(n)
+    xyzw[:, 3] = rng.choice([1.0, 0.5, 0.0, -1.0], n, p=[0.7, 0.2, 0.05, 0.05])
+    xyzw[:50, 0] = [np.nan, np.inf, -np.inf, 1e30, -1e30] * 10
+    xyzw[50:60, 2] = [0.0, 1.0, 1.0 / 255, 254.5 / 255, 2.0, -0.5, 1e-8, 0.999999, 0.5, 0.25]
+    ss = flame.screen_space_affine(W, H)
+    assert np.array_equal(ss.view(np.uint32), oracle_mod.screen_space_affine(oracle.flame, W, H).view(np.uint32))
+    gi, gp = flame.bucket_index(xyzw, ss, W, H)
+    wi, wp = oracle.bucket_index(xyzw, ss, W, H)
+    assert np.array_equal(gi, wi)
+    assert np.array_equal(gp, wp)
+    assert (gi >= 0).mean() > 0.2 and gi.max() < W * H and (gi[xyzw[:, 3] <= 0] == -1).all()
+
+
+def test_rng_seeding_bit_exact(gpu_ready, rfk, oracle):
+    """jsf32::warmup_ctx(state, slot) on the device (src/util.hpp:90-95); SURVEY Appendix B values"""
+    states = rfk.seed_rng_states(4096, 0)
+    assert [hex(v) for v in states[0]] == ["0x1b517aa6", "0xd3d55a3", "0x44d68d47", "0x7a484bc9"]
+    assert [hex(v) for v in states[1]] == ["0x927aed26", "0x131fa903", "0x750a9db8", "0xa696f285"]
+    for i in (0, 1, 2, 77, 4095):
+        assert np.array_equal(states[i], oracle.jsf32_warmup(i))
+    off = rfk.seed_rng_states(16, 2097151 - 3)
+    assert [hex(v) for v in off[3]] == ["0xf6e7ac5c", "0xe9cb99e", "0x73daf56", "0x299cd81f"]
+    rfk.set_sim_parameters(256 * 4, 4, 8, seed=5)
+    assert np.array_equal(rfk.copy_rng_states(0, 8), np.stack([oracle.jsf32_warmup(5 + i) for i in range(8)]))
+
+
+@pytest.mark.parametrize("count", [4096, 256, 1000, 777, 1])
+def test_sample_points_bit_exact(gpu_ready, rfk, oracle, count):
+    got = rfk.make_sample_points(count)
+    want = oracle.make_sample_points(count)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_shuffle_buffers_are_permutations(gpu_ready, rfk):
+    """every buffer is a permutation of [0, size); reproducible from the seed; buffers differ"""
+    for size in (4096, 1000, 256, 3):
+        a = rfk.make_shuffle_buffers(size, 16, seed=42)
+        assert np.array_equal(np.sort(a, axis=1), np.tile(np.arange(size, dtype=np.uint32), (16, 1)))
+        assert np.array_equal(a, rfk.make_shuffle_buffers(size, 16, seed=42))
+        if size > 16:
+            assert not np.array_equal(a[0], a[1])
+            assert not np.array_equal(a, rfk.make_shuffle_buffers(size, 16, seed=43))
+            # no fixed structure: displacement of a uniform permutation averages size/3
+            disp = np.abs(a.astype(np.int64) - np.arange(size)).mean()
+            assert 0.25 * size < disp < 0.42 * size
+
+
+def test_animate_matches_oracle(gpu_ready, flame, oracle):
+    """per-temporal-sample parameter blocks (animate.tpl.glsl): copies exact, rotated affines within 1e-6"""
+    for ts, width in ((512, 1.2 / 60), (32, 0.5), (64, 0.0)):
+        got = flame.animate(ts, width)
+        want = oracle.animate(ts, width)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+        rotated = set()
+        for m in oracle.slots7:
+            rotated.update(int(s) for s in m[:4])
+        keep = [i for i in range(got.shape[1]) if i not in rotated]
+        assert np.array_equal(got[:, keep], want[:, keep])
+    assert np.array_equal(flame.animate(64, 0.0)[5], oracle.params()[:169])

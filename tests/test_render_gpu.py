@@ -1,0 +1,224 @@
+"""GPU tests of the render path: density estimation + tonemap against the oracle on the same
+histogram, statistical parity of the chaos-game histogram, deterministic mode, the end-to-end frame."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TSS = 1.2 / 60.0
+
+
+def _synthetic_bins(W, H, seed, dense_frac=0.3, sparse_frac=0.3):
+    """float4 histogram with dense blobs (radius 0), sparse speckle (large radii) and empty areas"""
+    rng = np.random.default_rng(seed)
+    bins = np.zeros((H, W, 4), dtype=np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    blob = np.exp(-(((xx - W * 0.4) / (W * 0.15)) ** 2 + ((yy - H * 0.5) / (H * 0.2)) ** 2))
+    dens = np.floor(blob * 3000 * dense_frac * rng.random((H, W))).astype(np.float32)
+    speck = (rng.random((H, W)) < sparse_frac * 0.2).astype(np.float32) * rng.integers(1, 40, (H, W))
+    d = dens + speck
+    d[:, : W // 8] = 0
+    col = rng.random((H, W, 3)).astype(np.float32)
+    bins[..., :3] = col * d[..., None]
+    bins[..., 3] = d
+    # corners and edges populated: splats must clip at the image border
+    bins[0, 0] = [1, 2, 3, 1]
+    bins[H - 1, W - 1] = [2, 1, 1, 2]
+    bins[0, W - 1] = [5, 5, 5, 60]
+    return bins
+
+
+def _run_post(rfk, bins, p, fused=True):
+    H, W = bins.shape[:2]
+    d_bins = rfk.DeviceBuffer(bins.nbytes)
+    d_bins.upload(bins)
+    d_img = rfk.DeviceBuffer(bins.nbytes)
+    d_out = rfk.DeviceBuffer(bins.nbytes)
+    d_u8 = rfk.DeviceBuffer(W * H * 4)
+    if fused:
+        rfk.density_tonemap(d_bins.ptr, d_out.ptr, d_u8.ptr, W, H, p)
+        de = None
+    else:
+        rfk.density_estimate(d_bins.ptr, d_img.ptr, W, H, p)
+        rfk.tonemap(d_img.ptr, d_out.ptr, d_u8.ptr, W, H, p)
+        de = d_img.download(np.float32, (H, W, 4))
+    out = d_out.download(np.float32, (H, W, 4))
+    u8 = d_u8.download(np.uint8, (H, W, 4))
+    for b in (d_bins, d_img, d_out, d_u8):
+        b.free()
+    return de, out, u8
+
+
+@pytest.mark.parametrize("W,H,radius,min_,curve", [(200, 120, 11, 0, 0.6), (97, 61, 5, 0, 0.4), (64, 64, 11, 2, 0.6), (130, 70, 0, 0, 0.6), (75, 50, 20, 0, 1.0)])
+def test_density_tonemap_matches_oracle(gpu_ready, rfk, flame, oracle, oracle_mod, W, H, radius, min_, curve):
+    """same input histogram through the oracle (scatter form) and the GPU (gather form):
+    float image within 1e-4 (relative to the pixel's own scale), 8-bit within 1 LSB"""
+    bins = _synthetic_bins(W, H, seed=W * 7 + radius)
+    p = flame.post_params()
+    p.estimator_radius, p.estimator_min, p.estimator_curve = radius, min_, curve
+    de, out, u8 = _run_post(rfk, bins, p, fused=False)
+    want_de = oracle.density_estimate(bins, W, H, radius, min_, curve)
+    scale = np.maximum(1.0, np.abs(want_de))
+    assert (np.abs(de - want_de) / scale).max() <= 1e-4
+    want = oracle.tonemap(want_de, scale_constant=p.scale_constant)
+    assert np.abs(out - want).max() <= 1e-4
+    assert np.abs(u8.astype(int) - oracle_mod.to_rgba8(want).astype(int)).max() <= 1
+    _, fused_out, fused_u8 = _run_post(rfk, bins, p, fused=True)
+    assert np.array_equal(fused_out, out) and np.array_equal(fused_u8, u8)
+    assert (out[..., 3] == 1.0).all()
+    empty = want_de[..., 3] == 0
+    assert (out[empty][:, :3] == 0).all()
+
+
+def test_density_shift_and_gain(gpu_ready, rfk, flame):
+    """a single bin: radius-0 copy lands one pixel to the left; a radius-1 splat
+    has gain ~2.33 (item 11)"""
+    W, H = 33, 17
+    p = flame.post_params()
+    bins = np.zeros((H, W, 4), dtype=np.float32)
+    bins[H - 1 - 5, 10] = [100, 200, 300, 1000]  # histogram row by = H-1-cy
+    de, _, _ = _run_post(rfk, bins, p, fused=False)
+    assert np.array_equal(de[5, 9], bins[H - 1 - 5, 10]) and np.count_nonzero(de[..., 3]) == 1
+    p.estimator_radius, p.estimator_curve = 1, 0.0
+    bins[...] = 0
+    bins[H - 1 - 8, 20] = [1, 1, 1, 1]
+    de, _, _ = _run_post(rfk, bins, p, fused=False)
+    assert abs(de[..., 3].sum() - 2.326) < 0.01
+    ys, xs = np.nonzero(de[..., 3])
+    assert xs.min() >= 18 and xs.max() <= 20 and ys.min() >= 7 and ys.max() <= 9
+
+
+def _pooled_density(bins, k=4):
+    H, W = bins.shape[:2]
+    d = bins[: H // k * k, : W // k * k, 3].astype(np.float64)
+    return d.reshape(H // k, k, W // k, k).sum(axis=(1, 3))
+
+
+def _norm_l1(a, b):
+    return 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+
+
+def _gpu_histogram(rfk, flame, W, H, P, TS, passes, calls, seed, **options):
+    flame.set_options(fast_math=0, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=1, min_blocks=0)
+    if options:
+        flame.set_options(**options)
+    rfk.set_sim_parameters(P, TS, 64, seed=seed)
+    flame.warmup(16, TSS)
+    buf = rfk.DeviceBuffer(W * H * 16)
+    buf.zero_out()
+    binned = 0
+    for _ in range(calls):
+        binned += flame.draw_to_bins(buf.ptr, W * H, W, passes)
+    bins = buf.download(np.float32, (H, W, 4))
+    buf.free()
+    return bins, binned
+
+
+@pytest.fixture(scope="module")
+def oracle_hist(oracle):
+    """two independent oracle runs of the same small configuration"""
+    W, H, P, TS = 320, 180, 256 * 16 * 32, 32
+    out = []
+    for rng_seed, shuf, pas in ((0, 0x5EED0000, 0x5EED0001), (P, 0x1234, 0x99)):
+        oracle.set_sim_parameters(P, TS, 64, shuffle_seed=shuf, rng_seed=rng_seed, pass_seed=pas)
+        oracle.warmup(16, TSS)
+        bins = np.zeros((H, W, 4), dtype=np.float32)
+        binned = oracle.draw_to_bins(bins, W, 64, count_xforms=True)
+        out.append((bins, binned, oracle.xform_picks(10).astype(np.float64)))
+    return (W, H, P, TS, 64), out
+
+
+@pytest.mark.parametrize("mode", [dict(), dict(warp_aggregate=1), dict(per_lane_xform=1), dict(deterministic=1)])
+def test_histogram_statistical_parity(gpu_ready, rfk, flame, oracle_hist, mode):
+    """identical iteration counts, independent random streams (BASELINE.md §5 'histogram' row)"""
+    (W, H, P, TS, passes), ((b1, n1, p1), (b2, n2, p2)) = oracle_hist
+    bins, binned = _gpu_histogram(rfk, flame, W, H, P, TS, passes, 1, seed=12345, **mode)
+    total = P * passes
+    self_l1 = _norm_l1(_pooled_density(b1), _pooled_density(b2))
+    l1 = _norm_l1(_pooled_density(bins), _pooled_density(b1))
+    assert l1 <= max(0.02, 1.5 * self_l1), (l1, self_l1)
+    assert abs(binned / total - n1 / total) <= 0.002 * (n1 / total) + 3e-4, (binned / total, n1 / total, n2 / total)
+    assert abs(bins[..., 3].sum() - binned) <= 1e-3 * binned  # opacity 1: density channel counts samples
+    picks = flame.xform_counts(10).astype(np.float64)
+    assert picks.sum() == total
+    weights = flame.copy_flame_data_to_buffer()[[0, 13, 30, 43, 59, 76, 92, 110, 125, 141]]
+    draws = total if mode.get("per_lane_xform") else total / 32  # independent selections
+    assert np.abs(picks / picks.sum() - weights).max() <= max(1e-3, 4.5 * np.sqrt(0.25 / draws))
+    # colour: mean rgb per unit density agrees
+    c_gpu = bins[..., :3].sum(axis=(0, 1)) / bins[..., 3].sum()
+    c_ref = b1[..., :3].sum(axis=(0, 1)) / b1[..., 3].sum()
+    assert np.abs(c_gpu - c_ref).max() <= 0.01
+
+
+def test_deterministic_mode_is_bit_identical(gpu_ready, rfk, flame):
+    W, H, P, TS = 256, 144, 256 * 8 * 16, 16
+    a, na = _gpu_histogram(rfk, flame, W, H, P, TS, 48, 2, seed=9, deterministic=1)
+    b, nb = _gpu_histogram(rfk, flame, W, H, P, TS, 48, 2, seed=9, deterministic=1)
+    assert na == nb and np.array_equal(a, b)
+    c, nc = _gpu_histogram(rfk, flame, W, H, P, TS, 48, 2, seed=10, deterministic=1)
+    assert not np.array_equal(a, c)
+    # float accumulation of the same samples differs only by rounding order
+    d, nd = _gpu_histogram(rfk, flame, W, H, P, TS, 48, 2, seed=9, deterministic=0)
+    assert nd == na
+    assert np.abs(d[..., 3] - a[..., 3]).max() <= 1e-3 * max(1.0, a[..., 3].max())
+
+
+def test_draw_requires_warmup_and_tracks_state(gpu_ready, rfk, compiler):
+    from conftest import GENOME
+    f = rfk.Flame.load_flame(GENOME, compiler)
+    rfk.set_sim_parameters(256 * 4, 4, 8)
+    assert f.needs_warmup()
+    buf = rfk.DeviceBuffer(64 * 36 * 16)
+    buf.zero_out()
+    with pytest.raises(rfk.RefraktError):
+        f.draw_to_bins(buf.ptr, 64 * 36, 64, 4)
+    f.warmup(4, TSS)
+    assert not f.needs_warmup()
+    n = f.draw_to_bins(buf.ptr, 64 * 36, 64, 8)
+    assert 0 < n <= 256 * 4 * 8 and f.binned_total() == n
+    x = f.xform(0)
+    x.weight *= 2
+    f.set_xform(0, x)
+    assert f.needs_warmup()  # the UI forces warmup after an edit (main.cpp:397-409)
+    f.warmup(4, TSS)
+    rfk.set_sim_parameters(256 * 8, 8, 8)  # invalidates live flames (flame.cpp:153-157)
+    assert f.needs_warmup()
+    with pytest.raises(rfk.RefraktError):
+        rfk.set_sim_parameters(1000, 3, 8)  # particles per temporal sample not a multiple of 256
+    buf.free()
+
+
+def test_render_frame_end_to_end(gpu_ready, rfk, flame, oracle, oracle_mod):
+    """host-buffer frame: image statistically matches the oracle's frame of the same sample count"""
+    W, H, P, TS = 320, 180, 256 * 16 * 32, 32
+    flame.set_options(fast_math=0, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
+    rfk.set_sim_parameters(P, TS, 64, seed=777)
+    img = np.empty((H, W, 4), dtype=np.uint8)
+    fimg = np.empty((H, W, 4), dtype=np.float32)
+    _, stats = flame.render_frame(W, H, max_draw_calls=4, drawing_passes=64, rgba8_out=img, image_out=fimg)
+    assert stats.draw_calls == 4 and stats.iterations == 4 * 64 * P and 0 < stats.binned <= stats.iterations
+    assert np.array_equal(img, oracle_mod.to_rgba8(fimg))
+
+    def oracle_frame(rng_seed, shuf):
+        oracle.set_sim_parameters(P, TS, 64, shuffle_seed=shuf, rng_seed=rng_seed)
+        oracle.warmup(16, TSS)
+        bins = np.zeros((H, W, 4), dtype=np.float32)
+        for _ in range(4):
+            oracle.draw_to_bins(bins, W, 64)
+        return oracle_mod.to_rgba8(oracle.tonemap(oracle.density_estimate(bins, W, H)))
+
+    ref1, ref2 = oracle_frame(0, 1), oracle_frame(P, 2)
+
+    def psnr(a, b):
+        mse = np.mean((a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)) ** 2)
+        return 10 * np.log10(255.0**2 / mse)
+
+    self_psnr = psnr(ref1, ref2)
+    got = psnr(img, ref1)
+    assert got >= min(30.0, self_psnr - 1.0), (got, self_psnr)
+    mae = np.mean(np.abs(img[..., :3].astype(np.float64) - ref1[..., :3].astype(np.float64)))
+    self_mae = np.mean(np.abs(ref2[..., :3].astype(np.float64) - ref1[..., :3].astype(np.float64)))
+    assert mae <= max(2.0, 1.25 * self_mae), (mae, self_mae)
+    # the target-binned stopping rule of main.cpp:411
+    _, stats2 = flame.render_frame(W, H, target_binned=3 * W * H, drawing_passes=8)
+    assert stats2.binned >= 3 * W * H and stats2.binned - 3 * W * H < 8 * P
