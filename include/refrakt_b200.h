@@ -135,7 +135,9 @@ int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size);
 
 /* Options of the generated kernels (no reference counterpart). Changing them rebuilds the module. */
 typedef struct rfk_kernel_options {
-    int32_t fast_math;      /* SFU intrinsics (--use_fast_math); default 0: 1-2 ulp library functions */
+    int32_t math_mode;      /* 0: libdevice functions, IEEE division and sqrt. 1 (default): 2-ulp division/sqrt, range-reduced SFU
+                               sine/cosine, lg2/ex2 pow for small exponents - inside the 1e-5 single-step contract.
+                               2: --use_fast_math (outside the contract) */
     int32_t fmad;           /* FMA contraction; default 1 */
     int32_t per_lane_xform; /* 1: every particle picks its own xform (divergent). default 0: one pick per warp + on-chip re-deal */
     int32_t warp_aggregate; /* 1: match_any de-duplication of same-bin updates inside a warp */

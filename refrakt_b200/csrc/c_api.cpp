@@ -69,30 +69,14 @@ kernels::density_params to_density(const rfk_post_params& p, size_t W, size_t H)
     return d;
 }
 
-// thresholds table lives on the device for the duration of one call
-struct threshold_table {
-    float* dev = nullptr;
-    explicit threshold_table(const kernels::density_params& d) {
-        const int R = d.estimator_radius > d.estimator_min ? d.estimator_radius : d.estimator_min;
-        std::vector<float> host(R + 2, 0.0f);
-        kernels::density_thresholds(host.data(), d.estimator_radius, d.estimator_min, d.estimator_curve);
-        cuda_ok(cudaMalloc(&dev, host.size() * sizeof(float)), "cudaMalloc(thresholds)");
-        cuda_ok(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, current_stream()), "upload thresholds");
-        cuda_ok(cudaStreamSynchronize(current_stream()), "upload thresholds");
-    }
-    ~threshold_table() { cudaFree(dev); }
-};
-
 int run_post(const float* in, float* out_f4, uint8_t* out_rgba8, size_t W, size_t H, const rfk_post_params* p, bool density, bool tonemap) {
     if (!in || !p || W == 0 || H == 0 || W > 0x3fffffff || H > 0x3fffffff) throw std::invalid_argument("post: bad image arguments");
     if (!out_f4 && !out_rgba8) throw std::invalid_argument("post: no output buffer");
     auto d = to_density(*p, W, H);
-    threshold_table t(d);
-    kernels::density_tonemap(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out_f4), reinterpret_cast<uchar4*>(out_rgba8), d, t.dev, density, tonemap, current_stream());
+    kernels::density_tonemap(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out_f4), reinterpret_cast<uchar4*>(out_rgba8), d, density, tonemap, current_stream());
     count_launch(1);
     cuda_ok(cudaGetLastError(), "density_tonemap launch");
-    cuda_ok(cudaStreamSynchronize(current_stream()), "density_tonemap");
-    return RFK_OK;
+    return RFK_OK;  // stream-ordered: rfk_memcpy_to_host / rfk_synchronize wait for it
 }
 
 }  // namespace
@@ -350,15 +334,16 @@ int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size) {
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* o) {
     if (!f || !o) return fail(RFK_E_INVALID, "null argument");
     const auto& k = F(f)->options();
-    *o = rfk_kernel_options{k.fast_math, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks};
+    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks};
     return RFK_OK;
 }
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
     if (!f || !i) return fail(RFK_E_INVALID, "null argument");
     kernel_options k;
-    k.fast_math = i->fast_math != 0; k.fmad = i->fmad != 0; k.per_lane_xform = i->per_lane_xform != 0;
+    k.math_mode = i->math_mode; k.fmad = i->fmad != 0; k.per_lane_xform = i->per_lane_xform != 0;
     k.warp_aggregate = i->warp_aggregate != 0; k.deterministic = i->deterministic != 0; k.count_xforms = i->count_xforms != 0;
     k.min_blocks = i->min_blocks;
+    if (k.math_mode < 0 || k.math_mode > 2) return fail(RFK_E_INVALID, "math_mode must be 0, 1 or 2");
     if (k.count_xforms && F(f)->xforms.size() > 62) return fail(RFK_E_INVALID, "count_xforms supports at most 62 xforms");
     if (!F(f)->set_options(k)) return fail(RFK_E_CUDA, flame::last_error());
     return RFK_OK;
@@ -566,8 +551,7 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         rfk_flame_post_params(f, &pp);
         pp.scale_constant = (float)(1.0 / std::pow(10.0, (double)req->scale_constant_exp));
         auto d = to_density(pp, W, H);
-        threshold_table t(d);
-        kernels::density_tonemap(b.bins, b.image, b.rgba8, d, t.dev, true, true, s);
+        kernels::density_tonemap(b.bins, b.image, b.rgba8, d, true, true, s);
         count_launch(1);
         cuda_ok(cudaGetLastError(), "density_tonemap launch");
         cuda_ok(cudaEventRecord(b.ev[3], s), "event");

@@ -107,7 +107,6 @@ __device__ __forceinline__ float4 rfk_reduce_peers(unsigned int mask, unsigned i
 
 template <bool DRAW>
 __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
-    __shared__ float fp[RFK_TOTAL_PARAMS + 1];
     __shared__ float4 pal[256];
     __shared__ float ex_x[2][RFK_BLOCK], ex_y[2][RFK_BLOCK], ex_c[2][RFK_BLOCK];
 #if RFK_COUNT_XFORMS
@@ -120,7 +119,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     const unsigned int ts = blockIdx.x / blocks_per_ts;                  // gl_WorkGroupID.y
     const size_t slot = (size_t)blockIdx.x * RFK_BLOCK + tid;            // ts * ppt + gl_GlobalInvocationID.x
 
-    for (int i = tid; i < RFK_TOTAL_PARAMS; i += RFK_BLOCK) fp[i] = p.fp_inflated[(size_t)ts * RFK_TOTAL_PARAMS + i];
+    for (int i = tid; i < RFK_TOTAL_PARAMS; i += RFK_BLOCK) rfk_glsl::fp[i] = p.fp_inflated[(size_t)ts * RFK_TOTAL_PARAMS + i];
     if (DRAW) for (int i = tid; i < 256; i += RFK_BLOCK) pal[i] = p.palette[i];
 #if RFK_COUNT_XFORMS
     if (tid <= RFK_NUM_XFORMS) xcount[tid] = 0;
@@ -130,17 +129,31 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     float x, y, c;
     __syncthreads();
 
+#if !RFK_PER_LANE_XFORM && RFK_NUM_XFORMS <= 33
+    // xform_select.tpl.glsl as one vote: lane i keeps the i-th running sum (same binary32 additions, same
+    // order as the template), the first lane whose sum >= ratio names the xform, the last xform is the fall-through
+    float cum = fp[rfk_weight_slot[0]];
+    for (int i = 1; i < RFK_NUM_XFORMS - 1; i++)
+        if (i <= (int)lane) cum += fp[rfk_weight_slot[i]];
+    const bool cum_valid = (int)lane < RFK_NUM_XFORMS - 1;
+#endif
+
     unsigned int binned = 0;
     int parity = 0;
 
     auto pick_xform = [&]() -> int {
 #if RFK_PER_LANE_XFORM
-        return get_xform_id(rfk_randf(rs), fp);
+        return get_xform_id(rfk_randf(rs));
 #else
         float u = 0.0f;
         if (lane == 0) u = rfk_randf(rs);  // flame.glsl:51-53: the first thread of the group burns one draw
         u = __shfl_sync(0xffffffffu, u, 0);
-        return get_xform_id(u, fp);
+  #if RFK_NUM_XFORMS <= 33
+        unsigned int vote = __ballot_sync(0xffffffffu, cum_valid && cum >= u);
+        return vote ? __ffs(vote) - 1 : RFK_NUM_XFORMS - 1;
+  #else
+        return get_xform_id(u);
+  #endif
 #endif
     };
     auto deal = [&](int it) {
@@ -161,7 +174,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
         float r1 = rfk_randf(rs);
         vec2 sc = sincos(sqrtf(r1));
         float m = r0 * .1f * PI * 2.0f;
-        vec4 r = dispatch<true>(vec3(s.x + m * sc.x, s.y + m * sc.y, 0.0f), xid, fp, rs);
+        vec4 r = dispatch<true>(vec3(s.x + m * sc.x, s.y + m * sc.y, 0.0f), xid, rs);
         x = r.x; y = r.y; c = r.z;
         deal(-1);
     } else {
@@ -172,20 +185,22 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     for (int it = 0; it < p.num_iter; ++it) {
         const int xid = pick_xform();
 #if RFK_COUNT_XFORMS
+        if (DRAW) {  // picks of drawn iterations only (the read-out of main.cpp:595-611)
   #if RFK_PER_LANE_XFORM
-        atomicAdd(&xcount[xid], 1u);
+            atomicAdd(&xcount[xid], 1u);
   #else
-        if (lane == 0) atomicAdd(&xcount[xid], 32u);
+            if (lane == 0) atomicAdd(&xcount[xid], 32u);
   #endif
+        }
 #endif
-        vec4 r = dispatch<false>(vec3(x, y, c), xid, fp, rs);
+        vec4 r = dispatch<false>(vec3(x, y, c), xid, rs);
         x = r.x; y = r.y; c = r.z;  // flame.glsl:72
 
         if (DRAW) {
             float fx = r.x, fy = r.y, fc = r.z, fw = r.w;
 #if RFK_HAS_FINAL
             {   // src/flame.cpp:23: result = dispatch(result.xyz, -1) * vec4(1, 1, 1, result.w)
-                vec4 q = dispatch<false>(vec3(r.x, r.y, r.z), -1, fp, rs);
+                vec4 q = dispatch<false>(vec3(r.x, r.y, r.z), -1, rs);
                 fx = q.x; fy = q.y; fc = q.z; fw = q.w * r.w;
             }
 #endif
@@ -242,19 +257,40 @@ extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_draw(const __grid_constant__ rf
 // and parameter block — the single-step level of the parity contract.
 extern "C" __global__ void rfk_single_step(int n, const float* __restrict__ xyz, const int* __restrict__ xid, uint4* rng,
                                            const float* __restrict__ fp, int first_run, float4* out) {
+    for (int k = threadIdx.x; k < RFK_TOTAL_PARAMS; k += blockDim.x) rfk_glsl::fp[k] = fp[k];
+    __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     rfk_rng rs = rng[i];
     vec3 v(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-    vec4 r = first_run ? dispatch<true>(v, xid[i], fp, rs) : dispatch<false>(v, xid[i], fp, rs);
+    vec4 r = first_run ? dispatch<true>(v, xid[i], rs) : dispatch<false>(v, xid[i], rs);
     out[i] = make_float4(r.x, r.y, r.z, r.w);
     rng[i] = rs;
 }
 
 // Test hook: xform selection for caller-supplied ratios (xform_select.tpl.glsl).
 extern "C" __global__ void rfk_select_xform(int n, const float* __restrict__ ratio, const float* __restrict__ fp, int* out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = get_xform_id(ratio[i], fp);
+    for (int k = threadIdx.x; k < RFK_TOTAL_PARAMS; k += blockDim.x) rfk_glsl::fp[k] = fp[k];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float my_ratio = ratio[i < n ? i : n - 1];  // no early exit: the vote below needs whole warps
+    // both forms of the selection must agree: the template's if-chain and the hot kernels' vote
+    int chain = get_xform_id(my_ratio);
+    int result = chain;
+#if RFK_NUM_XFORMS <= 33
+    const int lane = threadIdx.x & 31;
+    float cum = rfk_glsl::fp[rfk_weight_slot[0]];
+    for (int k = 1; k < RFK_NUM_XFORMS - 1; k++)
+        if (k <= lane) cum += rfk_glsl::fp[rfk_weight_slot[k]];
+    int voted = RFK_NUM_XFORMS - 1;
+    for (int src = 0; src < 32; src++) {  // every lane's ratio in turn, so that each vote is warp-uniform
+        float u = __shfl_sync(0xffffffffu, my_ratio, src);
+        unsigned int vote = __ballot_sync(0xffffffffu, lane < RFK_NUM_XFORMS - 1 && cum >= u);
+        if (src == lane) voted = vote ? __ffs(vote) - 1 : RFK_NUM_XFORMS - 1;
+    }
+    if (voted != chain) result = -1000 - voted;
+#endif
+    if (i < n) out[i] = result;
 }
 
 struct rfk_bucket_params { float ss_affine[6]; int bin_w, bin_h; };

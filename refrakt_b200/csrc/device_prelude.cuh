@@ -8,6 +8,10 @@ namespace rfk_glsl {
 typedef unsigned int uint;
 typedef uint4 rfk_rng;  // (a, b, c, d) = local_random_state.xyzw (random.glsl:19-23)
 
+// flame.glsl:27 `shared float fp[1024]`: this CTA's temporal sample of the parameter buffer.
+// Namespace scope, so that every fp[k] of the generated code is one LDS with an immediate offset.
+__shared__ float fp[RFK_TOTAL_PARAMS + 1];
+
 struct vec2 {
     float x, y;
     vec2() = default;
@@ -65,15 +69,45 @@ static constexpr float PI = 3.141592653589793f;
 static constexpr float PI_2 = PI / 2.0f;  // used by some variations only
 static constexpr float EPS = (1e-10f);
 
+// RFK_MATH_MODE 0: libdevice functions (1-2 ulp), IEEE division and square root.
+// RFK_MATH_MODE 1: the same accuracy class against the 1e-5 parity contract at a fraction of the
+//   instructions: 2-ulp division / square root (compiler flags), sine and cosine on the SFU after a
+//   two-constant Cody-Waite reduction to [-pi, pi] (absolute error ~5e-7 for |x| < 1e5, libdevice
+//   beyond), pow through lg2/ex2 while |y| <= 16 and x >= 0 (relative error < 3e-6, libdevice otherwise).
+// RFK_MATH_MODE 2: --use_fast_math (SFU intrinsics with no range reduction; outside the parity contract).
+#if RFK_MATH_MODE == 1
+__device__ __forceinline__ float rfk_reduce_2pi(float v) {
+    float k = ::rintf(v * 0.15915494309189535f);
+    float r = ::fmaf(k, -6.2831854820251465f, v);
+    return ::fmaf(k, 1.7484555e-7f, r);
+}
+__device__ __forceinline__ float sin(float v) { return ::fabsf(v) < 1.0e5f ? ::__sinf(rfk_reduce_2pi(v)) : ::sinf(v); }
+__device__ __forceinline__ float cos(float v) { return ::fabsf(v) < 1.0e5f ? ::__cosf(rfk_reduce_2pi(v)) : ::cosf(v); }
+__device__ __forceinline__ void rfk_sincos(float v, float* s, float* c) {
+    if (::fabsf(v) < 1.0e5f) {
+        float r = rfk_reduce_2pi(v);
+        *s = ::__sinf(r);
+        *c = ::__cosf(r);
+    } else {
+        ::sincosf(v, s, c);
+    }
+}
+__device__ __forceinline__ float pow(float a, float b) {
+    if (a >= 0.0f && ::fabsf(b) <= 16.0f) return ::exp2f(b * ::__log2f(a));
+    return ::powf(a, b);
+}
+#else
 __device__ __forceinline__ float sin(float v) { return ::sinf(v); }
 __device__ __forceinline__ float cos(float v) { return ::cosf(v); }
+__device__ __forceinline__ void rfk_sincos(float v, float* s, float* c) { ::sincosf(v, s, c); }
+__device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
+#endif
 __device__ __forceinline__ float tan(float v) { return ::tanf(v); }
 __device__ __forceinline__ float sinh(float v) { return ::sinhf(v); }
 __device__ __forceinline__ float cosh(float v) { return ::coshf(v); }
 __device__ __forceinline__ float exp(float v) { return ::expf(v); }
 __device__ __forceinline__ float log(float v) { return ::logf(v); }
 __device__ __forceinline__ float sqrt(float v) { return ::sqrtf(v); }
-__device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
 __device__ __forceinline__ float atan(float a, float b) { return ::atan2f(a, b); }
 __device__ __forceinline__ float atan(float a) { return ::atanf(a); }
 __device__ __forceinline__ float acos(float v) { return ::acosf(v); }
@@ -98,15 +132,15 @@ __device__ __forceinline__ float mod(float a, float b) { return a - b * ::floorf
 __device__ __forceinline__ float dot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
 __device__ __forceinline__ float length(vec2 v) { return ::sqrtf(v.x * v.x + v.y * v.y); }
 
-__device__ __forceinline__ vec2 sin(vec2 v) { return vec2(::sinf(v.x), ::sinf(v.y)); }
-__device__ __forceinline__ vec2 cos(vec2 v) { return vec2(::cosf(v.x), ::cosf(v.y)); }
+__device__ __forceinline__ vec2 sin(vec2 v) { return vec2(sin(v.x), sin(v.y)); }
+__device__ __forceinline__ vec2 cos(vec2 v) { return vec2(cos(v.x), cos(v.y)); }
 __device__ __forceinline__ vec2 abs(vec2 v) { return vec2(::fabsf(v.x), ::fabsf(v.y)); }
 __device__ __forceinline__ vec2 mix(vec2 a, vec2 b, float t) { return vec2(mix(a.x, b.x, t), mix(a.y, b.y, t)); }
 
 // math.glsl:6-22
 __device__ __forceinline__ vec2 sincos(float v) {
     float s, c;
-    ::sincosf(v, &s, &c);
+    rfk_sincos(v, &s, &c);
     return vec2(s, c);
 }
 __device__ __forceinline__ vec2 sinhcosh(float v) { return vec2(::sinhf(v), ::coshf(v)); }
@@ -127,7 +161,8 @@ __device__ __forceinline__ uint rfk_ranval(rfk_rng& s) {
     return s.x;
 }
 __device__ __forceinline__ float rfk_randf(rfk_rng& s) {
-    return ::fminf(::fmaxf(__uint2float_rn(rfk_ranval(s)) / 4294967295.0f, 0.0f), 1.0f);
+    // clamp(float(u) / 4294967295.0f, 0, 1): the quotient is float(u) * 2^-32, already inside [0, 1]
+    return __uint2float_rn(rfk_ranval(s)) * 2.3283064365386963e-10f;
 }
 
 }  // namespace rfk_glsl

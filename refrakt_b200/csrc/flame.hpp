@@ -57,7 +57,7 @@ struct buffer_map_t {
 // Options of the generated chaos-game kernel (no reference counterpart: the GLSL
 // path has a single mode).
 struct kernel_options {
-    bool fast_math = false;       // SFU intrinsics instead of the 1-2 ulp library calls
+    int math_mode = 1;            // 0 libdevice + IEEE div/sqrt, 1 balanced (default, inside the 1e-5 contract), 2 --use_fast_math
     bool fmad = true;             // allow FMA contraction of a*b+c
     bool per_lane_xform = false;  // every particle picks its own xform (divergent); default one pick per warp
     bool warp_aggregate = false;  // match_any de-duplication of same-bin updates inside a warp

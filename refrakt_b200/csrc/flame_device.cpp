@@ -103,14 +103,15 @@ void count_launch(unsigned n) { g_sim.launches += n; }
 std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out) {
     {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
-        auto it = g_cubin_cache.find(source + (opt.fast_math ? "#F" : "") + (opt.fmad ? "" : "#M"));
+        auto it = g_cubin_cache.find(source + "#" + std::to_string(opt.math_mode) + (opt.fmad ? "" : "#M"));
         if (it != g_cubin_cache.end()) return it->second;
     }
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, source.c_str(), "rfk_chaos_game.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
         throw std::runtime_error("nvrtcCreateProgram failed");
     std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--generate-line-info"};
-    if (opt.fast_math) opts.push_back("--use_fast_math");
+    if (opt.math_mode == 2) opts.push_back("--use_fast_math");
+    if (opt.math_mode == 1) { opts.push_back("--prec-div=false"); opts.push_back("--prec-sqrt=false"); }
     if (!opt.fmad) opts.push_back("--fmad=false");
     nvrtcResult res = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
     std::size_t log_size = 0;
@@ -128,7 +129,7 @@ std::vector<char> compile_cubin(const std::string& source, const kernel_options&
     nvrtcGetCUBIN(prog, cubin.data());
     nvrtcDestroyProgram(&prog);
     std::lock_guard<std::mutex> lock(g_cache_mutex);
-    g_cubin_cache[source + (opt.fast_math ? "#F" : "") + (opt.fmad ? "" : "#M")] = cubin;
+    g_cubin_cache[source + "#" + std::to_string(opt.math_mode) + (opt.fmad ? "" : "#M")] = cubin;
     return cubin;
 }
 
@@ -191,6 +192,7 @@ void flame::rebuild_cuda_source() {
     s += "#define RFK_TOTAL_PARAMS " + std::to_string(buffer_map_.size) + "\n";
     s += "#define RFK_NUM_XFORMS " + std::to_string(n) + "\n";
     s += "#define RFK_HAS_FINAL " + std::to_string(final_xform ? 1 : 0) + "\n";
+    s += "#define RFK_MATH_MODE " + std::to_string(options_.math_mode) + "\n";
     s += "#define RFK_PER_LANE_XFORM " + std::to_string(options_.per_lane_xform ? 1 : 0) + "\n";
     s += "#define RFK_WARP_AGGREGATE " + std::to_string(options_.warp_aggregate ? 1 : 0) + "\n";
     s += "#define RFK_DETERMINISTIC " + std::to_string(options_.deterministic ? 1 : 0) + "\n";

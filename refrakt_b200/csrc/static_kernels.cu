@@ -143,8 +143,8 @@ constexpr int DE_TILE_W = 32, DE_ROWS_PER_WARP = 4, DE_WARPS = 8, DE_TILE_H = DE
 // rows, so dense regions (radius 0 everywhere) cost one 4-byte load per scanned bin.
 template <bool DENSITY, bool TONEMAP>
 __global__ void __launch_bounds__(DE_WARPS * 32) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
-                                                                       uchar4* __restrict__ out_rgba8, const density_params p,
-                                                                       const float* __restrict__ thresholds) {
+                                                                       uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
+    const float* thresholds = p.thresholds;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ox = blockIdx.x * DE_TILE_W + lane;
     const int oy0 = blockIdx.y * DE_TILE_H + warp * DE_ROWS_PER_WARP;
@@ -270,7 +270,7 @@ void animate(const float* fp, float* fp_inflated, int total_params, int temporal
     animate_kernel<<<(temporal_samples + 31) / 32, 32, 0, s>>>(fp, fp_inflated, total_params, temporal_samples, temporal_sample_width, xforms_dev, num_xforms);
 }
 
-void density_thresholds(float* host_out, int estimator_radius, int estimator_min, float estimator_curve) {
+static void density_thresholds(float* host_out, int estimator_radius, int estimator_min, float estimator_curve) {
     const int R = estimator_radius > estimator_min ? estimator_radius : estimator_min;
     host_out[0] = INFINITY;
     for (int k = 1; k <= R; k++) {
@@ -282,13 +282,13 @@ void density_thresholds(float* host_out, int estimator_radius, int estimator_min
     }
 }
 
-void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, const density_params& p, const float* thresholds_dev,
-                     bool do_density, bool do_tonemap, cudaStream_t s) {
+void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, density_params p, bool do_density, bool do_tonemap, cudaStream_t s) {
+    density_thresholds(p.thresholds, p.estimator_radius, p.estimator_min, p.estimator_curve);
     dim3 grid((p.W + DE_TILE_W - 1) / DE_TILE_W, (p.H + DE_TILE_H - 1) / DE_TILE_H);
     dim3 block(DE_WARPS * 32);
-    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p, thresholds_dev);
-    else if (do_density) density_tonemap_kernel<true, false><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p, thresholds_dev);
-    else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p, thresholds_dev);
+    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
+    else if (do_density) density_tonemap_kernel<true, false><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
+    else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
 }
 
 void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s) {

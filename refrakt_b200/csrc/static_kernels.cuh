@@ -26,14 +26,13 @@ struct density_params {
     int estimator_radius, estimator_min;  // density_vert.glsl:3-4 (radius already clamped to <= 100, main.cpp:502)
     float estimator_curve;
     float gamma, brightness, vibrancy, scale_constant;  // tonemap.glsl:13-16 (scale_constant = 10^-4, main.cpp:528)
+    // a bin of density d can only have radius >= k when d <= thresholds[k] (conservative pre-filter;
+    // the kernel re-derives the exact radius of every candidate); filled by density_tonemap()
+    float thresholds[102];
 };
 // Density estimation (density_vert.glsl:26-63 + density_frag.glsl:9-19 + main.cpp:490-515) and/or tonemap
-// (tonemap.glsl:18-39) in one pass. out_f4 / out_rgba8 may each be null. thresholds: device array
-// [estimator_radius + 1] from density_thresholds().
-void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, const density_params& p, const float* thresholds_dev,
-                     bool do_density, bool do_tonemap, cudaStream_t s);
-// density d can only have radius >= k when d <= thresholds[k] (conservative; the kernel re-derives the exact radius)
-void density_thresholds(float* host_out, int estimator_radius, int estimator_min, float estimator_curve);
+// (tonemap.glsl:18-39) in one pass. out_f4 / out_rgba8 may each be null.
+void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, density_params p, bool do_density, bool do_tonemap, cudaStream_t s);
 
 // deterministic mode: bins += fixed * 2^-24, one thread per bin
 void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s);

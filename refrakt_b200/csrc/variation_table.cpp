@@ -1,5 +1,6 @@
 #include "variation_table.hpp"
 
+#include <algorithm>
 #include <stack>
 #include <stdexcept>
 
@@ -116,7 +117,7 @@ void default_replace_macros(std::string& str) {  // variation_table.cpp:174-180
 }
 
 std::string xform_select_text(const buffer_map_t& map, bool cuda) {  // shaders/templates/xform_select.tpl.glsl
-    std::string s = cuda ? "__device__ __forceinline__ int get_xform_id(float ratio, const float* __restrict__ fp) {\n\n"
+    std::string s = cuda ? "__device__ __forceinline__ int get_xform_id(float ratio) {\n\n"
                          : "int get_xform_id(float ratio) {\n\n";
     const int n = (int)map.xforms.size();
     for (int i = 0; i < n; i++) {
@@ -141,7 +142,7 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
     const auto& buf_map = f.buffer_map();
     std::string disp_func = d == dialect::glsl
         ? std::string("vec4 dispatch(vec3 v, int xform){\n").append("switch(xform){\n")
-        : std::string("template <bool first_run>\n__device__ __forceinline__ vec4 dispatch(vec3 v, int xform, const float* __restrict__ fp, rfk_rng& rs){\n").append("switch(xform){\n");
+        : std::string("template <bool first_run>\n__device__ __forceinline__ vec4 dispatch(vec3 v, int xform, rfk_rng& rs){\n").append("switch(xform){\n");
     int rf_counter = 0;
 
     for (int i = -1; i < (int)f.xforms.size(); i++) {
@@ -170,7 +171,13 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
 
     disp_func = replace_all(disp_func, "\n", "\n\t");
     disp_func += "\n}";
-    if (d == dialect::cuda) return xid_func + "\n" + disp_func + "\n";
+    if (d == dialect::cuda) {
+        std::string slots = "__constant__ int rfk_weight_slot[" + std::to_string(std::max<std::size_t>(1, buf_map.xforms.size())) + "] = {";
+        for (std::size_t i = 0; i < buf_map.xforms.size(); i++) slots += (i ? ", " : "") + std::to_string(buf_map.xforms[i].weight);
+        if (buf_map.xforms.empty()) slots += "0";
+        slots += "};\n";
+        return slots + xid_func + "\n" + disp_func + "\n";
+    }
     return xid_func + disp_func;
 }
 

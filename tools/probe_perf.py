@@ -37,7 +37,8 @@ def main():
         ("min_blocks4", dict(min_blocks=4)),
         ("min_blocks6", dict(min_blocks=6)),
         ("warp_aggregate", dict(warp_aggregate=1)),
-        ("fast_math", dict(fast_math=1)),
+        ("math0_libdevice", dict(math_mode=0)),
+        ("math2_fast", dict(math_mode=2)),
         ("per_lane", dict(per_lane_xform=1)),
         ("deterministic", dict(deterministic=1)),
     ]
@@ -45,7 +46,7 @@ def main():
     if "--big" in sys.argv:
         sizes.append((15360, 8640))
     for name, opt in variants:
-        base = dict(fast_math=0, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
+        base = dict(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
         base.update(opt)
         t0 = time.time()
         flame.set_options(**base)
@@ -63,7 +64,7 @@ def main():
             out.append(rec)
             del bins
     # warm kernel (no histogram): the pure iteration rate
-    flame.set_options(fast_math=0, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
+    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
     torch.cuda.synchronize()
     t0 = time.time()
     flame.warmup(256, 1.2 / 60)
