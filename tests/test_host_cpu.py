@@ -1,0 +1,265 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol the header declares; genome
+parsing, buffer map, parameter buffer and generated GLSL match the oracle and SURVEY Appendix A/B;
+error behaviour of load_flame; NVRTC builds of the shipped genome and of every compile-clean variation."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import FIXTURES, GENOME, ROOT, VARIATIONS
+
+COMPILE_CLEAN = """linear sinusoidal spherical swirl horseshoe polar handkerchief heart disc spiral hyperbolic diamond ex julia bent
+waves fisheye popcorn exponential power cosine rings fan blob pdj fan2 rings2 eyefish bubble perspective noise julian juliascope blur
+gaussian_blur radial_blur pie ngon curl rectangles arch tangent square rays blade secant2 cross disc2 super_shape flower conic parabola
+boarders butterfly curve foci loonie exp log sin cos sinh pre_blur waves2 cylinder auger flux mobius""".split()
+BROKEN = "twintrian bent2 bipolar cell cpow edisc oscope coth".split()
+
+
+def test_abi_exports_every_declared_symbol(rfk):
+    header = open(os.path.join(ROOT, "include", "refrakt_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rfk_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) > 60
+    lib = rfk.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "library does not export " + name
+    assert declared == set(rfk.SIGNATURES), declared ^ set(rfk.SIGNATURES)
+    assert lib.rfk_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", rfk.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    exported = set(re.findall(r"\bT (rfk_[a-z0-9_]+)", out))
+    assert declared <= exported
+
+
+def test_library_has_no_libcuda_link_dependency(rfk):
+    """loads on a box without a GPU driver; GPU entry points fail loudly instead of falling back"""
+    out = subprocess.run(["ldd", rfk.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "libcuda.so" not in out and "libnvrtc" in out
+
+
+def test_variation_table(compiler, vt):
+    names = compiler.variations()
+    assert len(names) == 76 and names == sorted(names) and set(names) == set(vt.vars)
+    assert set(COMPILE_CLEAN) | set(BROKEN) == set(names)
+    for n in ("r", "rsq", "a", "phi", "sina", "cosa", "sinr", "cosr", "lr"):
+        assert compiler.is_common(n)
+    assert compiler.is_variation("julian") and not compiler.is_variation("julian_power")
+    assert compiler.is_param("julian_power") and compiler.param_owner("julian_power") == "julian"
+    assert compiler.get_parameters_for_variation("julian") == ["julian_power", "julian_dist"]  # document order
+    assert compiler.get_parameters_for_variation("linear") == []
+    assert compiler.get_parameters_for_variation("mobius") == vt.vars["mobius"].param
+    assert not compiler.is_param("weight") and not compiler.is_variation("coefs")
+    with pytest.raises(Exception):
+        compiler.get_parameters_for_variation("no_such_variation")
+
+
+def test_compiler_missing_file(rfk):
+    with pytest.raises(rfk.RefraktError):
+        rfk.FlameCompiler("/nonexistent/variations.yaml")
+
+
+def test_genome_fields(flame, oracle):
+    i, f = flame.info(), oracle.flame
+    assert (i.num_xforms, i.has_final_xform, i.param_count) == (10, 1, 169)
+    assert list(i.size) == [800, 592] == f.size
+    assert np.float32(i.scale) == f.scale and np.float32(i.rotate) == f.rotate
+    assert [np.float32(c) for c in i.center] == f.center
+    assert (i.estimator_min, i.estimator_radius) == (0, 11)  # estimator_minimum is not read (flame.cpp:171)
+    assert np.float32(i.estimator_curve) == np.float32(0.6) and i.gamma == 4.0 and i.vibrancy == 1.0
+    assert np.float32(i.brightness) == np.float32(29.718)
+    for k in list(range(10)) + [-1]:
+        x, ox = flame.xform(k), (f.final_xform if k == -1 else f.xforms[k])
+        assert [np.float32(v) for v in x.affine] == ox.affine
+        assert bool(x.has_post) == (ox.post is not None)
+        if ox.post is not None:
+            assert [np.float32(v) for v in x.post] == ox.post
+        assert flame.variations(k) == {n: float(v) for n, v in ox.variations.items()}
+        assert flame.params_of(k) == {n: float(v) for n, v in ox.var_param.items()}
+        assert (np.float32(x.weight), np.float32(x.color), np.float32(x.color_speed), np.float32(x.opacity)) == (ox.weight, ox.color, ox.color_speed, ox.opacity)
+        assert np.float32(x.rotation_frequency) == ox.rotation_frequency
+    assert flame.xform(-1).weight == 0.0 and flame.xform(-1).rotation_frequency == 0.0
+    assert flame.xform(2).rotation_frequency == 1.0  # animate="0.265579" > 0
+    pal = flame.palette()
+    assert np.array_equal(pal, f.palette)
+    assert pal[0].tolist() == [134 / 256.0, 181 / 256.0, 109 / 256.0, 1.0]  # stoi truncation (flame.cpp:217)
+
+
+def test_buffer_map_matches_survey_appendix_a(flame, oracle):
+    import json
+    bm = json.loads(flame.buffer_map_json())
+    assert bm == oracle.flame.buffer_map
+    assert bm["size"] == 169
+    starts = [x["meta"]["start"] for x in bm["xforms"]]
+    assert starts == [0, 13, 30, 43, 59, 76, 92, 110, 125, 141] and bm["final_xform"]["meta"]["start"] == 153
+    assert bm["xforms"][6]["post"] == list(range(99, 105)) and bm["xforms"][6]["variations"] == {"bubble": 105}
+    assert bm["xforms"][4]["variations"] == {"julian": 66, "rectangles": 67}
+    assert bm["xforms"][4]["param"] == {"julian_dist": 68, "julian_power": 69, "rectangles_x": 70, "rectangles_y": 71}
+    assert bm["final_xform"]["variations"] == {"bubble": 160, "linear": 161, "rectangles": 162}
+    assert [bm["xforms"][9][k] for k in ("color", "color_speed", "opacity", "rotation_frequency")] == [149, 150, 151, 152]
+
+
+def test_parameter_buffer_bit_exact(flame, oracle):
+    got, want = flame.copy_flame_data_to_buffer(), oracle.params()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    w = got[[0, 13, 30, 43, 59, 76, 92, 110, 125, 141]]
+    assert abs(w.sum() - 1.0) < 1e-6 and abs(w[4] - 0.3959) < 1e-4  # normalised weights (flame.cpp:78-82)
+    assert got[153] == 0.0  # final xform weight 0 / sum
+
+
+def test_generated_glsl_is_the_reference_text(flame, oracle):
+    """the product's compile_flame_xforms output equals the oracle's restatement character for character,
+    and carries the landmarks of SURVEY Appendix A"""
+    g = flame.glsl_source()
+    assert g == oracle.glsl
+    assert "case -1: {" in g and "default: {" in g and g.count("case ") == 10
+    assert "float a = atan(v.x, v.y);\n\t\tfloat r = length(v.xy);" in g  # precalcs in dependency/alphabetical order
+    assert "vec2 result = fp[7] *(randf() + randf() + randf() + randf() - 2.0) * sincos(randf() * 2.0 * PI).yx;" in g
+    assert "v.x + fp[16] * sin(v.y/(fp[18] * fp[18] + EPS))," in g  # waves reads this xform's affine slots
+    assert "return vec4(fp[148] * vec2(fma(fp[142], v.x, fma(fp[144], v.y, fp[146])), fma(fp[143], v.x, fma(fp[145], v.y, fp[147]))), mix(((first_run)? randf(): v.z), fp[149], fp[150]), fp[151]);" in g
+    assert "result = vec2(fma(fp[99], result.x, fma(fp[101], result.y, fp[103])), fma(fp[100], result.x, fma(fp[102], result.y, fp[104])));" in g
+    assert "if(sum >= ratio) return 8;\n\treturn 9;" in g
+
+
+def test_cuda_dialect_rewrites(flame):
+    c = flame.cuda_source()
+    assert "2.0f * PI" in c and ".yx()" in c and "fp[163] == 0)" in c
+    assert re.search(r"float _rf0 = randf\(\), _rf1 = randf\(\), _rf2 = randf\(\), _rf3 = randf\(\), _rf4 = randf\(\); vec2 result = fp\[7\] \*\(_rf0 \+ _rf1 \+ _rf2 \+ _rf3 - 2.0f\) \* sincos\(_rf4 \* 2.0f \* PI\)\.yx\(\);", c)
+    assert "((first_run)? randf(): v.z)" in c  # a conditional draw stays conditional
+    assert not re.search(r"(?<![\w.])\d+\.\d+(?![\dfeE])", c.split("namespace rfk_glsl {\n#define randf()")[1].split("#undef randf")[0])
+    assert "__constant__ int rfk_weight_slot[10] = {0, 13, 30, 43, 59, 76, 92, 110, 125, 141};" in c
+
+
+@pytest.mark.parametrize("W,H,hexes", [
+    (1280, 720, "c2f6ebbd 4367c677 c367c677 c2f6ebbd 4420f3fb 43a2de80"),
+    (3840, 2160, "c3b930ce 442dd4d9 c42dd4d9 c3b930ce 44f16df8 44744dc1"),
+    (7680, 4320, "c43930ce 44add4d9 c4add4d9 c43930ce 45716df8 44f44dc1"),
+    (15360, 8640, "c4b930ce 452dd4d9 c52dd4d9 c4b930ce 45f16df8 45744dc1")])
+def test_screen_space_affine_golden(flame, oracle, oracle_mod, W, H, hexes):
+    """SURVEY Appendix B (computed from the reference's flame.hpp:97-128 + flame.cpp:289-296)"""
+    got = flame.screen_space_affine(W, H)
+    assert ["%08x" % v for v in got.view(np.uint32)] == hexes.split()
+    assert np.array_equal(got.view(np.uint32), oracle_mod.screen_space_affine(oracle.flame, W, H).view(np.uint32))
+
+
+def test_affine_helpers_match_oracle(rfk, oracle_mod):
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        a = rng.normal(0, 2, 6).astype(np.float32)
+        deg, s, t = np.float32(rng.uniform(-720, 720)), np.float32(rng.uniform(0.1, 300)), rng.normal(0, 3, 2).astype(np.float32)
+        assert np.array_equal(rfk.rotate_affine(a, deg).view(np.uint32), np.array(oracle_mod.rotate_affine(a, deg), dtype=np.float32).view(np.uint32))
+        assert np.array_equal(rfk.scale_affine(a, s).view(np.uint32), np.array(oracle_mod.scale_affine(a, s), dtype=np.float32).view(np.uint32))
+        assert np.array_equal(rfk.translate_affine(a, t).view(np.uint32), np.array(oracle_mod.translate_affine(a, t), dtype=np.float32).view(np.uint32))
+
+
+def test_rotate_xforms_is_the_per_frame_animation_step(rfk, compiler, oracle_mod):
+    f = rfk.Flame.load_flame(GENOME, compiler)
+    before = [np.array(f.xform(k).affine, dtype=np.float32) for k in range(10)]
+    f.rotate_xforms(18.0 / 60.0)  # DEGREES_PER_SECOND * dt, main.cpp:224, :383-395
+    for k in range(10):
+        want = np.array(oracle_mod.rotate_affine(before[k], np.float32(18.0 / 60.0) * np.float32(f.xform(k).rotation_frequency)), dtype=np.float32)
+        assert np.array_equal(np.array(f.xform(k).affine, dtype=np.float32).view(np.uint32), want.view(np.uint32))
+    assert f.needs_warmup()
+
+
+GENOME_TEMPLATE = """<flame name="t" size="640 480" center="0 0" scale="120" rotate="0" brightness="4" gamma="4" vibrancy="1"
+ estimator_radius="9" estimator_curve="0.4">
+%s
+ <color index="0" rgb="255 0 0"/><color index="255" rgb="0 0 255"/>
+</flame>"""
+
+
+def test_load_flame_failures(rfk, compiler, tmp_path):
+    assert rfk.Flame.load_flame(str(tmp_path / "missing.flam3"), compiler) is None
+    assert "cannot read" in rfk.Flame.last_error()
+    bad = GENOME_TEMPLATE % '<xform weight="1" color="0" linear="1" not_a_variation="2" coefs="1 0 0 1 0 0" opacity="1"/>'
+    assert rfk.Flame.load_flame_string(bad, compiler) is None
+    assert "Unknown attribute not_a_variation" in rfk.Flame.last_error()  # flame.cpp:196
+    assert rfk.Flame.load_flame_string("<flame><xform weight=1/></flame>", compiler) is None  # malformed XML
+    assert rfk.Flame.load_flame_string(GENOME_TEMPLATE % "", compiler) is None  # no xforms
+    # a variation parameter missing from the XML leaves a bare identifier behind: compile failure
+    noparam = GENOME_TEMPLATE % '<xform weight="1" color="0" julian="1" coefs="1 0 0 1 0 0" opacity="1"/>'
+    assert rfk.Flame.load_flame_string(noparam, compiler) is None
+    assert "julian_power" in rfk.Flame.last_error()
+    # one of the variations that do not compile in the reference's table either
+    broken = GENOME_TEMPLATE % '<xform weight="1" color="0" oscope="1" coefs="1 0 0 1 0 0" opacity="1"/>'
+    assert rfk.Flame.load_flame_string(broken, compiler) is None
+
+
+def test_field_edits(rfk, compiler):
+    f = rfk.Flame.load_flame(GENOME, compiler)
+    x = f.xform(3)
+    x.color_speed = 0.25
+    f.set_xform(3, x)
+    assert f.xform(3).color_speed == 0.25 and f.copy_flame_data_to_buffer()[56] == np.float32(0.25)
+    f.set_variation(4, "julian", 0.5)
+    f.set_param(4, "julian_power", 3.0)
+    buf = f.copy_flame_data_to_buffer()
+    assert buf[66] == 0.5 and buf[69] == 3.0
+    with pytest.raises(rfk.RefraktError):
+        f.set_variation(4, "swirl", 1.0)  # structure is fixed after load
+    x = f.xform(6)
+    x.has_post = 0
+    with pytest.raises(rfk.RefraktError):
+        f.set_xform(6, x)
+    with pytest.raises(rfk.RefraktError):
+        f.xform(10)
+    i = f.info()
+    i.estimator_radius = 500
+    f.set_info(i)
+    assert f.post_params().estimator_radius == 100  # main.cpp:502
+    assert f.post_params().scale_constant == np.float32(1e-4)
+
+
+def test_shipped_genome_cubin_is_sm100_with_vector_reductions(flame, tmp_path):
+    """NVRTC builds the kernels for sm_100a without a GPU; the histogram update is one REDG.E.ADD.F32x4"""
+    path = tmp_path / "k.cubin"
+    path.write_bytes(flame.cubin())
+    elf = subprocess.run(["cuobjdump", "-elf", str(path)], stdout=subprocess.PIPE, text=True).stdout
+    assert "sm_100" in elf
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "rfk_draw", str(path)], stdout=subprocess.PIPE, text=True).stdout
+    assert "RED.E.ADD.F32x4" in sass.replace("REDG", "RED") or "REDG.E.ADD.F32x4" in sass
+    assert "LDL" not in sass or sass.count("LDL") < 80  # no register spilling in the hot loop
+    res = subprocess.run(["cuobjdump", "-res-usage", str(path)], stdout=subprocess.PIPE, text=True).stdout
+    m = re.search(r"Function rfk_draw:\s*\n\s*REG:(\d+)", res)
+    assert m and int(m.group(1)) <= 64
+
+
+def _xform_xml(names, vt, rng):
+    attrs = []
+    for n in names:
+        attrs.append('%s="%.4f"' % (n, rng.uniform(0.1, 0.9)))
+        for p in vt.vars[n].param:
+            attrs.append('%s="%.4f"' % (p, rng.uniform(0.5, 3.0)))
+    coefs = " ".join("%.4f" % v for v in rng.normal(0, 0.6, 6))
+    return '<xform weight="%.3f" color="%.3f" color_speed="0.5" animate="1" %s coefs="%s" opacity="1"/>' % (rng.uniform(0.2, 1), rng.random(), " ".join(attrs), coefs)
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_every_compile_clean_variation_builds(rfk, compiler, vt, oracle_mod, chunk):
+    """all 68 variations of SURVEY Appendix C that compile in the reference also compile here (CUDA dialect, NVRTC,
+    sm_100a) and in the oracle (g++), with identical GLSL text"""
+    rng = np.random.default_rng(chunk)
+    names = COMPILE_CLEAN[chunk::6]
+    xforms = [_xform_xml(names[i:i + 3], vt, rng) for i in range(0, len(names), 3)]
+    xml = GENOME_TEMPLATE % "\n".join(xforms)
+    f = rfk.Flame.load_flame_string(xml, compiler)
+    assert f is not None, rfk.Flame.last_error()
+    assert len(f.cubin()) > 1000
+    of = oracle_mod.load_flame_string(xml, vt)
+    assert f.glsl_source() == oracle_mod.compile_flame_xforms(of, vt)
+    assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(of).view(np.uint32))
+    oracle_mod.Oracle(of, vt)  # builds
+
+
+def test_gpu_entry_points_fail_loudly_without_a_device(rfk, flame):
+    """no CPU fallback: on a box without CUDA the run entry points raise instead of computing elsewhere"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(rfk.RefraktError):
+        rfk.set_sim_parameters(256 * 4, 4, 8)
+    with pytest.raises(rfk.RefraktError):
+        flame.single_step(np.zeros((1, 3), np.float32), np.zeros(1, np.int32), np.zeros((1, 4), np.uint32))
+    with pytest.raises(rfk.RefraktError):
+        flame.render_frame(64, 64, max_draw_calls=1)

@@ -1,0 +1,89 @@
+"""The oracle against every pin that exists for it (the reference has no tests of its own):
+SURVEY Appendix B values, and the two reference functions that compile from /root/reference
+(oracle/Makefile -> oracle/_ref/libref_pins.so)."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+PINS = os.path.join(ROOT, "oracle", "_ref", "libref_pins.so")
+
+
+def test_jsf32_appendix_b(oracle):
+    assert ["%08x" % v for v in oracle.jsf32_warmup(0)] == ["1b517aa6", "0d3d55a3", "44d68d47", "7a484bc9"]
+    assert ["%08x" % v for v in oracle.jsf32_warmup(1)] == ["927aed26", "131fa903", "750a9db8", "a696f285"]
+    assert ["%08x" % v for v in oracle.jsf32_warmup(2097151)] == ["f6e7ac5c", "0e9cb99e", "073daf56", "299cd81f"]
+
+
+def test_hammersley_appendix_b(oracle):
+    p = oracle.make_sample_points(4096)
+    assert p[0].tolist() == [-1.0, -1.0, 0.0, 0.0]
+    assert p[1, 0] == np.float32(-0.999511719) and p[1, 1] == 0.0
+    assert p[2].tolist()[:2] == [np.float32(-0.999023438), -0.5] and p[3, 1] == 0.5
+    assert p[4095, 0] == p[4095, 1] == np.float32(0.999511719)
+
+
+def test_device_randf_semantics(oracle):
+    """random.glsl:29-41: returns `a` after the update; randf = float(u) * 2^-32 in [0, 1]"""
+    state = oracle.jsf32_warmup(7)
+    vals, after = oracle.device_randf(state, 1000)
+    assert vals.min() >= 0.0 and vals.max() <= 1.0 and 0.45 < vals.mean() < 0.55
+    # first draw by hand
+    a, b, c, d = (int(v) for v in state)
+    rot = lambda x, k: ((x << k) | (x >> (32 - k))) & 0xFFFFFFFF
+    e = (a - rot(b, 27)) & 0xFFFFFFFF
+    a2 = b ^ rot(c, 17)
+    assert vals[0] == np.float32(np.float32(a2) / np.float32(4294967295.0))
+
+
+@pytest.mark.skipif(not os.path.exists(PINS), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_restatement_matches_reference_compiled_pins(oracle):
+    ref = ctypes.CDLL(PINS)
+    for seed in (0, 1, 2, 12345, 2097151, 0xFFFFFFFF):
+        out = np.zeros(4, dtype=np.uint32)
+        ref.ref_jsf32_warmup(ctypes.c_uint32(seed), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+        assert np.array_equal(out, oracle.jsf32_warmup(seed))
+    for count in (4096, 256, 1000, 777, 2, 1):
+        out = np.zeros((count, 4), dtype=np.float32)
+        ref.ref_make_sample_points(ctypes.c_uint32(count), out.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        assert np.array_equal(out.view(np.uint32), oracle.make_sample_points(count).view(np.uint32))
+
+
+def test_golden_single_step_vectors(oracle):
+    """committed fixture (tests/golden/make_golden.py): guards the oracle itself against drift"""
+    path = os.path.join(GOLDEN, "single_step_electricsheep.npz")
+    g = np.load(path)
+    out, rng = oracle.single_step(g["xyz"], g["xid"], g["rng_in"])
+    assert np.array_equal(rng, g["rng_out"])
+    np.testing.assert_allclose(out, g["out"], rtol=2e-6, atol=2e-7)
+
+
+def test_golden_density_tonemap(oracle):
+    g = np.load(os.path.join(GOLDEN, "density_tonemap_small.npz"))
+    H, W = g["bins"].shape[:2]
+    de = oracle.density_estimate(g["bins"], W, H, int(g["radius"]), int(g["min"]), float(g["curve"]))
+    np.testing.assert_allclose(de, g["de"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(oracle.tonemap(de, scale_constant=1e-4), g["tonemapped"], rtol=1e-5, atol=1e-6)
+    # Appendix D: kernel gain by radius for an isolated bin
+    for r, gain in ((1, 2.326), (2, 1.600), (5, 1.214), (11, 1.093)):
+        b = np.zeros((40, 40, 4), dtype=np.float32)
+        b[20, 20] = 1.0
+        out = oracle.density_estimate(b, 40, 40, r, 0, 0.0)
+        assert abs(out[..., 3].sum() - gain) < 2e-3
+
+
+def test_oracle_render_is_self_consistent(oracle):
+    """sequential oracle: counter equals the density sum (opacity 1), in-bounds fraction ~0.81, warmup leaves no NaNs"""
+    oracle.set_sim_parameters(256 * 2 * 8, 8, 16)
+    oracle.warmup(16, 1.2 / 60)
+    parts = oracle.particles()
+    assert np.isfinite(parts).mean() > 0.999
+    bins = np.zeros((90, 160, 4), dtype=np.float32)
+    n = oracle.draw_to_bins(bins, 160, 32, count_xforms=True)
+    assert n == int(round(float(bins[..., 3].sum())))
+    assert 0.7 < n / (256 * 2 * 8 * 32) < 0.9
+    assert oracle.xform_picks(10).sum() == 256 * 2 * 8 * 32
