@@ -9,7 +9,10 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <set>
 #include <stdexcept>
@@ -106,8 +109,21 @@ std::vector<char> compile_cubin(const std::string& source, const kernel_options&
         auto it = g_cubin_cache.find(source + "#" + std::to_string(opt.math_mode) + (opt.fmad ? "" : "#M"));
         if (it != g_cubin_cache.end()) return it->second;
     }
+    // RFK_SOURCE_DUMP_DIR: keep the generated translation unit on disk under the name the line info refers to
+    // (lets `ncu --import-source on` and cuobjdump map SASS back to the generated code)
+    std::string unit_name = "rfk_chaos_game.cu";
+    if (const char* dir = std::getenv("RFK_SOURCE_DUMP_DIR")) {
+        std::size_t h = std::hash<std::string>{}(source);
+        char tag[32];
+        std::snprintf(tag, sizeof tag, "%016zx", h);
+        unit_name = std::string(dir) + "/rfk_chaos_game_" + tag + ".cu";
+        if (FILE* fh = std::fopen(unit_name.c_str(), "w")) {
+            std::fwrite(source.data(), 1, source.size(), fh);
+            std::fclose(fh);
+        }
+    }
     nvrtcProgram prog;
-    if (nvrtcCreateProgram(&prog, source.c_str(), "rfk_chaos_game.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    if (nvrtcCreateProgram(&prog, source.c_str(), unit_name.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
         throw std::runtime_error("nvrtcCreateProgram failed");
     std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--generate-line-info"};
     if (opt.math_mode == 2) opts.push_back("--use_fast_math");

@@ -8,14 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import FIXTURES, GENOME, ROOT, VARIATIONS
-
-COMPILE_CLEAN = """linear sinusoidal spherical swirl horseshoe polar handkerchief heart disc spiral hyperbolic diamond ex julia bent
-waves fisheye popcorn exponential power cosine rings fan blob pdj fan2 rings2 eyefish bubble perspective noise julian juliascope blur
-gaussian_blur radial_blur pie ngon curl rectangles arch tangent square rays blade secant2 cross disc2 super_shape flower conic parabola
-boarders butterfly curve foci loonie exp log sin cos sinh pre_blur waves2 cylinder auger flux mobius""".split()
-BROKEN = "twintrian bent2 bipolar cell cpow edisc oscope coth".split()
-
+from conftest import BROKEN, COMPILE_CLEAN, FIXTURES, GENOME, GENOME_TEMPLATE, ROOT, VARIATIONS, chunk_genome, stress_genome
 
 def test_abi_exports_every_declared_symbol(rfk):
     header = open(os.path.join(ROOT, "include", "refrakt_b200.h")).read()
@@ -162,13 +155,6 @@ def test_rotate_xforms_is_the_per_frame_animation_step(rfk, compiler, oracle_mod
     assert f.needs_warmup()
 
 
-GENOME_TEMPLATE = """<flame name="t" size="640 480" center="0 0" scale="120" rotate="0" brightness="4" gamma="4" vibrancy="1"
- estimator_radius="9" estimator_curve="0.4">
-%s
- <color index="0" rgb="255 0 0"/><color index="255" rgb="0 0 255"/>
-</flame>"""
-
-
 def test_load_flame_failures(rfk, compiler, tmp_path):
     assert rfk.Flame.load_flame(str(tmp_path / "missing.flam3"), compiler) is None
     assert "cannot read" in rfk.Flame.last_error()
@@ -225,24 +211,11 @@ def test_shipped_genome_cubin_is_sm100_with_vector_reductions(flame, tmp_path):
     assert m and int(m.group(1)) <= 64
 
 
-def _xform_xml(names, vt, rng):
-    attrs = []
-    for n in names:
-        attrs.append('%s="%.4f"' % (n, rng.uniform(0.1, 0.9)))
-        for p in vt.vars[n].param:
-            attrs.append('%s="%.4f"' % (p, rng.uniform(0.5, 3.0)))
-    coefs = " ".join("%.4f" % v for v in rng.normal(0, 0.6, 6))
-    return '<xform weight="%.3f" color="%.3f" color_speed="0.5" animate="1" %s coefs="%s" opacity="1"/>' % (rng.uniform(0.2, 1), rng.random(), " ".join(attrs), coefs)
-
-
 @pytest.mark.parametrize("chunk", range(6))
 def test_every_compile_clean_variation_builds(rfk, compiler, vt, oracle_mod, chunk):
     """all 68 variations of SURVEY Appendix C that compile in the reference also compile here (CUDA dialect, NVRTC,
     sm_100a) and in the oracle (g++), with identical GLSL text"""
-    rng = np.random.default_rng(chunk)
-    names = COMPILE_CLEAN[chunk::6]
-    xforms = [_xform_xml(names[i:i + 3], vt, rng) for i in range(0, len(names), 3)]
-    xml = GENOME_TEMPLATE % "\n".join(xforms)
+    xml = chunk_genome(chunk, vt)
     f = rfk.Flame.load_flame_string(xml, compiler)
     assert f is not None, rfk.Flame.last_error()
     assert len(f.cubin()) > 1000
@@ -263,3 +236,28 @@ def test_gpu_entry_points_fail_loudly_without_a_device(rfk, flame):
         flame.single_step(np.zeros((1, 3), np.float32), np.zeros(1, np.int32), np.zeros((1, 4), np.uint32))
     with pytest.raises(rfk.RefraktError):
         flame.render_frame(64, 64, max_draw_calls=1)
+
+
+def test_overlay_fixes_the_eight_broken_variations(rfk, overlay_compiler, overlay_vt, oracle_mod):
+    """refrakt_b200/data/variations_b200.yaml: with the overlay all 76 names compile on both sides (flam3 semantics;
+    parity for these eight is unpinned — the reference's own text does not compile)"""
+    assert len(overlay_compiler.variations()) == 76
+    assert overlay_compiler.get_parameters_for_variation("oscope") == ["oscope_separation", "oscope_frequency", "oscope_amplitude", "oscope_damping"]
+    xml = chunk_genome(99, overlay_vt, names=BROKEN)
+    f = rfk.Flame.load_flame_string(xml, overlay_compiler)
+    assert f is not None, rfk.Flame.last_error()
+    of = oracle_mod.load_flame_string(xml, overlay_vt)
+    assert f.glsl_source() == oracle_mod.compile_flame_xforms(of, overlay_vt)
+    oracle_mod.Oracle(of, overlay_vt)
+
+
+def test_stress_genome_builds(rfk, overlay_compiler, overlay_vt, oracle_mod):
+    """BASELINE configs[4]: 12 xforms + final xform with divergent variations"""
+    xml = stress_genome(overlay_vt)
+    f = rfk.Flame.load_flame_string(xml, overlay_compiler)
+    assert f is not None, rfk.Flame.last_error()
+    i = f.info()
+    assert (i.num_xforms, i.has_final_xform) == (12, 1)
+    of = oracle_mod.load_flame_string(xml, overlay_vt)
+    assert f.glsl_source() == oracle_mod.compile_flame_xforms(of, overlay_vt)
+    assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(of).view(np.uint32))

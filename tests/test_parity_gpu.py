@@ -166,3 +166,56 @@ def test_animate_matches_oracle(gpu_ready, flame, oracle):
         keep = [i for i in range(got.shape[1]) if i not in rotated]
         assert np.array_equal(got[:, keep], want[:, keep])
     assert np.array_equal(flame.animate(64, 0.0)[5], oracle.params()[:169])
+
+
+def _parity_over_genome(rfk, oracle_mod, compiler, vt, xml, n_per_xform, seed):
+    """single-step parity for every xform of a synthetic genome; vectors whose reference result is non-finite or
+    huge (exp/cosh/tan blow-ups) are excluded from the 1e-5 statistic but must be non-finite/huge on both sides"""
+    f = rfk.Flame.load_flame_string(xml, compiler)
+    assert f is not None, rfk.Flame.last_error()
+    of = oracle_mod.load_flame_string(xml, vt)
+    orc = oracle_mod.Oracle(of, vt)
+    ids = list(range(len(of.xforms))) + ([-1] if of.final_xform is not None else [])
+    report = {}
+    for xid in ids:
+        xyz, states = _inputs(seed + 17 * xid, n_per_xform, spread=0.8)
+        idv = np.full(n_per_xform, xid, dtype=np.int32)
+        got, got_rng = f.single_step(xyz, idv, states)
+        want, want_rng = orc.single_step(xyz, idv, states)
+        assert np.array_equal(got_rng, want_rng), "xform %d: RNG state" % xid
+        sane = np.isfinite(want).all(axis=1) & (np.abs(want[:, :2]).max(axis=1) < 1e4)
+        assert sane.mean() > 0.5, "xform %d: test vectors mostly blow up" % xid
+        err = _rel_err(got, want)
+        bad = sane & ~(err <= 1e-5)
+        if bad.any():
+            idx = np.nonzero(bad)[0]
+            best = np.full(idx.size, np.inf)
+            for k in (-2, -1, 1, 2):
+                alt, _ = orc.single_step(_nudge(xyz[idx], k), idv[idx], states[idx])
+                best = np.minimum(best, _rel_err(got[idx], alt))
+            unexplained = (best > 1e-5).sum()
+        else:
+            unexplained = 0
+        names = list((of.final_xform if xid == -1 else of.xforms[xid]).variations)
+        report[xid] = (names, float(bad.mean()), int(unexplained))
+    return report
+
+
+@pytest.mark.parametrize("chunk", range(6))
+def test_single_step_all_variations(gpu_ready, rfk, oracle_mod, compiler, vt, chunk):
+    """every compile-clean variation of variations.yaml (68), three per xform, against the oracle"""
+    from conftest import chunk_genome
+    report = _parity_over_genome(rfk, oracle_mod, compiler, vt, chunk_genome(chunk, vt), 20000, 500 + chunk)
+    for xid, (names, frac_bad, unexplained) in report.items():
+        assert frac_bad <= 2e-3, (xid, names, frac_bad)
+        assert unexplained <= 2, (xid, names, unexplained)
+
+
+def test_single_step_overlay_and_stress_genome(gpu_ready, rfk, oracle_mod, overlay_compiler, overlay_vt):
+    """the eight corrected variations and the 12-xform stress genome of BASELINE configs[4]"""
+    from conftest import BROKEN, chunk_genome, stress_genome
+    for xml in (chunk_genome(99, overlay_vt, names=BROKEN), stress_genome(overlay_vt)):
+        report = _parity_over_genome(rfk, oracle_mod, overlay_compiler, overlay_vt, xml, 20000, 900)
+        for xid, (names, frac_bad, unexplained) in report.items():
+            assert frac_bad <= 2e-3, (xid, names, frac_bad)
+            assert unexplained <= 2, (xid, names, unexplained)
