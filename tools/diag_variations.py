@@ -28,7 +28,8 @@ def main():
     rows = []
     for name in COMPILE_CLEAN + BROKEN:
         rng = np.random.default_rng(abs(hash(name)) % 1000)
-        xml = GENOME_TEMPLATE % xform_xml([name], vt, np.random.default_rng(len(name)))
+        names = [name] if "pre_xform" not in vt.vars[name].flags else ["linear", name]  # a pre_xform variation alone declares no result
+        xml = GENOME_TEMPLATE % xform_xml(names, vt, np.random.default_rng(len(name)))
         of = ro.load_flame_string(xml, vt)
         orc = ro.Oracle(of, vt)
         f = r.Flame.load_flame_string(xml, compiler)
