@@ -47,13 +47,11 @@ __device__ __forceinline__ unsigned int rfk_hash32(unsigned int h) {
     return h;
 }
 
-// A bijection of [0, RFK_BLOCK): odd multiplier, xor-shift, odd multiplier.
+// A bijection of [0, RFK_BLOCK): j = (tid * a + b) mod RFK_BLOCK with a odd, a and b fresh every iteration.
+// Two particles of one warp land in the same warp again with probability ~1/8 (8 warps), as under a uniform
+// permutation; the multiplier changes every iteration, so no pair stays together.
 __device__ __forceinline__ unsigned int rfk_deal_slot(unsigned int tid, unsigned int key) {
-    const unsigned int mask = RFK_BLOCK - 1;
-    unsigned int j = (tid * (key | 1u) + (key >> 8)) & mask;
-    j ^= j >> (RFK_LOG2_BLOCK / 2);
-    j = (j * ((key >> 16) | 1u) + (key >> 24)) & mask;
-    return j;
+    return (tid * ((key >> 8) | 1u) + (key >> 20)) & (RFK_BLOCK - 1);
 }
 
 // src/hammersley.cpp:29-48 for point `i` (z = w = 0)
@@ -76,8 +74,8 @@ __device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const fl
 }
 
 __device__ __forceinline__ unsigned int rfk_palette_index(float z) {
-    float c = ceilf(z * 255.0f);
-    unsigned int u = c > 0.0f ? (unsigned int)c : 0u;  // uint(negative) is undefined in GLSL; clamp to 0
+    // min(255, uint(ceil(z * 255))): one saturating convert (negative and NaN -> 0; uint(negative) is undefined in GLSL)
+    unsigned int u = __float2uint_ru(z * 255.0f);
     return u < 255u ? u : 255u;
 }
 
@@ -156,9 +154,10 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
   #endif
 #endif
     };
-    auto deal = [&](int it) {
-        unsigned int key = rfk_hash32(p.deal_seed ^ (blockIdx.x * 0x9E3779B9u) ^ ((unsigned int)it * 0x7FEB352Du));
-        unsigned int j = rfk_deal_slot(tid, key);
+    unsigned int deal_key = rfk_hash32(p.deal_seed ^ (blockIdx.x * 0x9E3779B9u));
+    auto deal = [&](int) {
+        deal_key = deal_key * 1664525u + 1013904223u;  // CTA-uniform
+        unsigned int j = rfk_deal_slot(tid, deal_key);
         ex_x[parity][j] = x; ex_y[parity][j] = y; ex_c[parity][j] = c;
         __syncthreads();
         x = ex_x[parity][tid]; y = ex_y[parity][tid]; c = ex_c[parity][tid];

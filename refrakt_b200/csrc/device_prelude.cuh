@@ -72,25 +72,23 @@ static constexpr float EPS = (1e-10f);
 // RFK_MATH_MODE 0: libdevice functions (1-2 ulp), IEEE division and square root.
 // RFK_MATH_MODE 1: the same accuracy class against the 1e-5 parity contract at a fraction of the
 //   instructions: 2-ulp division / square root (compiler flags), sine and cosine on the SFU after a
-//   two-constant Cody-Waite reduction to [-pi, pi] (absolute error ~5e-7 for |x| < 1e5, libdevice
-//   beyond), pow through lg2/ex2 while |y| <= 16 and x >= 0 (relative error < 3e-6, libdevice otherwise).
+//   two-constant Cody-Waite reduction to [-pi, pi] (absolute error ~5e-7), denormals flushed, pow through lg2/ex2 while |y| <= 16 and x >= 0 (relative error < 3e-6, libdevice otherwise).
 // RFK_MATH_MODE 2: --use_fast_math (SFU intrinsics with no range reduction; outside the parity contract).
 #if RFK_MATH_MODE == 1
+// x - rint(x / 2pi) * 2pi with 2pi split in two binary32 constants: the product k * hi is exact inside the
+// fma, so the reduced argument is good to ~3e-6 rad even at |x| = 1e9 (where binary32 itself resolves 64 rad);
+// no large-argument fallback branch is needed. Inf / NaN give NaN like sinf / cosf.
 __device__ __forceinline__ float rfk_reduce_2pi(float v) {
     float k = ::rintf(v * 0.15915494309189535f);
     float r = ::fmaf(k, -6.2831854820251465f, v);
     return ::fmaf(k, 1.7484555e-7f, r);
 }
-__device__ __forceinline__ float sin(float v) { return ::fabsf(v) < 1.0e5f ? ::__sinf(rfk_reduce_2pi(v)) : ::sinf(v); }
-__device__ __forceinline__ float cos(float v) { return ::fabsf(v) < 1.0e5f ? ::__cosf(rfk_reduce_2pi(v)) : ::cosf(v); }
+__device__ __forceinline__ float sin(float v) { return ::__sinf(rfk_reduce_2pi(v)); }
+__device__ __forceinline__ float cos(float v) { return ::__cosf(rfk_reduce_2pi(v)); }
 __device__ __forceinline__ void rfk_sincos(float v, float* s, float* c) {
-    if (::fabsf(v) < 1.0e5f) {
-        float r = rfk_reduce_2pi(v);
-        *s = ::__sinf(r);
-        *c = ::__cosf(r);
-    } else {
-        ::sincosf(v, s, c);
-    }
+    float r = rfk_reduce_2pi(v);
+    *s = ::__sinf(r);
+    *c = ::__cosf(r);
 }
 __device__ __forceinline__ float pow(float a, float b) {
     if (a >= 0.0f && ::fabsf(b) <= 16.0f) return ::exp2f(b * ::__log2f(a));
