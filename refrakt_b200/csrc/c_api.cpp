@@ -521,15 +521,23 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         const size_t W = req->width, H = req->height, n = W * H;
         cudaStream_t s = current_stream();
 
+        // library-owned frame buffers: kept between calls and regrown only when the frame gets larger
         struct buffers {
             float4* bins = nullptr; float4* image = nullptr; uchar4* rgba8 = nullptr;
+            size_t bins_n = 0, image_n = 0, rgba8_n = 0;
             cudaEvent_t ev[5] = {};
-            ~buffers() { cudaFree(bins); cudaFree(image); cudaFree(rgba8); for (auto e : ev) if (e) cudaEventDestroy(e); }
-        } b;
-        cuda_ok(cudaMalloc(&b.bins, n * sizeof(float4)), "cudaMalloc(bins)");
-        if (image_out) cuda_ok(cudaMalloc(&b.image, n * sizeof(float4)), "cudaMalloc(image)");
-        if (rgba8_out) cuda_ok(cudaMalloc(&b.rgba8, n * sizeof(uchar4)), "cudaMalloc(rgba8)");
-        for (auto& e : b.ev) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
+        };
+        static buffers b;
+        auto grow = [](auto*& ptr, size_t& have, size_t want, const char* what) {
+            if (have >= want) return;
+            cudaFree(ptr); ptr = nullptr; have = 0;
+            cuda_ok(cudaMalloc(&ptr, want * sizeof(*ptr)), what);
+            have = want;
+        };
+        grow(b.bins, b.bins_n, n, "cudaMalloc(bins)");
+        if (image_out) grow(b.image, b.image_n, n, "cudaMalloc(image)");
+        if (rgba8_out) grow(b.rgba8, b.rgba8_n, n, "cudaMalloc(rgba8)");
+        for (auto& e : b.ev) if (!e) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
 
         cuda_ok(cudaEventRecord(b.ev[0], s), "event");
         fl->warmup(req->warmup_passes, req->tss_width);
@@ -551,7 +559,7 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         rfk_flame_post_params(f, &pp);
         pp.scale_constant = (float)(1.0 / std::pow(10.0, (double)req->scale_constant_exp));
         auto d = to_density(pp, W, H);
-        kernels::density_tonemap(b.bins, b.image, b.rgba8, d, true, true, s);
+        kernels::density_tonemap(b.bins, image_out ? b.image : nullptr, rgba8_out ? b.rgba8 : nullptr, d, true, true, s);
         count_launch(1);
         cuda_ok(cudaGetLastError(), "density_tonemap launch");
         cuda_ok(cudaEventRecord(b.ev[3], s), "event");

@@ -132,22 +132,37 @@ __device__ __forceinline__ float4 tonemap_pixel(float4 color, const density_para
 }
 
 constexpr int DE_TILE_W = 32, DE_ROWS_PER_WARP = 4, DE_WARPS = 8, DE_TILE_H = DE_ROWS_PER_WARP * DE_WARPS;
+constexpr int DE_THREADS = DE_WARPS * 32;
+constexpr int DE_CAP = 512;            // candidate-list entries per batch (48 B each)
+constexpr int DE_MAX_COUNTERS = 2048;  // (32 + 2 * 100) rows x 8 column chunks
 
-// Gather form of the reference's point-sprite splat. A warp owns 4 output rows x 32
-// columns and keeps their float4 sums in registers (no atomics, fixed summation order).
-// Source bin (bx, by) with radius r lands on out[cy + m][bx - 1 + i], cy = H-1-by,
-// i, m in [-r, r], weight (1 - n(i)^2 - n(m)^2) * (2/pi) / r^2 when that is >= 0, with
-// n(k) = 2k/(2r+1) + 1/(2r+1)^2; r == 0 copies the bin to out[cy][bx-1].
-// The warp scans the source rows within the maximum radius; a bin is a candidate only if
-// its density is below the threshold of the smallest radius that could reach the warp's
-// rows, so dense regions (radius 0 everywhere) cost one 4-byte load per scanned bin.
+// Gather form of the reference's point-sprite splat. Source bin (bx, by) with radius r lands on
+// out[cy + m][bx - 1 + i], cy = H-1-by, i, m in [-r, r], weight (1 - n(i)^2 - n(m)^2) * (2/pi) / r^2 when
+// that is >= 0, n(k) = 2k/(2r+1) + 1/(2r+1)^2; r == 0 copies the bin to out[cy][bx-1].
+//
+// A CTA produces a 32 x 32 output tile; a warp owns 4 rows x 32 columns and keeps their float4 sums in
+// registers (no atomics, fixed summation order => deterministic).
+//  A. The CTA scans its (32 + 2R)^2 source window once. A bin is a candidate when its density is below the
+//     threshold of radius 1 (one 4-byte load and a compare for the dense bulk of the image), its exact
+//     radius (the reference's int(R / pow(d, curve))) is >= 1 and its footprint reaches the tile.
+//     Candidates are counted per (row, 32-column chunk), prefix-summed, and written to a shared-memory list
+//     in row-major order with their colour and the per-radius constants.
+//  B. Every warp walks the list entries whose source row can reach its 4 rows (a contiguous range, the list
+//     being row-major) and accumulates; lanes are output columns.
+// Lists longer than DE_CAP are processed in batches (rescan + walk).
 template <bool DENSITY, bool TONEMAP>
-__global__ void __launch_bounds__(DE_WARPS * 32) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
-                                                                       uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
-    const float* thresholds = p.thresholds;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ox = blockIdx.x * DE_TILE_W + lane;
-    const int oy0 = blockIdx.y * DE_TILE_H + warp * DE_ROWS_PER_WARP;
+__global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
+                                                                     uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
+    __shared__ int s_off[DE_MAX_COUNTERS + 1];
+    __shared__ int s_part[DE_THREADS];
+    __shared__ float4 s_col[DE_CAP];
+    __shared__ int4 s_geo[DE_CAP];    // source column, source row (cy), radius
+    __shared__ float4 s_k[DE_CAP];    // 2/S, 1/S^2, (2/pi)/r^2
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * DE_TILE_W, ty0 = blockIdx.y * DE_TILE_H;
+    const int ox = tx0 + lane;
+    const int oy0 = ty0 + warp * DE_ROWS_PER_WARP;
     const int W = p.W, H = p.H;
 
     float4 acc[DE_ROWS_PER_WARP];
@@ -167,55 +182,115 @@ __global__ void __launch_bounds__(DE_WARPS * 32) density_tonemap_kernel(const fl
                 }
             }
         }
-        // radius >= 1 sources
         if (R >= 1) {
-            const int bx_first = blockIdx.x * DE_TILE_W + 1 - R;  // leftmost source column that can reach the tile
-            const int span = DE_TILE_W + 2 * R;
-            const float t_any = thresholds[1];
-            for (int cy = max(0, oy0 - R); cy <= min(H - 1, oy0 + DE_ROWS_PER_WARP - 1 + R); cy++) {
-                // smallest |m| between this source row and the warp's rows
-                int dy = cy < oy0 ? oy0 - cy : (cy > oy0 + DE_ROWS_PER_WARP - 1 ? cy - (oy0 + DE_ROWS_PER_WARP - 1) : 0);
-                const float t_row = dy <= 1 ? t_any : thresholds[dy];
-                const float4* row = bins + (size_t)(H - 1 - cy) * W;
-                for (int c0 = 0; c0 < span; c0 += 32) {
-                    int bx = bx_first + c0 + lane;
-                    float d = 0.0f;
-                    if (c0 + lane < span && bx >= 0 && bx < W) d = __ldg(&row[bx].w);
-                    unsigned int cand = __ballot_sync(0xffffffffu, d != 0.0f && d <= t_row);
-                    if (!cand) continue;
-                    // candidates: exact radius and colour, then every lane accumulates its column
-                    float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int r = 0;
-                    if (cand & (1u << lane)) {
-                        col = __ldg(&row[bx]);
-                        r = estimator_radius_of(d, p);
+            const int win_x0 = tx0 + 1 - R, win_w = DE_TILE_W + 2 * R, nch = (win_w + 31) >> 5;
+            const int win_y0 = ty0 - R, nrows = DE_TILE_H + 2 * R;
+            const int ncnt = nrows * nch;
+            const float t_any = p.thresholds[1];
+
+            // exact radius and reach test of the bin this lane looks at; 0 = not a candidate
+            auto candidate_radius = [&](int row, int c, float* d_out) -> int {
+                const int cy = win_y0 + row, col = (c << 5) + lane, bx = win_x0 + col;
+                if (cy < 0 || cy >= H || col >= win_w || bx < 0 || bx >= W) return 0;
+                const float d = __ldg(&bins[(size_t)(H - 1 - cy) * W + bx].w);
+                if (!(d != 0.0f && d <= t_any)) return 0;
+                const int r = estimator_radius_of(d, p);
+                if (r < 1) return 0;
+                if (bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1) return 0;
+                *d_out = d;
+                return r;
+            };
+
+            // A1: counts per (row, chunk)
+            for (int row = warp; row < nrows; row += DE_WARPS)
+                for (int c = 0; c < nch; c++) {
+                    float d;
+                    unsigned int vote = __ballot_sync(0xffffffffu, candidate_radius(row, c, &d) > 0);
+                    if (lane == 0) s_off[row * nch + c] = __popc(vote);
+                }
+            __syncthreads();
+            // A2: exclusive prefix sum over the counters
+            {
+                const int per = (ncnt + DE_THREADS - 1) / DE_THREADS;
+                const int lo = min(tid * per, ncnt), hi = min(lo + per, ncnt);
+                int sum = 0;
+                for (int i = lo; i < hi; i++) sum += s_off[i];
+                s_part[tid] = sum;
+                __syncthreads();
+                if (warp == 0) {
+                    int carry = 0;
+                    for (int base = 0; base < DE_THREADS; base += 32) {
+                        int v = s_part[base + lane], incl = v;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            int t = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += t;
+                        }
+                        s_part[base + lane] = carry + incl - v;
+                        carry += __shfl_sync(0xffffffffu, incl, 31);
                     }
-                    while (cand) {
-                        int src = __ffs(cand) - 1;
-                        cand &= cand - 1;
-                        int sr = __shfl_sync(0xffffffffu, r, src);
-                        if (sr < 1 || sr < dy) continue;  // warp-uniform
-                        float sx = __shfl_sync(0xffffffffu, col.x, src), sy = __shfl_sync(0xffffffffu, col.y, src);
-                        float sz = __shfl_sync(0xffffffffu, col.z, src), sw = __shfl_sync(0xffffffffu, col.w, src);
-                        int sbx = bx_first + c0 + src;
-                        int i = ox - sbx + 1;
-                        if (i < -sr || i > sr) continue;  // per lane
-                        float S = (float)(2 * sr + 1);
-                        float bias = 1.0f / (S * S);
-                        float ni = 2.0f * (float)i / S + bias;
-                        float norm = 0.63661977236f / (float)(sr * sr);  // density_vert.glsl:62
-#pragma unroll
-                        for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
-                            int m = oy0 + k - cy;
-                            if (m < -sr || m > sr) continue;
-                            float nm = 2.0f * (float)m / S + bias;
-                            float dist = ni * ni + nm * nm;
-                            if (dist > 1.0f) continue;  // density_frag.glsl:17
-                            float wgt = (1.0f - dist) * norm;
-                            acc[k].x += sx * wgt; acc[k].y += sy * wgt; acc[k].z += sz * wgt; acc[k].w += sw * wgt;
+                    if (lane == 0) s_off[ncnt] = carry;
+                }
+                __syncthreads();
+                int run = s_part[tid];
+                for (int i = lo; i < hi; i++) {
+                    int v = s_off[i];
+                    s_off[i] = run;
+                    run += v;
+                }
+                __syncthreads();
+            }
+            const int total = s_off[ncnt];
+
+            // source rows that can reach this warp's output rows, as window rows
+            const int rlo = warp * DE_ROWS_PER_WARP, rhi = min(nrows - 1, warp * DE_ROWS_PER_WARP + DE_ROWS_PER_WARP - 1 + 2 * R);
+            const int w_lo = s_off[rlo * nch], w_hi = s_off[(rhi + 1) * nch];
+
+            for (int base = 0; base < total; base += DE_CAP) {
+                // A3: write this batch of the list
+                for (int row = warp; row < nrows; row += DE_WARPS) {
+                    const int first = s_off[row * nch], last = s_off[(row + 1) * nch];
+                    if (last <= base || first >= base + DE_CAP) continue;  // warp-uniform
+                    for (int c = 0; c < nch; c++) {
+                        float d = 0.0f;
+                        const int r = candidate_radius(row, c, &d);
+                        const unsigned int vote = __ballot_sync(0xffffffffu, r > 0);
+                        if (r > 0) {
+                            const int e = s_off[row * nch + c] + __popc(vote & ((1u << lane) - 1u)) - base;
+                            if (e >= 0 && e < DE_CAP) {
+                                const int cy = win_y0 + row, bx = win_x0 + (c << 5) + lane;
+                                s_col[e] = __ldg(&bins[(size_t)(H - 1 - cy) * W + bx]);
+                                s_geo[e] = make_int4(bx, cy, r, 0);
+                                const float S = (float)(2 * r + 1);
+                                s_k[e] = make_float4(2.0f / S, 1.0f / (S * S), 0.63661977236f / (float)(r * r), 0.0f);  // density_vert.glsl:62
+                            }
                         }
                     }
                 }
+                __syncthreads();
+                // B: accumulate
+                const int e_lo = max(w_lo, base) - base, e_hi = min(w_hi, base + DE_CAP) - base;
+                for (int e = e_lo; e < e_hi; e++) {
+                    const int4 g = s_geo[e];
+                    const int sr = g.z, m0 = oy0 - g.y;
+                    if (m0 > sr || m0 + DE_ROWS_PER_WARP - 1 < -sr) continue;  // warp-uniform
+                    const float4 col = s_col[e];
+                    const float4 k = s_k[e];
+                    const int i = ox - g.x + 1;
+                    const bool lane_in = i >= -sr && i <= sr;
+                    const float ni = fmaf((float)i, k.x, k.y);
+                    const float ni2 = ni * ni;
+#pragma unroll
+                    for (int q = 0; q < DE_ROWS_PER_WARP; q++) {
+                        const int m = m0 + q;
+                        const float nm = fmaf((float)m, k.x, k.y);
+                        const float dist = fmaf(nm, nm, ni2);
+                        const bool ok = lane_in && m >= -sr && m <= sr && dist <= 1.0f;  // density_frag.glsl:17
+                        const float wgt = ok ? (1.0f - dist) * k.z : 0.0f;
+                        acc[q].x = fmaf(col.x, wgt, acc[q].x); acc[q].y = fmaf(col.y, wgt, acc[q].y);
+                        acc[q].z = fmaf(col.z, wgt, acc[q].z); acc[q].w = fmaf(col.w, wgt, acc[q].w);
+                    }
+                }
+                __syncthreads();
             }
         }
     } else {
@@ -285,7 +360,7 @@ static void density_thresholds(float* host_out, int estimator_radius, int estima
 void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, density_params p, bool do_density, bool do_tonemap, cudaStream_t s) {
     density_thresholds(p.thresholds, p.estimator_radius, p.estimator_min, p.estimator_curve);
     dim3 grid((p.W + DE_TILE_W - 1) / DE_TILE_W, (p.H + DE_TILE_H - 1) / DE_TILE_H);
-    dim3 block(DE_WARPS * 32);
+    dim3 block(DE_THREADS);
     if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
     else if (do_density) density_tonemap_kernel<true, false><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
     else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
