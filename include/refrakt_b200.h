@@ -226,6 +226,9 @@ typedef struct rfk_frame_stats {
 int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_out, float* image_out /* optional float4 */,
                      rfk_frame_stats* stats);
 
+/* ---- output: the reference's screenshot (src/main.cpp:590-593, stbi_write_png of get_pixels()) ---- */
+int rfk_write_png(const char* path, const uint8_t* rgba8, size_t width, size_t height); /* host pixels, rows top to bottom */
+
 /* ---- test hooks: the generated device functions on host-supplied vectors ---- */
 /* one dispatch(v, xid) per element (variation_table.cpp:222-263). xyz: n x 3 in, xid: n, rng: n x 4 in/out,
  * fp: 1024 floats or NULL for the flame's current values, out: n x 4 (x, y, colour, opacity) */

@@ -130,6 +130,7 @@ SIGNATURES = {
     "rfk_make_shuffle_buffers": (_i, [_vp, C.c_uint32, C.c_uint32, C.c_uint64]),
     "rfk_copy_rng_states": (_i, [_upp, _sz, _sz]),
     "rfk_render_frame": (_i, [_vp, C.POINTER(FrameRequest), _vp, _vp, C.POINTER(FrameStats)]),
+    "rfk_write_png": (_i, [_cp, _vp, _sz, _sz]),
     "rfk_flame_single_step": (_i, [_vp, _i, _fpp, _ipp, _upp, _fpp, _i, _fpp]),
     "rfk_flame_select_xform": (_i, [_vp, _i, _fpp, _fpp, _ipp]),
     "rfk_flame_bucket_index": (_i, [_vp, _i, _fpp, _fpp, _i, _i, _ipp, _ipp]),
@@ -497,6 +498,13 @@ def make_shuffle_buffers(size: int, count: int, seed: int = 0) -> np.ndarray:
     out = buf.download(np.uint32, (count, size))
     buf.free()
     return out
+
+
+def write_png(path: str, rgba8: np.ndarray):
+    """screenshot (src/main.cpp:590-593): rgba8 is H x W x 4 uint8, rows top to bottom"""
+    rgba8 = np.ascontiguousarray(rgba8, dtype=np.uint8)
+    h, w = rgba8.shape[:2]
+    _check(lib().rfk_write_png(path.encode(), rgba8.ctypes.data, w, h), "write_png")
 
 
 def copy_rng_states(first: int, count: int) -> np.ndarray:

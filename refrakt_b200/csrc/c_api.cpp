@@ -10,6 +10,7 @@
 
 #include "flame.hpp"
 #include "flame_device.hpp"
+#include "png_writer.hpp"
 #include "static_kernels.cuh"
 #include "textutil.hpp"
 #include "variation_table.hpp"
@@ -576,6 +577,14 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         }
         return RFK_OK;
     });
+}
+
+int rfk_write_png(const char* path, const uint8_t* rgba8, size_t width, size_t height) {
+    try {
+        if (!path || !rgba8) return fail(RFK_E_INVALID, "rfk_write_png: null argument");
+        write_png_rgba8(path, rgba8, width, height);
+        return RFK_OK;
+    } catch (const std::exception& e) { return fail(RFK_E_INVALID, e.what()); }
 }
 
 // ---- test hooks ----

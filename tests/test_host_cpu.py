@@ -261,3 +261,27 @@ def test_stress_genome_builds(rfk, overlay_compiler, overlay_vt, oracle_mod):
     of = oracle_mod.load_flame_string(xml, overlay_vt)
     assert f.glsl_source() == oracle_mod.compile_flame_xforms(of, overlay_vt)
     assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(of).view(np.uint32))
+
+
+def test_png_writer_roundtrip(rfk, tmp_path):
+    """rfk_write_png (the reference's stbi_write_png screenshot, main.cpp:590-593) decodes to the same pixels"""
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    for shape in ((37, 53, 4), (1, 1, 4), (64, 200, 4)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        path = str(tmp_path / ("t%d.png" % shape[0]))
+        rfk.write_png(path, img)
+        assert np.array_equal(np.array(Image.open(path)), img)
+    with pytest.raises(rfk.RefraktError):
+        rfk.write_png(str(tmp_path / "no_such_dir" / "x.png"), img)
+
+
+def test_cli_fails_loudly_without_a_device(rfk, tmp_path):
+    import torch
+    cli = os.path.join(os.path.dirname(rfk.LIB_PATH), "rfk_render")
+    assert os.path.exists(cli)
+    assert subprocess.run([cli], stdout=subprocess.PIPE, stderr=subprocess.PIPE).returncode == 2  # usage
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([cli, "--genome", GENOME, "--variations", VARIATIONS, "--out", str(tmp_path / "x.png")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "rfk_render:" in r.stderr and not (tmp_path / "x.png").exists()

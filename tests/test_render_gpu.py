@@ -222,3 +222,23 @@ def test_render_frame_end_to_end(gpu_ready, rfk, flame, oracle, oracle_mod):
     # the target-binned stopping rule of main.cpp:411
     _, stats2 = flame.render_frame(W, H, target_binned=3 * W * H, drawing_passes=8)
     assert stats2.binned >= 3 * W * H and stats2.binned - 3 * W * H < 8 * P
+
+
+def test_cli_renders_animation_frames(gpu_ready, rfk, tmp_path):
+    """rfk_render: headless stills / animation to PNG through the C ABI"""
+    import json
+    import os
+    import subprocess
+    from PIL import Image
+    from conftest import GENOME, VARIATIONS
+    cli = os.path.join(os.path.dirname(rfk.LIB_PATH), "rfk_render")
+    out = str(tmp_path / "frame_%03d.png")
+    r = subprocess.run([cli, "--genome", GENOME, "--variations", VARIATIONS, "--out", out, "--width", "320", "--height", "180", "--quality", "50",
+                        "--particles", str(256 * 16 * 32), "--temporal-samples", "32", "--passes", "32", "--frames", "3", "--fps", "2"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = [json.loads(l) for l in r.stdout.strip().split("\n")]
+    assert len(lines) == 3 and all(l["binned"] >= 50 * 320 * 180 for l in lines)
+    imgs = [np.array(Image.open(out % k)) for k in range(3)]
+    assert all(i.shape == (180, 320, 4) and i[..., :3].max() > 100 and (i[..., 3] == 255).all() for i in imgs)
+    assert np.abs(imgs[0].astype(int) - imgs[2].astype(int)).mean() > 0.5  # the xforms rotated between frames
