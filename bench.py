@@ -42,8 +42,16 @@ TSS_WIDTH = 1.2 / 60.0
 METRIC = "chaos_game_iterations_per_second"
 UNIT = "iterations/s"
 WORKLOAD = "configs[1]: electricsheep.247.11256 still, 3840x2160, 2000 samples/pixel, P=2097152, TS=512, warmup 16 + draw 128 passes/call, density estimation + tonemap"
-# dram__bytes_read.sum + dram__bytes_write.sum of one rfk_draw launch, from profiles/ (ncu --set full); None until captured
-DRAW_DRAM_TRAFFIC_BYTES = None
+# From the committed ncu captures of rfk_draw (profiles/r01*_rfk_draw*.md): DRAM bytes of one launch
+# (dram__bytes_read.sum + dram__bytes_write.sum) and executed warp instructions per warp-iteration.
+DRAW_DRAM_TRAFFIC_BYTES = 437.4e6
+DRAW_WARP_INST_PER_WARP_ITERATION = 248.6
+
+
+def roofline_probes():
+    """profiles/r01_roofline_probes.json: measured FFMA issue rate and red.global.add.v4.f32 rates (tools/roofline_probes.cu)"""
+    path = os.path.join(ROOT, "profiles", "r01_roofline_probes.json")
+    return json.load(open(path)) if os.path.exists(path) else None
 
 
 def measured_peaks():
@@ -279,6 +287,16 @@ def main():
                          "binding_limit": "fp32/alu issue, not memory: see DESIGN.md and profiles/",
                          "iterations_per_s_kernel": P * DRAW_PASSES / (mean_draw_ms * 1e-3)},
         }
+        probes = roofline_probes()
+        if probes:
+            kernel_iters_s = P * DRAW_PASSES / (mean_draw_ms * 1e-3)
+            winst = kernel_iters_s / 32.0 * DRAW_WARP_INST_PER_WARP_ITERATION
+            line["roofline"]["issue"] = {"achieved_warp_inst_per_s": winst, "peak_measured_ffma_issue": probes["ffma_warp_inst_per_s"],
+                                         "frac": winst / probes["ffma_warp_inst_per_s"], "warp_inst_per_warp_iteration": DRAW_WARP_INST_PER_WARP_ITERATION,
+                                         "source": "ncu smsp__inst_executed.sum (profiles/) x CUDA-event kernel rate; peak = tools/roofline_probes.cu"}
+            red = probes["red_v4_f32"]["132.7MB_4K"]["v4_gred_per_s"]
+            line["roofline"]["atomics"] = {"achieved_gred_per_s": mean_binned / (mean_draw_ms * 1e-3) / 1e9, "uniform_random_probe_gred_per_s": red,
+                                           "note": "red.global.add.v4.f32 at random addresses over the same 132.7 MB footprint; a flame's hits are concentrated, so the kernel can exceed it"}
         if not args.no_cpu_baseline and world == 1:
             try:
                 base = cpu_reference_run(1, 0)

@@ -144,6 +144,8 @@ typedef struct rfk_kernel_options {
     int32_t deterministic;  /* 1: fixed-point integer accumulation, bit-identical histograms run to run */
     int32_t count_xforms;   /* 1: count xform selections (rfk_flame_xform_counts) */
     int32_t min_blocks;     /* __launch_bounds__ minBlocksPerSM, 0 = unset */
+    int32_t block_width;    /* threads per CTA = particles per re-deal pool: 128, 256 (default, the reference's workgroup) or 512 */
+    int32_t deal_period;    /* re-deal the CTA's particles across warps every n-th iteration; default 1 */
 } rfk_kernel_options;
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* out);
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* in);

@@ -335,7 +335,7 @@ int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size) {
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* o) {
     if (!f || !o) return fail(RFK_E_INVALID, "null argument");
     const auto& k = F(f)->options();
-    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks};
+    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks, k.block_width, k.deal_period};
     return RFK_OK;
 }
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
@@ -344,6 +344,10 @@ int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
     k.math_mode = i->math_mode; k.fmad = i->fmad != 0; k.per_lane_xform = i->per_lane_xform != 0;
     k.warp_aggregate = i->warp_aggregate != 0; k.deterministic = i->deterministic != 0; k.count_xforms = i->count_xforms != 0;
     k.min_blocks = i->min_blocks;
+    k.block_width = i->block_width;
+    k.deal_period = i->deal_period;
+    if (k.block_width != 128 && k.block_width != 256 && k.block_width != 512) return fail(RFK_E_INVALID, "block_width must be 128, 256 or 512");
+    if (k.deal_period < 1) return fail(RFK_E_INVALID, "deal_period must be >= 1");
     if (k.math_mode < 0 || k.math_mode > 2) return fail(RFK_E_INVALID, "math_mode must be 0, 1 or 2");
     if (k.count_xforms && F(f)->xforms.size() > 62) return fail(RFK_E_INVALID, "count_xforms supports at most 62 xforms");
     if (!F(f)->set_options(k)) return fail(RFK_E_CUDA, flame::last_error());

@@ -231,7 +231,11 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #endif
         }
 #if !RFK_PER_LANE_XFORM
+  #if RFK_DEAL_PERIOD == 1
         deal(it);
+  #else
+        if ((it + 1) % RFK_DEAL_PERIOD == 0) deal(it);
+  #endif
 #endif
     }
 

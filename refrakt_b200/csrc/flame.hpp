@@ -64,6 +64,8 @@ struct kernel_options {
     bool deterministic = false;   // fixed-point (integer) accumulation: bit-identical histograms
     bool count_xforms = false;    // per-xform selection counters
     int min_blocks = 0;           // __launch_bounds__ second argument, 0 = compiler's choice
+    int block_width = 256;        // threads per CTA = particles per re-deal pool (128, 256 or 512; the reference's workgroup is 256)
+    int deal_period = 1;          // re-deal particles across warps every n-th iteration
     bool operator==(const kernel_options&) const = default;
 };
 

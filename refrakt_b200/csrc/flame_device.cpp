@@ -201,9 +201,10 @@ void flame::rebuild_cuda_source() {
     const int n = (int)xforms.size();
     std::string s;
     s += "// generated by refrakt_b200 for one genome: options, prelude, dispatch, kernels\n";
-    s += "#define RFK_BLOCK " + std::to_string(BLOCK_WIDTH) + "\n";
+    s += "#define RFK_BLOCK " + std::to_string(options_.block_width) + "\n";
+    s += "#define RFK_DEAL_PERIOD " + std::to_string(options_.deal_period) + "\n";
     int log2b = 0;
-    while ((1 << log2b) < BLOCK_WIDTH) log2b++;
+    while ((1 << log2b) < options_.block_width) log2b++;
     s += "#define RFK_LOG2_BLOCK " + std::to_string(log2b) + "\n";
     s += "#define RFK_TOTAL_PARAMS " + std::to_string(buffer_map_.size) + "\n";
     s += "#define RFK_NUM_XFORMS " + std::to_string(n) + "\n";
@@ -323,6 +324,8 @@ static void ensure_buffers(flame& f) {
     ensure_module(f);
     flame_device& d = *f.device();
     if (g_sim.total_particles == 0) throw std::runtime_error("set_sim_parameters has not been called");
+    if ((g_sim.total_particles / g_sim.temporal_samples) % f.options().block_width != 0)
+        throw std::invalid_argument("particles per temporal sample must be a multiple of the kernel's block_width");
     const int total_params = f.buffer_map().size;
     if (!d.fp) {
         cuda_check(cudaMalloc(&d.fp, flame::PARAM_BUFFER * sizeof(float)), "cudaMalloc(fp)");
@@ -398,7 +401,7 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
     p.first_run = 1;
     p.num_iter = (int)num_passes;
     void* args[] = {&p};
-    launch(d.warm, (unsigned)(g_sim.total_particles / BLOCK_WIDTH), BLOCK_WIDTH, args);
+    launch(d.warm, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
     cuda_check(cudaStreamSynchronize(g_sim.stream), "warmup");
     d.binned_reported = 0;
     d.warmed = true;
@@ -430,7 +433,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         p.fixed_bins = d.fixed_bins;
     }
     void* args[] = {&p};
-    launch(d.draw, (unsigned)(g_sim.total_particles / BLOCK_WIDTH), BLOCK_WIDTH, args);
+    launch(d.draw, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
     if (options_.deterministic) {
         kernels::fixed_to_float(d.fixed_bins, p.bins, W * H, g_sim.stream);
         count_launch(1);
@@ -542,7 +545,7 @@ void flame_kernel_info(flame& f, const char* kernel, int* regs, int* smem_bytes,
     cu_check(driver().ModuleGetFunction(&fn, f.device()->module, kernel), kernel);
     cu_check(driver().FuncGetAttribute(regs, CU_FUNC_ATTRIBUTE_NUM_REGS, fn), "regs");
     cu_check(driver().FuncGetAttribute(smem_bytes, CU_FUNC_ATTRIBUTE_SHARED_SIZE_BYTES, fn), "smem");
-    cu_check(driver().OccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, flame::BLOCK_WIDTH, 0), "occupancy");
+    cu_check(driver().OccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, f.options().block_width, 0), "occupancy");
 }
 
 void flame_read_counters(flame& f, unsigned long long* out, int n) {

@@ -99,7 +99,7 @@ def _norm_l1(a, b):
 
 
 def _gpu_histogram(rfk, flame, W, H, P, TS, passes, calls, seed, **options):
-    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=1, min_blocks=0)
+    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=1, min_blocks=0, block_width=256, deal_period=1)
     if options:
         flame.set_options(**options)
     rfk.set_sim_parameters(P, TS, 64, seed=seed)
@@ -191,7 +191,7 @@ def test_draw_requires_warmup_and_tracks_state(gpu_ready, rfk, compiler):
 def test_render_frame_end_to_end(gpu_ready, rfk, flame, oracle, oracle_mod):
     """host-buffer frame: image statistically matches the oracle's frame of the same sample count"""
     W, H, P, TS = 320, 180, 256 * 16 * 32, 32
-    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
+    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1)
     rfk.set_sim_parameters(P, TS, 64, seed=777)
     img = np.empty((H, W, 4), dtype=np.uint8)
     fimg = np.empty((H, W, 4), dtype=np.float32)

@@ -36,6 +36,12 @@ def main():
         ("default", {}),
         ("min_blocks4", dict(min_blocks=4)),
         ("min_blocks6", dict(min_blocks=6)),
+        ("min_blocks7", dict(min_blocks=7)),
+        ("min_blocks8", dict(min_blocks=8)),
+        ("block128", dict(block_width=128)),
+        ("block512", dict(block_width=512)),
+        ("deal_period2", dict(deal_period=2)),
+        ("deal_period4", dict(deal_period=4)),
         ("warp_aggregate", dict(warp_aggregate=1)),
         ("math0_libdevice", dict(math_mode=0)),
         ("math2_fast", dict(math_mode=2)),
@@ -46,7 +52,7 @@ def main():
     if "--big" in sys.argv:
         sizes.append((15360, 8640))
     for name, opt in variants:
-        base = dict(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
+        base = dict(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1)
         base.update(opt)
         t0 = time.time()
         flame.set_options(**base)
@@ -64,7 +70,7 @@ def main():
             out.append(rec)
             del bins
     # warm kernel (no histogram): the pure iteration rate
-    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0)
+    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1)
     torch.cuda.synchronize()
     t0 = time.time()
     flame.warmup(256, 1.2 / 60)
