@@ -32,6 +32,7 @@ struct rfk_iter_params {
     unsigned long long* counters;       // [0] binned samples (buffers.glsl:31-34), [1 + i] picks of xform i
     float ss_affine[6];                 // flame.glsl:22
     int bin_w, bin_h;                   // flame.glsl:17
+    float bin_wf, bin_hf;               // the same as binary32 (exact: both are below 2^24)
     int num_iter;
     int ppt;                            // particles per temporal sample
     int first_run;                      // flame.glsl:13
@@ -62,15 +63,15 @@ __device__ __forceinline__ float2 rfk_sample_point(unsigned int i, int bits, flo
     return make_float2((float)((double)fx * 2.0 - 1.0), (float)((double)fy * 2.0 - 1.0));
 }
 
-// flame.glsl:78-84: screen affine, floor, bounds and opacity test, row flip.
-// Returns the bin index or -1. Non-finite positions never bin (the reference leaves
-// ivec2(floor(NaN)) undefined).
-__device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const float* ss, int W, int H) {
-    float px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
-    float py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
-    float fx = floorf(px), fy = floorf(py);
-    if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)W && fy < (float)H && w > 0.0f)) return -1;
-    return (H - (int)fy - 1) * W + (int)fx;
+// flame.glsl:78-84: screen affine, floor, bounds and opacity test, row flip. Returns the bin index or -1.
+// coords = ivec2(floor(pos)) lies in [0, W) x [0, H) exactly when 0 <= pos.x < W and 0 <= pos.y < H (W, H integers),
+// so the test runs on the un-floored position (NaN fails every comparison: non-finite positions never bin, where the
+// reference leaves ivec2(floor(NaN)) undefined), and inside the bounds truncation equals floor.
+__device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const float* ss, int W, int H, float Wf, float Hf) {
+    const float px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
+    const float py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
+    if (!(px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f)) return -1;
+    return (H - __float2int_rz(py) - 1) * W + __float2int_rz(px);
 }
 
 __device__ __forceinline__ unsigned int rfk_palette_index(float z) {
@@ -106,7 +107,7 @@ __device__ __forceinline__ float4 rfk_reduce_peers(unsigned int mask, unsigned i
 template <bool DRAW>
 __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     __shared__ float4 pal[256];
-    __shared__ float ex_x[2][RFK_BLOCK], ex_y[2][RFK_BLOCK], ex_c[2][RFK_BLOCK];
+    __shared__ float ex[2][3][RFK_BLOCK];  // re-deal exchange: [double buffer][x, y, colour][slot]
 #if RFK_COUNT_XFORMS
     __shared__ unsigned int xcount[RFK_NUM_XFORMS + 1];
 #endif
@@ -139,13 +140,18 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     unsigned int binned = 0;
     int parity = 0;
 
+    // flame.glsl:51-53: the first thread of a workgroup burns one randf() per pass to pick the group's xform. Here
+    // every lane burns one every 32 iterations and iteration i uses lane (i mod 32)'s draw: the same number of extra
+    // draws per warp, all lanes active when they are made.
+    float pick_pool = 0.0f;
+    int pick_count = 0;
     auto pick_xform = [&]() -> int {
 #if RFK_PER_LANE_XFORM
         return get_xform_id(rfk_randf(rs));
 #else
-        float u = 0.0f;
-        if (lane == 0) u = rfk_randf(rs);  // flame.glsl:51-53: the first thread of the group burns one draw
-        u = __shfl_sync(0xffffffffu, u, 0);
+        if ((pick_count & 31) == 0) pick_pool = rfk_randf(rs);
+        const float u = __shfl_sync(0xffffffffu, pick_pool, pick_count & 31);
+        pick_count++;
   #if RFK_NUM_XFORMS <= 33
         unsigned int vote = __ballot_sync(0xffffffffu, cum_valid && cum >= u);
         return vote ? __ffs(vote) - 1 : RFK_NUM_XFORMS - 1;
@@ -158,9 +164,11 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     auto deal = [&](int) {
         deal_key = deal_key * 1664525u + 1013904223u;  // CTA-uniform
         unsigned int j = rfk_deal_slot(tid, deal_key);
-        ex_x[parity][j] = x; ex_y[parity][j] = y; ex_c[parity][j] = c;
+        float* out = &ex[parity][0][j];
+        out[0] = x; out[RFK_BLOCK] = y; out[2 * RFK_BLOCK] = c;
         __syncthreads();
-        x = ex_x[parity][tid]; y = ex_y[parity][tid]; c = ex_c[parity][tid];
+        const float* in = &ex[parity][0][tid];
+        x = in[0]; y = in[RFK_BLOCK]; c = in[2 * RFK_BLOCK];
         parity ^= 1;
     };
 
@@ -203,7 +211,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
                 fx = q.x; fy = q.y; fc = q.z; fw = q.w * r.w;
             }
 #endif
-            const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h);
+            const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf);
 #if RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC
             const unsigned int hit = __ballot_sync(0xffffffffu, idx >= 0);
             if (idx >= 0) {
@@ -303,6 +311,6 @@ extern "C" __global__ void rfk_bucket_index(int n, const float* __restrict__ xyz
                                             int* idx_out, int* pal_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    idx_out[i] = rfk_bin_index(xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 3], bp.ss_affine, bp.bin_w, bp.bin_h);
+    idx_out[i] = rfk_bin_index(xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 3], bp.ss_affine, bp.bin_w, bp.bin_h, (float)bp.bin_w, (float)bp.bin_h);
     pal_out[i] = (int)rfk_palette_index(xyzw[4 * i + 2]);
 }

@@ -162,6 +162,7 @@ struct rfk_iter_params_host {  // must match rfk_iter_params in chaos_kernels.cu
     unsigned long long* counters;
     float ss_affine[6];
     int bin_w, bin_h;
+    float bin_wf, bin_hf;
     int num_iter;
     int ppt;
     int first_run;
@@ -414,13 +415,15 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
     if (!bins || bins_width == 0 || bins_len < bins_width) throw std::invalid_argument("draw_to_bins: bad bins buffer");
     flame_device& d = *device_;
     const std::size_t W = bins_width, H = bins_len / bins_width;  // flame.cpp:290
-    if (W > 0x7fffffff / 4 || H > 0x7fffffff / 4 || W * H > 0x7fffffffull) throw std::invalid_argument("draw_to_bins: histogram too large for 32-bit bin indices");
+    if (W >= (1u << 24) || H >= (1u << 24) || W * H > 0x7fffffffull) throw std::invalid_argument("draw_to_bins: histogram too large for 32-bit bin indices");
 
     rfk_iter_params_host p = base_params(*this);
     auto ss = screen_space_affine(W, H);
     for (int i = 0; i < 6; i++) p.ss_affine[i] = ss[i];
     p.bin_w = (int)W;
     p.bin_h = (int)H;
+    p.bin_wf = (float)W;
+    p.bin_hf = (float)H;
     p.bins = reinterpret_cast<float4*>(bins);
     p.num_iter = num_iter;
     p.first_run = 0;
