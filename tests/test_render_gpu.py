@@ -242,3 +242,75 @@ def test_cli_renders_animation_frames(gpu_ready, rfk, tmp_path):
     imgs = [np.array(Image.open(out % k)) for k in range(3)]
     assert all(i.shape == (180, 320, 4) and i[..., :3].max() > 100 and (i[..., 3] == 255).all() for i in imgs)
     assert np.abs(imgs[0].astype(int) - imgs[2].astype(int)).mean() > 0.5  # the xforms rotated between frames
+
+
+def _linear_genome(n, final=False):
+    rng = np.random.default_rng(n)
+    xf = []
+    for i in range(n):
+        coefs = " ".join("%.4f" % v for v in (rng.normal(0, 0.45, 6)))
+        xf.append('<xform weight="%.3f" color="%.3f" color_speed="0.5" animate="1" linear="1" spherical="%.2f" coefs="%s" opacity="1"/>' % (rng.uniform(0.1, 1), rng.random(), 0.05 * (i % 3), coefs))
+    if final:
+        xf.append('<finalxform color="0.5" color_speed="0.2" linear="1" coefs="0.9 0 0 0.9 0.05 0" opacity="1"/>')
+    from conftest import GENOME_TEMPLATE
+    return GENOME_TEMPLATE % "\n".join(xf)
+
+
+@pytest.mark.parametrize("n,final", [(1, False), (2, True), (33, False), (34, True), (40, False)])
+def test_xform_count_edge_cases(gpu_ready, rfk, compiler, vt, oracle_mod, n, final):
+    """1 xform (the select template has no fall-through return), exactly 33 (largest warp-vote case), 34 and 40
+    (if-chain fallback), with and without a final xform: selection bit-exact, single step within 1e-5, histogram mass conserved"""
+    xml = _linear_genome(n, final)
+    f = rfk.Flame.load_flame_string(xml, compiler)
+    assert f is not None, rfk.Flame.last_error()
+    of = oracle_mod.load_flame_string(xml, vt)
+    orc = oracle_mod.Oracle(of, vt)
+    ratio = np.concatenate([np.random.default_rng(1).random(50000).astype(np.float32), [0.0, 1.0]])
+    got = f.select_xform(ratio)
+    assert np.array_equal(got, orc.select_xform(ratio)) and got.min() >= 0 and got.max() == n - 1
+    rng = np.random.default_rng(2)
+    m = 20000
+    xyz = np.concatenate([rng.normal(0, 1, (m, 2)), rng.random((m, 1))], axis=1).astype(np.float32)
+    ids = rng.integers(-1 if final else 0, n, m).astype(np.int32)
+    states = rng.integers(0, 2**32, (m, 4), dtype=np.uint64).astype(np.uint32)
+    a, ra = f.single_step(xyz, ids, states)
+    b, rb = orc.single_step(xyz, ids, states)
+    assert np.array_equal(ra, rb)
+    ok = np.isfinite(b).all(axis=1)
+    err = np.linalg.norm(a[ok, :2] - b[ok, :2], axis=1) / np.maximum(1.0, np.linalg.norm(b[ok, :2], axis=1))
+    assert (err <= 1e-5).mean() > 0.999
+    f.set_options(count_xforms=1) if n <= 40 else None
+    W, H, P, TS = 128, 96, 256 * 2 * 8, 8
+    rfk.set_sim_parameters(P, TS, 8, seed=n)
+    f.warmup(8, TSS)
+    buf = rfk.DeviceBuffer(W * H * 16)
+    buf.zero_out()
+    binned = f.draw_to_bins(buf.ptr, W * H, W, 32)
+    bins = buf.download(np.float32, (H, W, 4))
+    buf.free()
+    assert binned > 0 and abs(float(bins[..., 3].sum()) - binned) < 0.5
+    picks = f.xform_counts(n).astype(np.float64)
+    assert picks.sum() == P * 32
+    w = f.copy_flame_data_to_buffer()[[m_["weight"] for m_ in of.buffer_map["xforms"]]]
+    assert np.abs(picks / picks.sum() - w).max() < 0.05
+
+
+def test_non_default_stream(gpu_ready, rfk, compiler):
+    """rfk_set_stream: all work is ordered on the caller's stream"""
+    import torch
+    from conftest import GENOME
+    f = rfk.Flame.load_flame(GENOME, compiler)
+    s = torch.cuda.Stream()
+    rfk.lib().rfk_set_stream(s.cuda_stream)
+    try:
+        rfk.set_sim_parameters(256 * 8 * 16, 16, 8, seed=4)
+        W, H = 160, 90
+        with torch.cuda.stream(s):
+            bins = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
+        s.synchronize()
+        f.warmup(8, TSS)
+        n = f.draw_to_bins(bins.data_ptr(), W * H, W, 16)
+        s.synchronize()
+        assert n > 0 and int(round(float(bins.view(-1, 4)[:, 3].sum()))) == n
+    finally:
+        rfk.lib().rfk_set_stream(None)
