@@ -18,8 +18,8 @@
 //
 // PARITY UNPINNED: the reference has no tests, golden vectors or fixtures
 // (SURVEY.md §4), and it cannot be built or run here (GL + 12 fetched dependencies).
-// The pieces that DO compile from /root/reference (jsf32, hammersley — oracle/Makefile
-// -> oracle/_ref/) pin the corresponding functions below; everything else is pinned only
+// The pieces that DO compile from /root/reference (jsf32, hammersley, the affine helpers of flame.hpp —
+// oracle/Makefile -> oracle/_ref/) pin the corresponding functions; everything else is pinned only
 // by reading the reference source.
 //
 // Where the reference leaves behaviour open, the oracle fixes it and says so:

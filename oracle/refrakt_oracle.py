@@ -20,10 +20,10 @@ The generated GLSL is compiled for the CPU against glsl_shim.hpp with g++ (-ffp-
 into oracle/_build/ and driven through ctypes.
 
 PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
-and cannot be built or run here. Pins that exist: jsf32 and hammersley compile from the
-reference sources (oracle/Makefile -> oracle/_ref/libref_pins.so) and are compared with
-this restatement by tests/test_oracle_pins.py; SURVEY.md Appendix A/B values are checked
-by tests/test_oracle_golden.py.
+and cannot be built or run here. Pins that exist: jsf32, hammersley and the affine helpers of
+flame.hpp compile from the reference sources (oracle/Makefile -> oracle/_ref/libref_pins*.so)
+and are compared with this restatement, together with the SURVEY.md Appendix A/B values, by
+tests/test_oracle_golden.py.
 """
 from __future__ import annotations
 

@@ -1,0 +1,52 @@
+// TEST INFRASTRUCTURE. Declarations-only stand-in for glad (OpenGL loader), just enough for the reference's
+// headers (src/buffer_objects.hpp, src/shaders.hpp) to parse so that the PURE inline helpers of src/flame.hpp
+// (rotate_affine / scale_affine / translate_affine) can be compiled from the reference source and used as pins.
+// Every GL entry point is an empty inline template: nothing here touches a GL context, and the wrappers in
+// ref_pins_flame.cpp only call the reference's pure arithmetic helpers.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+#include <array>
+#include <iostream>
+#include <cmath>
+typedef unsigned int GLuint; typedef int GLint; typedef unsigned int GLenum; typedef int GLsizei; typedef float GLfloat;
+typedef unsigned char GLboolean; typedef char GLchar; typedef std::ptrdiff_t GLsizeiptr; typedef std::ptrdiff_t GLintptr; typedef unsigned int GLbitfield;
+#define RFK_GLC(name, value) static const GLenum name = value;
+RFK_GLC(GL_DYNAMIC_STORAGE_BIT, 0x0100) RFK_GLC(GL_DYNAMIC_COPY, 0x88EA) RFK_GLC(GL_R32UI, 0x8236) RFK_GLC(GL_RED_INTEGER, 0x8D94) RFK_GLC(GL_UNSIGNED_INT, 0x1405)
+RFK_GLC(GL_UNIFORM_BUFFER, 0x8A11) RFK_GLC(GL_TEXTURE_2D, 0x0DE1) RFK_GLC(GL_RGBA32F, 0x8814) RFK_GLC(GL_RGBA32UI, 0x8D70) RFK_GLC(GL_RGBA32I, 0x8D82)
+RFK_GLC(GL_RGBA, 0x1908) RFK_GLC(GL_UNSIGNED_BYTE, 0x1401) RFK_GLC(GL_FRAMEBUFFER, 0x8D40) RFK_GLC(GL_COLOR_ATTACHMENT0, 0x8CE0) RFK_GLC(GL_FLOAT, 0x1406)
+RFK_GLC(GL_TEXTURE_MIN_FILTER, 0x2801) RFK_GLC(GL_TEXTURE_MAG_FILTER, 0x2800) RFK_GLC(GL_LINEAR, 0x2601) RFK_GLC(GL_NEAREST, 0x2600)
+RFK_GLC(GL_TEXTURE_WRAP_S, 0x2802) RFK_GLC(GL_TEXTURE_WRAP_T, 0x2803) RFK_GLC(GL_CLAMP_TO_EDGE, 0x812F) RFK_GLC(GL_CLAMP_TO_BORDER, 0x812D)
+RFK_GLC(GL_COMPUTE_SHADER, 0x91B9) RFK_GLC(GL_VERTEX_SHADER, 0x8B31) RFK_GLC(GL_FRAGMENT_SHADER, 0x8B30) RFK_GLC(GL_COMPILE_STATUS, 0x8B81)
+RFK_GLC(GL_LINK_STATUS, 0x8B82) RFK_GLC(GL_INFO_LOG_LENGTH, 0x8B84) RFK_GLC(GL_FALSE, 0) RFK_GLC(GL_TRUE, 1) RFK_GLC(GL_INT, 0x1404)
+RFK_GLC(GL_SHADER_STORAGE_BUFFER, 0x90D2) RFK_GLC(GL_DRAW_FRAMEBUFFER, 0x8CA9) RFK_GLC(GL_READ_FRAMEBUFFER, 0x8CA8) RFK_GLC(GL_RGBA_INTEGER, 0x8D99)
+RFK_GLC(GL_TEXTURE_BORDER_COLOR, 0x1004) RFK_GLC(GL_REPEAT, 0x2901) RFK_GLC(GL_FRAMEBUFFER_COMPLETE, 0x8CD5)
+// any GL call in an inline body of the reference's headers resolves to an empty variadic template
+#define RFK_GLF(name) template <typename... A> void name(A...) {}
+RFK_GLF(glCreateBuffers) RFK_GLF(glNamedBufferStorage) RFK_GLF(glNamedBufferData) RFK_GLF(glDeleteBuffers) RFK_GLF(glNamedBufferSubData)
+RFK_GLF(glGetNamedBufferSubData) RFK_GLF(glClearNamedBufferData) RFK_GLF(glBindBufferBase) RFK_GLF(glCreateTextures) RFK_GLF(glTextureStorage2D)
+RFK_GLF(glDeleteTextures) RFK_GLF(glGetTextureImage) RFK_GLF(glTextureParameteri) RFK_GLF(glTextureParameterfv) RFK_GLF(glCreateFramebuffers) RFK_GLF(glDeleteFramebuffers)
+RFK_GLF(glBindFramebuffer) RFK_GLF(glNamedFramebufferTexture) RFK_GLF(glFramebufferTexture) RFK_GLF(glFramebufferTexture2D) RFK_GLF(glUniform1i) RFK_GLF(glUniform1ui) RFK_GLF(glUniform1f)
+RFK_GLF(glUniform2fv) RFK_GLF(glUniform3fv) RFK_GLF(glUniform4fv) RFK_GLF(glUniform2uiv) RFK_GLF(glUniform3uiv) RFK_GLF(glUniform4uiv)
+RFK_GLF(glUniform2iv) RFK_GLF(glUniform3iv) RFK_GLF(glUniform4iv) RFK_GLF(glUniformMatrix4fv) RFK_GLF(glUniform1fv) RFK_GLF(glUseProgram)
+RFK_GLF(glShaderSource) RFK_GLF(glCompileShader) RFK_GLF(glGetShaderiv) RFK_GLF(glGetShaderInfoLog) RFK_GLF(glDeleteShader)
+RFK_GLF(glAttachShader) RFK_GLF(glLinkProgram) RFK_GLF(glGetProgramiv) RFK_GLF(glGetProgramInfoLog) RFK_GLF(glDeleteProgram) RFK_GLF(glDetachShader)
+RFK_GLF(glDrawBuffers) RFK_GLF(glBindTexture) RFK_GLF(glClearTexImage) RFK_GLF(glBindBuffer) RFK_GLF(glGenFramebuffers) RFK_GLF(glTexImage2D) RFK_GLF(glGenTextures)
+template <typename... A> GLuint glCreateShader(A...) { return 0; }
+template <typename... A> GLuint glCreateProgram(A...) { return 0; }
+template <typename... A> GLint glGetUniformLocation(A...) { return 0; }
+template <typename... A> GLenum glCheckFramebufferStatus(A...) { return 0; }
+template <typename... A> GLenum glCheckNamedFramebufferStatus(A...) { return 0; }
+// further names the reference's headers mention (values are never used)
+RFK_GLC(GL_DYNAMIC_DRAW, 0)
+RFK_GLC(GL_R8, 0)
+RFK_GLC(GL_READ_WRITE, 0)
+RFK_GLC(GL_RED, 0)
+RFK_GLC(GL_RGB, 0)
+RFK_GLC(GL_TEXTURE_BINDING_2D, 0)
+RFK_GLF(glGenerateMipmap)
+RFK_GLF(glGetIntegerv)
+RFK_GLF(glMapNamedBuffer)
+RFK_GLF(glTexParameteri)
+RFK_GLF(glUnmapNamedBuffer)

@@ -87,3 +87,36 @@ def test_oracle_render_is_self_consistent(oracle):
     assert n == int(round(float(bins[..., 3].sum())))
     assert 0.7 < n / (256 * 2 * 8 * 32) < 0.9
     assert oracle.xform_picks(10).sum() == 256 * 2 * 8 * 32
+
+
+PINS_FLAME = os.path.join(ROOT, "oracle", "_ref", "libref_pins_flame.so")
+
+
+@pytest.mark.skipif(not os.path.exists(PINS_FLAME), reason="oracle/_ref flame.hpp pins not built")
+def test_affine_helpers_match_reference_compiled_flame_hpp(oracle, oracle_mod, rfk, flame):
+    """rotate/scale/translate_affine and the screen-space affine of draw_to_bins, compiled from the reference's
+    src/flame.hpp:97-128, against the oracle's and the product's restatements — bit-exact"""
+    ref = ctypes.CDLL(PINS_FLAME)
+    fp = ctypes.POINTER(ctypes.c_float)
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        a = rng.normal(0, 2, 6).astype(np.float32)
+        deg, s = np.float32(rng.uniform(-1000, 1000)), np.float32(rng.uniform(0.01, 500))
+        t = rng.normal(0, 3, 2).astype(np.float32)
+        out = np.zeros(6, dtype=np.float32)
+        ref.ref_rotate_affine(a.ctypes.data_as(fp), ctypes.c_float(deg), out.ctypes.data_as(fp))
+        assert np.array_equal(out.view(np.uint32), np.array(oracle_mod.rotate_affine(a, deg), dtype=np.float32).view(np.uint32))
+        assert np.array_equal(out.view(np.uint32), rfk.rotate_affine(a, deg).view(np.uint32))
+        ref.ref_scale_affine(a.ctypes.data_as(fp), ctypes.c_float(s), out.ctypes.data_as(fp))
+        assert np.array_equal(out.view(np.uint32), np.array(oracle_mod.scale_affine(a, s), dtype=np.float32).view(np.uint32))
+        assert np.array_equal(out.view(np.uint32), rfk.scale_affine(a, s).view(np.uint32))
+        ref.ref_translate_affine(a.ctypes.data_as(fp), t.ctypes.data_as(fp), out.ctypes.data_as(fp))
+        assert np.array_equal(out.view(np.uint32), np.array(oracle_mod.translate_affine(a, t), dtype=np.float32).view(np.uint32))
+        assert np.array_equal(out.view(np.uint32), rfk.translate_affine(a, t).view(np.uint32))
+    f = oracle.flame
+    for W, H in ((1280, 720), (3840, 2160), (7680, 4320), (15360, 8640), (333, 77)):
+        out = np.zeros(6, dtype=np.float32)
+        ref.ref_screen_space_affine(ctypes.c_float(f.scale), ctypes.c_float(f.rotate), ctypes.c_float(f.center[0]), ctypes.c_float(f.center[1]),
+                                    ctypes.c_uint(f.size[1]), ctypes.c_ulong(W), ctypes.c_ulong(H), out.ctypes.data_as(fp))
+        assert np.array_equal(out.view(np.uint32), oracle_mod.screen_space_affine(f, W, H).view(np.uint32))
+        assert np.array_equal(out.view(np.uint32), flame.screen_space_affine(W, H).view(np.uint32))
