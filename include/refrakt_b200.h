@@ -239,6 +239,10 @@ int rfk_flame_single_step(rfk_flame* f, int n, const float* xyz, const int* xid,
 int rfk_flame_select_xform(rfk_flame* f, int n, const float* ratio, const float* fp, int* out);
 /* flame.glsl:78-84 per element: xyzw n x 4 (x, y, colour, opacity) -> bin index (-1 = rejected) and palette index */
 int rfk_flame_bucket_index(rfk_flame* f, int n, const float* xyzw, const float ss_affine[6], int width, int height, int* idx_out, int* palette_out);
+/* the macro grammar of the flame compiler: replace_macro / find_macros, src/util.cpp:6-23. Results are written to out
+ * (NUL-terminated; find_macros joins the names with '\n' in std::set order); returns the length or a negative code */
+int rfk_text_replace_macro(const char* str, const char* name, const char* value, char* out, size_t out_len);
+int rfk_text_find_macros(const char* str, char* out, size_t out_len);
 /* animate.tpl.glsl: the temporal_samples x param_count blocks, to host */
 int rfk_flame_animate(rfk_flame* f, float tss_width, int temporal_samples, float* out);
 

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE. C wrappers over reference code compiled from /root/reference
-// (see Makefile): make_sample_points (src/hammersley.cpp:29) and jsf32::warmup_ctx
-// (src/util.hpp:90). Used only to pin the oracle's restatement of those functions.
+// (see Makefile): make_sample_points (src/hammersley.cpp:29), jsf32::warmup_ctx (src/util.hpp:90) and
+// replace_macro / find_macros (src/util.cpp:6-23). Used only to pin the oracle's restatement of those functions.
 #include <array>
 #include <cstdint>
 #include <vector>
@@ -9,7 +9,23 @@
 
 std::vector<std::array<float, 4>> make_sample_points(std::uint32_t count);  // hammersley.cpp
 
+#include <cstring>
+
 extern "C" {
+// src/util.cpp:6-23 (compiled from the reference): the macro grammar of the flame compiler
+int ref_replace_macro(const char* str, const char* name, const char* value, char* out, int cap) {
+    std::string r = replace_macro(str, name, value);
+    if ((int)r.size() + 1 > cap) return -1;
+    std::memcpy(out, r.c_str(), r.size() + 1);
+    return (int)r.size();
+}
+int ref_find_macros(const char* str, char* out, int cap) {  // names joined by '\n', std::set order
+    std::string joined;
+    for (auto& m : find_macros(str)) joined += m + "\n";
+    if ((int)joined.size() + 1 > cap) return -1;
+    std::memcpy(out, joined.c_str(), joined.size() + 1);
+    return (int)joined.size();
+}
 void ref_make_sample_points(std::uint32_t count, float* out) {
     auto pts = make_sample_points(count);
     for (std::uint32_t i = 0; i < count; i++)

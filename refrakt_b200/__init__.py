@@ -135,6 +135,8 @@ SIGNATURES = {
     "rfk_flame_select_xform": (_i, [_vp, _i, _fpp, _fpp, _ipp]),
     "rfk_flame_bucket_index": (_i, [_vp, _i, _fpp, _fpp, _i, _i, _ipp, _ipp]),
     "rfk_flame_animate": (_i, [_vp, _f, _i, _fpp]),
+    "rfk_text_replace_macro": (_i, [_cp, _cp, _cp, _cp, _sz]),
+    "rfk_text_find_macros": (_i, [_cp, _cp, _sz]),
 }
 
 _lib = None
@@ -498,6 +500,20 @@ def make_shuffle_buffers(size: int, count: int, seed: int = 0) -> np.ndarray:
     out = buf.download(np.uint32, (count, size))
     buf.free()
     return out
+
+
+def replace_macro(text: str, name: str, value: str) -> str:
+    """util.cpp:6-9"""
+    buf = C.create_string_buffer(len(text) + (len(value) + 2) * (text.count("$") + 1) + 16)
+    _check(lib().rfk_text_replace_macro(text.encode(), name.encode(), value.encode(), buf, len(buf)), "replace_macro")
+    return buf.value.decode()
+
+
+def find_macros(text: str) -> set:
+    """util.cpp:11-23"""
+    buf = C.create_string_buffer(len(text) + 16)
+    _check(lib().rfk_text_find_macros(text.encode(), buf, len(buf)), "find_macros")
+    return set(buf.value.decode().split("\n")) - {""}
 
 
 def write_png(path: str, rgba8: np.ndarray):

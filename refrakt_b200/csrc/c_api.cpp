@@ -616,6 +616,21 @@ int rfk_flame_bucket_index(rfk_flame* f, int n, const float* xyzw, const float s
         return RFK_OK;
     });
 }
+static int copy_out(const std::string& r, char* out, size_t out_len) {
+    if (!out || r.size() + 1 > out_len) return fail(RFK_E_INVALID, "output buffer too small");
+    std::memcpy(out, r.c_str(), r.size() + 1);
+    return (int)r.size();
+}
+int rfk_text_replace_macro(const char* str, const char* name, const char* value, char* out, size_t out_len) {
+    if (!str || !name || !value) return fail(RFK_E_INVALID, "null argument");
+    return copy_out(replace_macro(str, name, value), out, out_len);
+}
+int rfk_text_find_macros(const char* str, char* out, size_t out_len) {
+    if (!str) return fail(RFK_E_INVALID, "null argument");
+    std::string joined;
+    for (auto& m : find_macros(str)) joined += m + "\n";
+    return copy_out(joined, out, out_len);
+}
 int rfk_flame_animate(rfk_flame* f, float tss_width, int temporal_samples, float* out) {
     return guarded([&]() -> int {
         if (!f || !out || temporal_samples <= 0) throw std::invalid_argument("rfk_flame_animate: bad argument");

@@ -120,3 +120,26 @@ def test_affine_helpers_match_reference_compiled_flame_hpp(oracle, oracle_mod, r
                                     ctypes.c_uint(f.size[1]), ctypes.c_ulong(W), ctypes.c_ulong(H), out.ctypes.data_as(fp))
         assert np.array_equal(out.view(np.uint32), oracle_mod.screen_space_affine(f, W, H).view(np.uint32))
         assert np.array_equal(out.view(np.uint32), flame.screen_space_affine(W, H).view(np.uint32))
+
+
+@pytest.mark.skipif(not os.path.exists(PINS), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_macro_grammar_matches_reference_compiled_util_cpp(oracle_mod, vt, rfk):
+    """replace_macro / find_macros (src/util.cpp:6-23, std::regex) against the oracle's restatement, on every snippet of
+    variations.yaml and on adversarial strings (macro at the end of the text, adjacent macros, prefixes of longer names)"""
+    ref = ctypes.CDLL(PINS)
+    if not hasattr(ref, "ref_replace_macro"):
+        pytest.skip("prebuilt pins predate the util.cpp wrappers")
+    texts = [v.source for v in vt.vars.values()] + [v.result for v in vt.vars.values()] + list(vt.common.values())
+    texts += ["$x", "$x$x $y", "a$x)", "$xy + $x_y + $x1 + $x ", "$$x $x$ ", "", "$weight *$v", "$c10*$c1 $c100 ", "$r;$r\n$r", "x$y.z$v,"]
+    names = ["x", "y", "v", "weight", "r", "c10", "c1", "result", "julian_power", "a"]
+    buf = ctypes.create_string_buffer(1 << 16)
+    for t in texts:
+        n = ref.ref_find_macros(t.encode(), buf, len(buf))
+        assert n >= 0
+        got = set(buf.value.decode().split("\n")) - {""}
+        assert got == oracle_mod.find_macros(t), t
+        for name in names:
+            n = ref.ref_replace_macro(t.encode(), name.encode(), b"fp[7]", buf, len(buf))
+            assert n >= 0 and buf.value.decode() == oracle_mod.replace_macro(t, name, "fp[7]"), (t, name)
+            assert buf.value.decode() == rfk.replace_macro(t, name, "fp[7]"), (t, name)  # the product's own (csrc/textutil.cpp)
+        assert rfk.find_macros(t) == oracle_mod.find_macros(t), t
