@@ -115,17 +115,22 @@ __device__ __forceinline__ int estimator_radius_of(float density, const density_
     return max(p.estimator_min, r);
 }
 
+// x^g for x > 0 through lg2 / ex2 (relative error ~1e-6 for the exponents 1/gamma used here; the outputs are
+// colours in [0, 1] compared at 1e-4 / 1 LSB)
+__device__ __forceinline__ float pow_pos(float x, float g) { return exp2f(g * __log2f(x)); }
+
 // tonemap.glsl:25-36; an empty pixel (alpha 0) is 0 * (0/0) in the reference — defined as black here
 __device__ __forceinline__ float4 tonemap_pixel(float4 color, const density_params& p) {
     if (!(color.w > 0.0f)) return make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-    float s = .5f * p.brightness * logf(1.0f + color.w * p.scale_constant) * 0.434294481903251827651128918916f / color.w;
+    float s = .5f * p.brightness * logf(1.0f + color.w * p.scale_constant) * 0.434294481903251827651128918916f / color.w;  // (the SFU log loses the small arguments)
     color.x *= s; color.y *= s; color.z *= s; color.w *= s;
     float inv_gamma = 1.0f / p.gamma;
-    float z = powf(color.w, inv_gamma);
+    float z = pow_pos(color.w, inv_gamma);
     float gamma_factor = z / color.w;
     float v = p.vibrancy;
     auto chan = [&](float ch) {
-        float m = powf(ch, inv_gamma) * (1.0f - v) + (gamma_factor * ch) * v;
+        // mix(pow(ch, 1/gamma), gamma_factor * ch, vibrancy); at vibrancy 1 the first term is multiplied by zero
+        float m = v == 1.0f ? gamma_factor * ch : (ch > 0.0f ? pow_pos(ch, inv_gamma) : 0.0f) * (1.0f - v) + (gamma_factor * ch) * v;
         return fminf(fmaxf(m, 0.0f), 1.0f);
     };
     return make_float4(chan(color.x), chan(color.y), chan(color.z), 1.0f);
@@ -142,14 +147,14 @@ constexpr int DE_MAX_COUNTERS = 2048;  // (32 + 2 * 100) rows x 8 column chunks
 //
 // A CTA produces a 32 x 32 output tile; a warp owns 4 rows x 32 columns and keeps their float4 sums in
 // registers (no atomics, fixed summation order => deterministic).
-//  A. The CTA scans its (32 + 2R)^2 source window once. A bin is a candidate when its density is below the
-//     threshold of radius 1 (one 4-byte load and a compare for the dense bulk of the image), its exact
-//     radius (the reference's int(R / pow(d, curve))) is >= 1 and its footprint reaches the tile.
-//     Candidates are counted per (row, 32-column chunk), prefix-summed, and written to a shared-memory list
-//     in row-major order with their colour and the per-radius constants.
-//  B. Every warp walks the list entries whose source row can reach its 4 rows (a contiguous range, the list
-//     being row-major) and accumulates; lanes are output columns.
-// Lists longer than DE_CAP are processed in batches (rescan + walk).
+//  A0. The CTA reads the densities of its (32 + 2R)^2 source window once and stores one radius byte per bin in
+//      shared memory: 0 unless the density is below the threshold of radius 1 (one 4-byte load and a compare for
+//      the dense bulk of the image), the exact radius (the reference's int(R / pow(d, curve))) is >= 1 and the
+//      footprint reaches the tile.
+//  A1-A3. Candidates are counted per (row, 32-column chunk), prefix-summed, and written to a shared-memory list in
+//      row-major order with their colour and the per-radius constants (batches of DE_CAP).
+//  B.  Every warp walks the list entries whose source row can reach its 4 rows (a contiguous range, the list being
+//      row-major) and accumulates; lanes are output columns.
 template <bool DENSITY, bool TONEMAP>
 __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
                                                                      uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
@@ -158,6 +163,7 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
     __shared__ float4 s_col[DE_CAP];
     __shared__ int4 s_geo[DE_CAP];    // source column, source row (cy), radius
     __shared__ float4 s_k[DE_CAP];    // 2/S, 1/S^2, (2/pi)/r^2
+    extern __shared__ unsigned char s_rad[];  // [nrows][pitch] radius of every window bin, 0 = not a candidate
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * DE_TILE_W, ty0 = blockIdx.y * DE_TILE_H;
@@ -171,6 +177,7 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
 
     if (DENSITY) {
         const int R = max(p.estimator_radius, p.estimator_min);
+        const float t_any = p.thresholds[1];  // no bin denser than this has a radius >= 1 (conservative)
         // radius-0 sources: out[cy][ox] takes bin (ox + 1, cy)
         if (p.estimator_min == 0) {
 #pragma unroll
@@ -178,36 +185,37 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
                 int cy = oy0 + k, bx = ox + 1;
                 if (cy < H && bx < W) {
                     float4 c = __ldg(bins + (size_t)(H - 1 - cy) * W + bx);
-                    if (c.w != 0.0f && estimator_radius_of(c.w, p) == 0) acc[k] = c;
+                    if (c.w != 0.0f && (c.w > t_any || estimator_radius_of(c.w, p) == 0)) acc[k] = c;
                 }
             }
         }
         if (R >= 1) {
-            const int win_x0 = tx0 + 1 - R, win_w = DE_TILE_W + 2 * R, nch = (win_w + 31) >> 5;
+            const int win_x0 = tx0 + 1 - R, win_w = DE_TILE_W + 2 * R, nch = (win_w + 31) >> 5, pitch = nch << 5;
             const int win_y0 = ty0 - R, nrows = DE_TILE_H + 2 * R;
             const int ncnt = nrows * nch;
-            const float t_any = p.thresholds[1];
 
-            // exact radius and reach test of the bin this lane looks at; 0 = not a candidate
-            auto candidate_radius = [&](int row, int c, float* d_out) -> int {
-                const int cy = win_y0 + row, col = (c << 5) + lane, bx = win_x0 + col;
-                if (cy < 0 || cy >= H || col >= win_w || bx < 0 || bx >= W) return 0;
-                const float d = __ldg(&bins[(size_t)(H - 1 - cy) * W + bx].w);
-                if (!(d != 0.0f && d <= t_any)) return 0;
-                const int r = estimator_radius_of(d, p);
-                if (r < 1) return 0;
-                if (bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1) return 0;
-                *d_out = d;
-                return r;
-            };
-
-            // A1: counts per (row, chunk)
-            for (int row = warp; row < nrows; row += DE_WARPS)
+            // A0: radius byte of every window bin
+            for (int row = warp; row < nrows; row += DE_WARPS) {
+                const int cy = win_y0 + row;
                 for (int c = 0; c < nch; c++) {
-                    float d;
-                    unsigned int vote = __ballot_sync(0xffffffffu, candidate_radius(row, c, &d) > 0);
-                    if (lane == 0) s_off[row * nch + c] = __popc(vote);
+                    const int col = (c << 5) + lane, bx = win_x0 + col;
+                    int r = 0;
+                    if (cy >= 0 && cy < H && col < win_w && bx >= 0 && bx < W) {
+                        const float d = __ldg(&bins[(size_t)(H - 1 - cy) * W + bx].w);
+                        if (d != 0.0f && d <= t_any) {
+                            r = estimator_radius_of(d, p);
+                            if (r < 1 || bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1) r = 0;
+                        }
+                    }
+                    s_rad[row * pitch + col] = (unsigned char)r;
                 }
+            }
+            __syncthreads();
+            // A1: counts per (row, chunk)
+            for (int i = warp; i < ncnt; i += DE_WARPS) {
+                unsigned int vote = __ballot_sync(0xffffffffu, s_rad[(i << 5) + lane] != 0);
+                if (lane == 0) s_off[i] = __popc(vote);
+            }
             __syncthreads();
             // A2: exclusive prefix sum over the counters
             {
@@ -247,15 +255,15 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
 
             for (int base = 0; base < total; base += DE_CAP) {
                 // A3: write this batch of the list
-                for (int row = warp; row < nrows; row += DE_WARPS) {
-                    const int first = s_off[row * nch], last = s_off[(row + 1) * nch];
-                    if (last <= base || first >= base + DE_CAP) continue;  // warp-uniform
+                for (int row = warp; row < nrows; row += DE_WARPS)
                     for (int c = 0; c < nch; c++) {
-                        float d = 0.0f;
-                        const int r = candidate_radius(row, c, &d);
-                        const unsigned int vote = __ballot_sync(0xffffffffu, r > 0);
-                        if (r > 0) {
-                            const int e = s_off[row * nch + c] + __popc(vote & ((1u << lane) - 1u)) - base;
+                        const int i = row * nch + c;
+                        const int first = s_off[i], last = s_off[i + 1];
+                        if (last == first || last <= base || first >= base + DE_CAP) continue;  // warp-uniform
+                        const int r = s_rad[(i << 5) + lane];
+                        const unsigned int vote = __ballot_sync(0xffffffffu, r != 0);
+                        if (r != 0) {
+                            const int e = first + __popc(vote & ((1u << lane) - 1u)) - base;
                             if (e >= 0 && e < DE_CAP) {
                                 const int cy = win_y0 + row, bx = win_x0 + (c << 5) + lane;
                                 s_col[e] = __ldg(&bins[(size_t)(H - 1 - cy) * W + bx]);
@@ -265,7 +273,6 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
                             }
                         }
                     }
-                }
                 __syncthreads();
                 // B: accumulate
                 const int e_lo = max(w_lo, base) - base, e_hi = min(w_hi, base + DE_CAP) - base;
@@ -361,8 +368,17 @@ void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, dens
     density_thresholds(p.thresholds, p.estimator_radius, p.estimator_min, p.estimator_curve);
     dim3 grid((p.W + DE_TILE_W - 1) / DE_TILE_W, (p.H + DE_TILE_H - 1) / DE_TILE_H);
     dim3 block(DE_THREADS);
-    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
-    else if (do_density) density_tonemap_kernel<true, false><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
+    // radius bytes of the (32 + 2R)^2 source window: 3.4 KB at R = 11, 58 KB at the maximum R = 100
+    const int R = p.estimator_radius > p.estimator_min ? p.estimator_radius : p.estimator_min;
+    const size_t rad_bytes = do_density ? (size_t)(DE_TILE_H + 2 * R) * (((DE_TILE_W + 2 * R + 31) >> 5) << 5) : 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(density_tonemap_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(density_tonemap_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        configured = true;
+    }
+    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, rad_bytes, s>>>(bins, out_f4, out_rgba8, p);
+    else if (do_density) density_tonemap_kernel<true, false><<<grid, block, rad_bytes, s>>>(bins, out_f4, out_rgba8, p);
     else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
 }
 
