@@ -228,6 +228,22 @@ typedef struct rfk_frame_stats {
 int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_out, float* image_out /* optional float4 */,
                      rfk_frame_stats* stats);
 
+/* ---- on-disk buffer cache in the reference's format (src/buffer_cache.hpp:12-60, src/buffer_cache.cpp:7-21):
+ * <root>/cache/<type>/<group>/<name>.bin = size_t byte count + payload. refrakt caches its 1024 shuffle permutations
+ * under shuffle/<particles per temporal sample>/ and its JSF32 states under rand_state/<total particles>/
+ * (src/flame.cpp:112-148). The render path here never needs the cache (seeding runs on the device); these calls let it
+ * produce buffers a refrakt build consumes and consume the ones refrakt cached, for seeded A/B runs. ---- */
+int rfk_cache_write_buffer(const char* root, const char* type, const char* group, const void* data, size_t bytes,
+                           const char* name_or_null, char* name_out, size_t name_out_len); /* buffer_group::write_buffer */
+int64_t rfk_cache_read_buffer(const char* root, const char* type, const char* group, const char* name, void* out, size_t out_len); /* bytes, or the size needed when out is NULL */
+int rfk_cache_list(const char* root, const char* type, const char* group, char* names_out, size_t names_out_len); /* cached_buffers: count; names joined by '\n' */
+/* writes the current global JSF32 states (rand_state/<P>/) and `shuffle_count` device-generated permutations of
+ * [0, P/TS) (shuffle/<P/TS>/) of the current simulation parameters */
+int rfk_export_sim_cache(const char* root, uint64_t shuffle_seed);
+/* replaces the global JSF32 states with cached ones (rand_state/<P>/<name>; name NULL = first in the directory) */
+int rfk_import_rng_states(const char* root, const char* name_or_null);
+int rfk_set_rng_states(const uint32_t* states, size_t first, size_t count); /* host (a, b, c, d) quadruples -> global states */
+
 /* ---- output: the reference's screenshot (src/main.cpp:590-593, stbi_write_png of get_pixels()) ---- */
 int rfk_write_png(const char* path, const uint8_t* rgba8, size_t width, size_t height); /* host pixels, rows top to bottom */
 

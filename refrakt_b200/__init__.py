@@ -130,6 +130,12 @@ SIGNATURES = {
     "rfk_make_shuffle_buffers": (_i, [_vp, C.c_uint32, C.c_uint32, C.c_uint64]),
     "rfk_copy_rng_states": (_i, [_upp, _sz, _sz]),
     "rfk_render_frame": (_i, [_vp, C.POINTER(FrameRequest), _vp, _vp, C.POINTER(FrameStats)]),
+    "rfk_cache_write_buffer": (_i, [_cp, _cp, _cp, _vp, _sz, _cp, _cp, _sz]),
+    "rfk_cache_read_buffer": (C.c_int64, [_cp, _cp, _cp, _cp, _vp, _sz]),
+    "rfk_cache_list": (_i, [_cp, _cp, _cp, _cp, _sz]),
+    "rfk_export_sim_cache": (_i, [_cp, C.c_uint64]),
+    "rfk_import_rng_states": (_i, [_cp, _cp]),
+    "rfk_set_rng_states": (_i, [_upp, _sz, _sz]),
     "rfk_write_png": (_i, [_cp, _vp, _sz, _sz]),
     "rfk_flame_single_step": (_i, [_vp, _i, _fpp, _ipp, _upp, _fpp, _i, _fpp]),
     "rfk_flame_select_xform": (_i, [_vp, _i, _fpp, _fpp, _ipp]),
@@ -514,6 +520,43 @@ def find_macros(text: str) -> set:
     buf = C.create_string_buffer(len(text) + 16)
     _check(lib().rfk_text_find_macros(text.encode(), buf, len(buf)), "find_macros")
     return set(buf.value.decode().split("\n")) - {""}
+
+
+class BufferGroup:
+    """buffer_cache::buffer_group (src/buffer_cache.hpp:12-60): <root>/cache/<type>/<group>/<name>.bin"""
+
+    def __init__(self, root: str, type_: str, group: str):
+        self.root, self.type, self.group = root.encode(), type_.encode(), str(group).encode()
+
+    def write_buffer(self, data: np.ndarray, name: Optional[str] = None) -> str:
+        data = np.ascontiguousarray(data)
+        out = C.create_string_buffer(128)
+        _check(lib().rfk_cache_write_buffer(self.root, self.type, self.group, data.ctypes.data, data.nbytes, name.encode() if name else None, out, 128), "cache_write_buffer")
+        return out.value.decode()
+
+    def read_buffer(self, name: str, dtype=np.uint8) -> np.ndarray:
+        n = _check(lib().rfk_cache_read_buffer(self.root, self.type, self.group, name.encode(), None, 0), "cache_read_buffer")
+        raw = np.empty(n, dtype=np.uint8)
+        _check(lib().rfk_cache_read_buffer(self.root, self.type, self.group, name.encode(), raw.ctypes.data, n), "cache_read_buffer")
+        return raw.view(dtype)
+
+    def cached_buffers(self):
+        buf = C.create_string_buffer(1 << 20)
+        n = _check(lib().rfk_cache_list(self.root, self.type, self.group, buf, len(buf)), "cache_list")
+        return buf.value.decode().split("\n") if n else []
+
+
+def export_sim_cache(root: str, shuffle_seed: int = 0):
+    _check(lib().rfk_export_sim_cache(root.encode(), shuffle_seed), "export_sim_cache")
+
+
+def import_rng_states(root: str, name: Optional[str] = None):
+    _check(lib().rfk_import_rng_states(root.encode(), name.encode() if name else None), "import_rng_states")
+
+
+def set_rng_states(states: np.ndarray, first: int = 0):
+    states = np.ascontiguousarray(states, dtype=np.uint32).reshape(-1, 4)
+    _check(lib().rfk_set_rng_states(_ptr(states, C.c_uint32), first, states.shape[0]), "set_rng_states")
 
 
 def write_png(path: str, rgba8: np.ndarray):

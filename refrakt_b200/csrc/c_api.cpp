@@ -11,6 +11,7 @@
 #include "flame.hpp"
 #include "flame_device.hpp"
 #include "png_writer.hpp"
+#include "buffer_cache.hpp"
 #include "static_kernels.cuh"
 #include "textutil.hpp"
 #include "variation_table.hpp"
@@ -580,6 +581,98 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
             cudaEventElapsedTime(&stats->ms_readback, b.ev[3], b.ev[4]);
         }
         return RFK_OK;
+    });
+}
+
+// ---- buffer cache ----
+int rfk_cache_write_buffer(const char* root, const char* type, const char* group, const void* data, size_t bytes, const char* name, char* name_out, size_t name_out_len) {
+    return guarded([&]() -> int {
+        if (!root || !type || !group || (!data && bytes)) throw std::invalid_argument("rfk_cache_write_buffer: null argument");
+        std::string written = buffer_cache::buffer_group(root, type, group).write_buffer(data, bytes, name ? name : "");
+        if (name_out && name_out_len) {
+            std::strncpy(name_out, written.c_str(), name_out_len - 1);
+            name_out[name_out_len - 1] = '\0';
+        }
+        return RFK_OK;
+    });
+}
+int64_t rfk_cache_read_buffer(const char* root, const char* type, const char* group, const char* name, void* out, size_t out_len) {
+    int64_t result = 0;
+    int rc = guarded([&]() -> int {
+        if (!root || !type || !group || !name) throw std::invalid_argument("rfk_cache_read_buffer: null argument");
+        auto data = buffer_cache::buffer_group(root, type, group).read_buffer(name);
+        result = (int64_t)data.size();
+        if (out) {
+            if (out_len < data.size()) throw std::invalid_argument("rfk_cache_read_buffer: output buffer too small");
+            std::memcpy(out, data.data(), data.size());
+        }
+        return RFK_OK;
+    });
+    return rc == RFK_OK ? result : rc;
+}
+int rfk_cache_list(const char* root, const char* type, const char* group, char* names_out, size_t names_out_len) {
+    return guarded([&]() -> int {
+        if (!root || !type || !group) throw std::invalid_argument("rfk_cache_list: null argument");
+        auto names = buffer_cache::buffer_group(root, type, group).cached_buffers();
+        std::string joined;
+        for (size_t i = 0; i < names.size(); i++) joined += (i ? "\n" : "") + names[i];
+        if (names_out && names_out_len) {
+            if (joined.size() + 1 > names_out_len) throw std::invalid_argument("rfk_cache_list: output buffer too small");
+            std::memcpy(names_out, joined.c_str(), joined.size() + 1);
+        }
+        return (int)names.size();
+    });
+}
+int rfk_export_sim_cache(const char* root, uint64_t shuffle_seed) {
+    return guarded([&]() -> int {
+        if (!root) throw std::invalid_argument("rfk_export_sim_cache: null root");
+        const size_t P = sim_total_particles(), TS = sim_temporal_samples();
+        if (!P) throw std::runtime_error("set_sim_parameters has not been called");
+        std::vector<uint32_t> states(P * 4);
+        cuda_ok(cudaMemcpyAsync(states.data(), sim_rng_states(), P * sizeof(uint4), cudaMemcpyDeviceToHost, current_stream()), "read rng states");
+        cuda_ok(cudaStreamSynchronize(current_stream()), "read rng states");
+        buffer_cache::buffer_group("" + std::string(root), "rand_state", std::to_string(P)).write_buffer(states.data(), states.size() * 4);
+        const size_t ppt = P / TS, count = sim_shuffle_count();
+        if (count) {
+            uint32_t* dev = nullptr;
+            cuda_ok(cudaMalloc(&dev, ppt * count * sizeof(uint32_t)), "cudaMalloc(shuffle buffers)");
+            kernels::make_shuffle_buffers(dev, (uint32_t)ppt, (uint32_t)count, shuffle_seed, current_stream());
+            count_launch(1);
+            std::vector<uint32_t> host(ppt * count);
+            cudaError_t e = cudaMemcpyAsync(host.data(), dev, host.size() * 4, cudaMemcpyDeviceToHost, current_stream());
+            if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+            cudaFree(dev);
+            cuda_ok(e, "read shuffle buffers");
+            buffer_cache::buffer_group group(root, "shuffle", std::to_string(ppt));
+            for (size_t k = 0; k < count; k++) group.write_buffer(host.data() + k * ppt, ppt * 4);
+        }
+        return RFK_OK;
+    });
+}
+int rfk_set_rng_states(const uint32_t* states, size_t first, size_t count) {
+    return guarded([&]() -> int {
+        if (!states) throw std::invalid_argument("rfk_set_rng_states: null argument");
+        if (!sim_rng_states() || first + count > sim_total_particles()) throw std::invalid_argument("range outside the particle RNG states");
+        cuda_ok(cudaMemcpyAsync(sim_rng_states_mutable() + first, states, count * sizeof(uint4), cudaMemcpyHostToDevice, current_stream()), "upload rng states");
+        cuda_ok(cudaStreamSynchronize(current_stream()), "upload rng states");
+        return RFK_OK;
+    });
+}
+int rfk_import_rng_states(const char* root, const char* name) {
+    return guarded([&]() -> int {
+        if (!root) throw std::invalid_argument("rfk_import_rng_states: null root");
+        const size_t P = sim_total_particles();
+        if (!P) throw std::runtime_error("set_sim_parameters has not been called");
+        buffer_cache::buffer_group group(root, "rand_state", std::to_string(P));
+        std::string which = name ? name : "";
+        if (which.empty()) {
+            auto names = group.cached_buffers();
+            if (names.empty()) return fail(RFK_E_NOTFOUND, "no cached rand_state buffer for " + std::to_string(P) + " particles under " + group.path());
+            which = names.front();
+        }
+        auto data = group.read_buffer(which);
+        if (data.size() != P * sizeof(uint4)) return fail(RFK_E_INVALID, "cached rand_state buffer has the wrong size");
+        return rfk_set_rng_states(reinterpret_cast<const uint32_t*>(data.data()), 0, P);
     });
 }
 

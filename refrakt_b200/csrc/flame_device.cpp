@@ -303,6 +303,8 @@ void flame::set_sim_parameters(std::size_t total_particles, std::size_t temporal
 std::size_t sim_total_particles() { return g_sim.total_particles; }
 std::size_t sim_temporal_samples() { return g_sim.temporal_samples; }
 const uint4* sim_rng_states() { return g_sim.rng; }
+uint4* sim_rng_states_mutable() { return g_sim.rng; }
+std::size_t sim_shuffle_count() { return g_sim.shuffle_count; }
 
 // ---------------------------------------------------------------------------------
 // device state

@@ -18,6 +18,8 @@ void count_launch(unsigned n);
 std::size_t sim_total_particles();
 std::size_t sim_temporal_samples();
 const uint4* sim_rng_states();
+uint4* sim_rng_states_mutable();
+std::size_t sim_shuffle_count();
 
 // NVRTC: CUDA source -> sm_100a cubin (no GPU needed). Throws with the compile log on failure.
 std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out);

@@ -285,3 +285,30 @@ def test_cli_fails_loudly_without_a_device(rfk, tmp_path):
         pytest.skip("a GPU is present")
     r = subprocess.run([cli, "--genome", GENOME, "--variations", VARIATIONS, "--out", str(tmp_path / "x.png")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "rfk_render:" in r.stderr and not (tmp_path / "x.png").exists()
+
+
+def test_buffer_cache_is_the_reference_file_format(rfk, tmp_path):
+    """src/buffer_cache.cpp:7-21: <root>/cache/<type>/<group>/<32 hex digits>.bin = size_t byte count + payload;
+    buffers are found by listing the directory (cached_buffers), so names only need to be unique"""
+    import struct
+    g = rfk.BufferGroup(str(tmp_path), "shuffle", "4096")
+    assert g.cached_buffers() == []
+    perm = np.random.default_rng(0).permutation(4096).astype(np.uint32)
+    name = g.write_buffer(perm)
+    assert len(name) == 32 and name == name.upper() and all(c in "0123456789ABCDEF" for c in name)
+    raw = (tmp_path / "cache" / "shuffle" / "4096" / (name + ".bin")).read_bytes()
+    assert struct.unpack("<Q", raw[:8])[0] == perm.nbytes and raw[8:] == perm.tobytes()
+    assert np.array_equal(g.read_buffer(name, np.uint32), perm)
+    assert g.write_buffer(perm) == name and g.cached_buffers() == [name]  # content-derived name
+    other = g.write_buffer(perm[::-1].copy())
+    assert sorted(g.cached_buffers()) == sorted([name, other])
+    # a file written the way the reference writes it is read back
+    ref_style = tmp_path / "cache" / "rand_state" / "8"
+    ref_style.mkdir(parents=True)
+    states = np.arange(32, dtype=np.uint32)
+    (ref_style / "00000000DEADBEEF00000000CAFEF00D.bin").write_bytes(struct.pack("<Q", states.nbytes) + states.tobytes())
+    g2 = rfk.BufferGroup(str(tmp_path), "rand_state", "8")
+    assert g2.cached_buffers() == ["00000000DEADBEEF00000000CAFEF00D"]
+    assert np.array_equal(g2.read_buffer("00000000DEADBEEF00000000CAFEF00D", np.uint32), states)
+    with pytest.raises(rfk.RefraktError):
+        g2.read_buffer("missing")

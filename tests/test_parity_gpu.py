@@ -232,3 +232,25 @@ def test_single_step_overlay_and_stress_genome(gpu_ready, rfk, oracle_mod, overl
     from conftest import BROKEN, chunk_genome, stress_genome
     for xml in (chunk_genome(99, overlay_vt, names=BROKEN), stress_genome(overlay_vt)):
         _check_report(_parity_over_genome(rfk, oracle_mod, overlay_compiler, overlay_vt, xml, 20000, 900))
+
+
+def test_sim_cache_export_import_round_trip(gpu_ready, rfk, oracle, tmp_path):
+    """the reference's on-disk cache layout (src/flame.cpp:112-148): rand_state/<P>/ holds the JSF32 states, shuffle/<PPT>/
+    one permutation per file; states written by one run seed another"""
+    P, TS = 256 * 4 * 2, 4
+    rfk.set_sim_parameters(P, TS, 8, seed=0)
+    rfk.export_sim_cache(str(tmp_path), shuffle_seed=3)
+    gs = rfk.BufferGroup(str(tmp_path), "rand_state", str(P))
+    names = gs.cached_buffers()
+    assert len(names) == 1
+    states = gs.read_buffer(names[0], np.uint32).reshape(P, 4)
+    assert np.array_equal(states[5], oracle.jsf32_warmup(5)) and np.array_equal(states, rfk.copy_rng_states(0, P))
+    gp = rfk.BufferGroup(str(tmp_path), "shuffle", str(P // TS))
+    perms = [gp.read_buffer(n, np.uint32) for n in gp.cached_buffers()]
+    assert len(perms) == 8 and all(np.array_equal(np.sort(p), np.arange(P // TS)) for p in perms)
+    rfk.set_sim_parameters(P, TS, 8, seed=999)
+    assert not np.array_equal(rfk.copy_rng_states(0, P), states)
+    rfk.import_rng_states(str(tmp_path))
+    assert np.array_equal(rfk.copy_rng_states(0, P), states)
+    rfk.set_rng_states(states[:4][::-1].copy(), first=10)
+    assert np.array_equal(rfk.copy_rng_states(10, 4), states[:4][::-1])
