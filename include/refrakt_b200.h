@@ -198,6 +198,11 @@ int rfk_tonemap(const float* image_in_dev, float* image_out_dev, uint8_t* rgba8_
 int rfk_density_tonemap(const float* bins_dev, float* image_out_dev, uint8_t* rgba8_dev, size_t width, size_t height, const rfk_post_params* p);
 /* 2x2 box average of a float4 image: out is out_width x out_height, in is twice that in each dimension */
 int rfk_downsample2x(const float* image_in_dev, float* image_out_dev, size_t out_width, size_t out_height);
+/* flam3-style spatial filter + supersample reduction (absent in the reference, main.cpp:195-196: SURVEY §8f item 2):
+ * separable Gaussian exp(-2x^2) of support 1.5 and radius `filter_radius` output pixels (the genome's filter="..."),
+ * in is (out_width*ss) x (out_height*ss). rfk_spatial_filter_taps returns the per-axis tap count and weights (<= 64). */
+int rfk_spatial_downsample(const float* image_in_dev, float* image_out_dev, size_t out_width, size_t out_height, int supersample, float filter_radius);
+int rfk_spatial_filter_taps(int supersample, float filter_radius, float* taps_out_64);
 
 /* ---- seeding kernels (src/flame.cpp:105-158 moved to the device) ---- */
 int rfk_seed_rng_states(uint32_t* states_dev, size_t count, uint32_t seed_base); /* jsf32::warmup_ctx, src/util.hpp:90-95 */

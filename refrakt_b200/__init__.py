@@ -125,6 +125,8 @@ SIGNATURES = {
     "rfk_tonemap": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(PostParams)]),
     "rfk_density_tonemap": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(PostParams)]),
     "rfk_downsample2x": (_i, [_vp, _vp, _sz, _sz]),
+    "rfk_spatial_downsample": (_i, [_vp, _vp, _sz, _sz, _i, _f]),
+    "rfk_spatial_filter_taps": (_i, [_i, _f, _fpp]),
     "rfk_seed_rng_states": (_i, [_vp, _sz, C.c_uint32]),
     "rfk_make_sample_points": (_i, [_vp, C.c_uint32]),
     "rfk_make_shuffle_buffers": (_i, [_vp, C.c_uint32, C.c_uint32, C.c_uint64]),
@@ -482,6 +484,16 @@ def density_tonemap(bins_ptr, out_ptr, rgba8_ptr, W, H, p: PostParams):
 
 def downsample2x(in_ptr, out_ptr, W, H):
     _check(lib().rfk_downsample2x(in_ptr, out_ptr, W, H), "downsample2x")
+
+
+def spatial_downsample(in_ptr, out_ptr, W, H, supersample, filter_radius):
+    _check(lib().rfk_spatial_downsample(in_ptr, out_ptr, W, H, supersample, filter_radius), "spatial_downsample")
+
+
+def spatial_filter_taps(supersample: int, filter_radius: float) -> np.ndarray:
+    taps = np.zeros(64, dtype=np.float32)
+    n = _check(lib().rfk_spatial_filter_taps(supersample, filter_radius, _ptr(taps)), "spatial_filter_taps")
+    return taps[:n].copy()
 
 
 def seed_rng_states(count: int, seed_base: int = 0) -> np.ndarray:

@@ -479,6 +479,20 @@ int rfk_downsample2x(const float* in, float* out, size_t W, size_t H) {
     });
 }
 
+int rfk_spatial_downsample(const float* in, float* out, size_t W, size_t H, int ss, float filter_radius) {
+    return guarded([&]() -> int {
+        if (!in || !out || !W || !H || ss < 1 || ss > 16 || !(filter_radius >= 0.0f)) throw std::invalid_argument("rfk_spatial_downsample: bad argument");
+        kernels::spatial_downsample(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), (int)W, (int)H, ss, filter_radius, current_stream());
+        count_launch(1);
+        cuda_ok(cudaGetLastError(), "spatial_downsample");
+        return RFK_OK;
+    });
+}
+int rfk_spatial_filter_taps(int ss, float filter_radius, float* taps) {
+    if (ss < 1 || ss > 16 || !(filter_radius >= 0.0f)) return fail(RFK_E_INVALID, "rfk_spatial_filter_taps: bad argument");
+    return kernels::spatial_filter_taps(ss, filter_radius, taps);
+}
+
 // ---- seeding ----
 int rfk_seed_rng_states(uint32_t* states, size_t count, uint32_t seed_base) {
     return guarded([&]() -> int {

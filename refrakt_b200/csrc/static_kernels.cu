@@ -108,6 +108,31 @@ __global__ void downsample2x_kernel(const float4* __restrict__ in, float4* __res
                                          (a.z + b.z + c.z + d.z) * 0.25f, (a.w + b.w + c.w + d.w) * 0.25f);
 }
 
+struct filter_taps { float w[64]; int n; int offset; };
+
+__global__ void spatial_downsample_kernel(const float4* __restrict__ in, float4* __restrict__ out, int W, int H, int ss, const __grid_constant__ filter_taps t) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const int IW = W * ss, IH = H * ss;
+    const int x0 = x * ss - t.offset, y0 = y * ss - t.offset;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wsum = 0.0f;
+    for (int j = 0; j < t.n; j++) {
+        int sy = y0 + j;
+        if (sy < 0 || sy >= IH) continue;
+        for (int i = 0; i < t.n; i++) {
+            int sx = x0 + i;
+            if (sx < 0 || sx >= IW) continue;
+            float w = t.w[i] * t.w[j];
+            float4 v = __ldg(in + (size_t)sy * IW + sx);
+            acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+            wsum += w;
+        }
+    }
+    float inv = wsum > 0.0f ? 1.0f / wsum : 0.0f;
+    out[(size_t)y * W + x] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
 // density_vert.glsl:35-44
 __device__ __forceinline__ int estimator_radius_of(float density, const density_params& p) {
     int r = (int)((float)p.estimator_radius / powf(density, p.estimator_curve));
@@ -385,6 +410,31 @@ void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, dens
 void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s) {
     if (!count) return;
     fixed_to_float_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(fixed, bins, count);
+}
+
+int spatial_filter_taps(int ss, float filter_radius, float* taps_out) {
+    const double support = 1.5;
+    const double fw = 2.0 * support * ss * (double)filter_radius;
+    int fwidth = (int)fw + 1;
+    if ((fwidth ^ ss) & 1) fwidth++;  // same parity as the supersample factor: the taps centre on the output pixel
+    if (fwidth > 64) fwidth = 64 - ((64 ^ ss) & 1);
+    const double adjust = fw > 0.0 ? support * fwidth / fw : 1.0;
+    double sum = 0.0, w[64];
+    for (int i = 0; i < fwidth; i++) {
+        double x = ((2.0 * i + 1.0) / fwidth - 1.0) * adjust;
+        w[i] = std::exp(-2.0 * x * x) * std::sqrt(2.0 / 3.14159265358979323846);
+        sum += w[i];
+    }
+    if (taps_out) for (int i = 0; i < fwidth; i++) taps_out[i] = (float)(w[i] / sum);
+    return fwidth;
+}
+
+void spatial_downsample(const float4* in, float4* out, int W, int H, int ss, float filter_radius, cudaStream_t s) {
+    filter_taps t{};
+    t.n = spatial_filter_taps(ss, filter_radius, t.w);
+    t.offset = (t.n - ss) / 2;
+    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+    spatial_downsample_kernel<<<grid, block, 0, s>>>(in, out, W, H, ss, t);
 }
 
 void downsample2x(const float4* in, float4* out, int W, int H, cudaStream_t s) {

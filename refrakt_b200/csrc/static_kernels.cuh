@@ -40,4 +40,12 @@ void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t c
 // 2x2 box average of a float4 image (config 3: 2x supersampled histogram -> image); W, H are the OUTPUT dims
 void downsample2x(const float4* in, float4* out, int W, int H, cudaStream_t s);
 
+// flam3-style spatial filter + supersample reduction (the reference has none: main.cpp:195-196).
+// Separable Gaussian g(x) = exp(-2 x^2) sqrt(2/pi) of support 1.5, width fw = 2 * 1.5 * ss * filter_radius supersampled
+// pixels rounded up to fwidth taps of the parity of ss, weights normalised to 1. The tap table (<= 64 per axis) is
+// returned in `taps_out` (host, may be null). in is (W*ss) x (H*ss), out is W x H; taps outside the image are dropped
+// and the weights of the remaining ones renormalised.
+int spatial_filter_taps(int ss, float filter_radius, float* taps_out);
+void spatial_downsample(const float4* in, float4* out, int W, int H, int ss, float filter_radius, cudaStream_t s);
+
 }  // namespace rfk::kernels

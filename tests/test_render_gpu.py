@@ -314,3 +314,43 @@ def test_non_default_stream(gpu_ready, rfk, compiler):
         assert n > 0 and int(round(float(bins.view(-1, 4)[:, 3].sum()))) == n
     finally:
         rfk.lib().rfk_set_stream(None)
+
+
+@pytest.mark.parametrize("ss,radius", [(2, 1.0), (1, 1.0), (3, 0.7), (2, 0.0)])
+def test_spatial_downsample_matches_numpy(gpu_ready, rfk, ss, radius):
+    """flam3-style spatial filter + supersample reduction against a direct numpy evaluation of the
+    same separable taps; a constant image stays constant (weights renormalised at the border); radius 0 at ss = 2 is
+    the 2x2 box of rfk_downsample2x"""
+    import torch
+    W, H = 37, 23
+    rng = np.random.default_rng(ss)
+    src = rng.random((H * ss, W * ss, 4)).astype(np.float32)
+    taps = rfk.spatial_filter_taps(ss, radius).astype(np.float64)
+    n, off = len(taps), (len(taps) - ss) // 2
+    assert abs(taps.sum() - 1) < 1e-6 and np.allclose(taps, taps[::-1]) and (n - ss) % 2 == 0
+    want = np.zeros((H, W, 4))
+    for y in range(H):
+        for x in range(W):
+            acc, ws = np.zeros(4), 0.0
+            for j in range(n):
+                sy = y * ss - off + j
+                if not 0 <= sy < H * ss:
+                    continue
+                for i in range(n):
+                    sx = x * ss - off + i
+                    if 0 <= sx < W * ss:
+                        acc += taps[i] * taps[j] * src[sy, sx]
+                        ws += taps[i] * taps[j]
+            want[y, x] = acc / ws
+    d_in = torch.from_numpy(src).cuda()
+    d_out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    rfk.spatial_downsample(d_in.data_ptr(), d_out.data_ptr(), W, H, ss, radius)
+    got = d_out.cpu().numpy()
+    assert np.abs(got - want).max() < 1e-5
+    const = torch.full((H * ss, W * ss, 4), 0.75, dtype=torch.float32, device="cuda")
+    rfk.spatial_downsample(const.data_ptr(), d_out.data_ptr(), W, H, ss, radius)
+    assert float((d_out - 0.75).abs().max()) < 1e-6
+    if ss == 2 and radius == 0.0:
+        box = torch.empty_like(d_out)
+        rfk.downsample2x(d_in.data_ptr(), box.data_ptr(), W, H)
+        assert torch.allclose(box, torch.from_numpy(got).cuda(), atol=1e-6)
