@@ -223,6 +223,9 @@ typedef struct rfk_frame_request {
     uint64_t target_binned;    /* stop once this many samples are binned (quality * W * H, main.cpp:411); 0 = use max_draw_calls only */
     uint32_t max_draw_calls;   /* upper bound on draw_to_bins calls; 0 = unlimited */
     float scale_constant_exp;  /* 4, main.cpp:228 */
+    uint32_t supersample;      /* histogram = image size x supersample in each dimension (main.cpp:195-196); 0 or 1 = none.
+                                  With supersample > 1 the tonemapped image is reduced by rfk_spatial_downsample */
+    float filter_radius;       /* spatial filter radius in output pixels (the genome's filter="..."); used when supersample > 1 */
 } rfk_frame_request;
 typedef struct rfk_frame_stats {
     uint64_t iterations;   /* chaos-game iterations run (warmup excluded) */

@@ -49,7 +49,8 @@ class PostParams(C.Structure):
 
 class FrameRequest(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("warmup_passes", C.c_uint32), ("drawing_passes", C.c_uint32),
-                ("tss_width", C.c_float), ("target_binned", C.c_uint64), ("max_draw_calls", C.c_uint32), ("scale_constant_exp", C.c_float)]
+                ("tss_width", C.c_float), ("target_binned", C.c_uint64), ("max_draw_calls", C.c_uint32), ("scale_constant_exp", C.c_float),
+                ("supersample", C.c_uint32), ("filter_radius", C.c_float)]
 
 
 class FrameStats(C.Structure):
@@ -395,8 +396,9 @@ class Flame:
         return p
 
     def render_frame(self, width, height, target_binned=0, max_draw_calls=0, warmup_passes=16, drawing_passes=128, tss_width=1.2 / 60.0,
-                     scale_constant_exp=4.0, rgba8_out: Optional[np.ndarray] = None, image_out: Optional[np.ndarray] = None):
-        req = FrameRequest(width, height, warmup_passes, drawing_passes, tss_width, target_binned, max_draw_calls, scale_constant_exp)
+                     scale_constant_exp=4.0, rgba8_out: Optional[np.ndarray] = None, image_out: Optional[np.ndarray] = None,
+                     supersample=1, filter_radius=1.0):
+        req = FrameRequest(width, height, warmup_passes, drawing_passes, tss_width, target_binned, max_draw_calls, scale_constant_exp, supersample, filter_radius)
         if rgba8_out is None and image_out is None:
             rgba8_out = np.empty((height, width, 4), dtype=np.uint8)
         stats = FrameStats()

@@ -538,13 +538,16 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         if (!req->width || !req->height) throw std::invalid_argument("rfk_render_frame: empty image");
         if (!req->target_binned && !req->max_draw_calls) throw std::invalid_argument("rfk_render_frame: neither target_binned nor max_draw_calls given");
         flame* fl = F(f);
-        const size_t W = req->width, H = req->height, n = W * H;
+        const size_t ss = req->supersample > 1 ? req->supersample : 1;
+        if (ss > 16) throw std::invalid_argument("rfk_render_frame: supersample > 16");
+        const size_t OW = req->width, OH = req->height, on = OW * OH;  // output image
+        const size_t W = OW * ss, H = OH * ss, n = W * H;              // histogram (and full-resolution image)
         cudaStream_t s = current_stream();
 
         // library-owned frame buffers: kept between calls and regrown only when the frame gets larger
         struct buffers {
-            float4* bins = nullptr; float4* image = nullptr; uchar4* rgba8 = nullptr;
-            size_t bins_n = 0, image_n = 0, rgba8_n = 0;
+            float4* bins = nullptr; float4* image = nullptr; uchar4* rgba8 = nullptr; float4* small = nullptr;
+            size_t bins_n = 0, image_n = 0, rgba8_n = 0, small_n = 0;
             cudaEvent_t ev[5] = {};
         };
         static buffers b;
@@ -555,8 +558,9 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
             have = want;
         };
         grow(b.bins, b.bins_n, n, "cudaMalloc(bins)");
-        if (image_out) grow(b.image, b.image_n, n, "cudaMalloc(image)");
-        if (rgba8_out) grow(b.rgba8, b.rgba8_n, n, "cudaMalloc(rgba8)");
+        if (image_out || ss > 1) grow(b.image, b.image_n, n, "cudaMalloc(image)");
+        if (rgba8_out) grow(b.rgba8, b.rgba8_n, on, "cudaMalloc(rgba8)");
+        if (ss > 1) grow(b.small, b.small_n, on, "cudaMalloc(filtered image)");
         for (auto& e : b.ev) if (!e) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
 
         cuda_ok(cudaEventRecord(b.ev[0], s), "event");
@@ -579,12 +583,21 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         rfk_flame_post_params(f, &pp);
         pp.scale_constant = (float)(1.0 / std::pow(10.0, (double)req->scale_constant_exp));
         auto d = to_density(pp, W, H);
-        kernels::density_tonemap(b.bins, image_out ? b.image : nullptr, rgba8_out ? b.rgba8 : nullptr, d, true, true, s);
-        count_launch(1);
+        const float4* final_image = b.image;
+        if (ss == 1) {
+            kernels::density_tonemap(b.bins, image_out ? b.image : nullptr, rgba8_out ? b.rgba8 : nullptr, d, true, true, s);
+            count_launch(1);
+        } else {
+            kernels::density_tonemap(b.bins, b.image, nullptr, d, true, true, s);
+            kernels::spatial_downsample(b.image, b.small, (int)OW, (int)OH, (int)ss, req->filter_radius, s);
+            count_launch(2);
+            if (rgba8_out) { kernels::pack_rgba8(b.small, b.rgba8, on, s); count_launch(1); }
+            final_image = b.small;
+        }
         cuda_ok(cudaGetLastError(), "density_tonemap launch");
         cuda_ok(cudaEventRecord(b.ev[3], s), "event");
-        if (rgba8_out) cuda_ok(cudaMemcpyAsync(rgba8_out, b.rgba8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, s), "read back rgba8");
-        if (image_out) cuda_ok(cudaMemcpyAsync(image_out, b.image, n * sizeof(float4), cudaMemcpyDeviceToHost, s), "read back image");
+        if (rgba8_out) cuda_ok(cudaMemcpyAsync(rgba8_out, b.rgba8, on * sizeof(uchar4), cudaMemcpyDeviceToHost, s), "read back rgba8");
+        if (image_out) cuda_ok(cudaMemcpyAsync(image_out, final_image, on * sizeof(float4), cudaMemcpyDeviceToHost, s), "read back image");
         cuda_ok(cudaEventRecord(b.ev[4], s), "event");
         cuda_ok(cudaStreamSynchronize(s), "rfk_render_frame");
         if (stats) {

@@ -15,7 +15,9 @@ static void usage() {
                  "usage: rfk_render --genome FILE.flam3 --variations variations.yaml [--overlay FILE.yaml] --out OUT.png\n"
                  "  [--width 1280] [--height 720] [--quality 2000 (samples/pixel)] [--passes 128] [--warmup 16]\n"
                  "  [--particles 2097152] [--temporal-samples 512] [--tss-width 0.02] [--seed 0] [--device 0]\n"
-                 "  [--frames N --fps 60] (OUT.png takes a %%d / %%04d frame number) [--deterministic] [--math-mode 0|1|2]\n");
+                 "  [--frames N --fps 60] (OUT.png takes a %%d / %%04d frame number) [--deterministic] [--math-mode 0|1|2]\n"
+                 "  [--supersample 1] [--filter 1.0] (histogram at supersample x the image size, spatial filter radius in pixels;\n"
+                 "   --quality is samples per histogram bin)\n");
 }
 
 int main(int argc, char** argv) {
@@ -25,6 +27,8 @@ int main(int argc, char** argv) {
     float tss_width = 1.2f / 60.0f, fps = 60.0f;
     unsigned long long seed = 0;
     int device = 0, deterministic = 0, math_mode = -1;
+    unsigned supersample = 1;
+    float filter_radius = 1.0f;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(2); } return argv[++i]; };
@@ -44,6 +48,8 @@ int main(int argc, char** argv) {
         else if (a == "--device") device = std::atoi(next());
         else if (a == "--frames") frames = std::strtoul(next(), nullptr, 10);
         else if (a == "--fps") fps = std::strtof(next(), nullptr);
+        else if (a == "--supersample") supersample = std::strtoul(next(), nullptr, 10);
+        else if (a == "--filter") filter_radius = std::strtof(next(), nullptr);
         else if (a == "--deterministic") deterministic = 1;
         else if (a == "--math-mode") math_mode = std::atoi(next());
         else { usage(); return 2; }
@@ -69,7 +75,8 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> pixels((size_t)width * height * 4);
     rfk_frame_request req{};
     req.width = width; req.height = height; req.warmup_passes = warmup; req.drawing_passes = passes; req.tss_width = tss_width;
-    req.target_binned = (uint64_t)quality * width * height; req.max_draw_calls = 0; req.scale_constant_exp = 4.0f;
+    req.target_binned = (uint64_t)quality * width * height * supersample * supersample; req.max_draw_calls = 0; req.scale_constant_exp = 4.0f;
+    req.supersample = supersample; req.filter_radius = filter_radius;
     for (unsigned frame = 0; frame < frames; frame++) {
         if (frame) rfk_flame_rotate_xforms(f, 18.0f / fps);  // DEGREES_PER_SECOND * dt, main.cpp:224
         rfk_frame_stats st{};

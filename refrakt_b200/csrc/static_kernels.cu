@@ -133,6 +133,14 @@ __global__ void spatial_downsample_kernel(const float4* __restrict__ in, float4*
     out[(size_t)y * W + x] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
 }
 
+__global__ void pack_rgba8_kernel(const float4* __restrict__ in, uchar4* __restrict__ out, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float4 v = in[i];
+    out[i] = make_uchar4((unsigned char)rintf(fminf(fmaxf(v.x, 0.f), 1.f) * 255.0f), (unsigned char)rintf(fminf(fmaxf(v.y, 0.f), 1.f) * 255.0f),
+                         (unsigned char)rintf(fminf(fmaxf(v.z, 0.f), 1.f) * 255.0f), (unsigned char)rintf(fminf(fmaxf(v.w, 0.f), 1.f) * 255.0f));
+}
+
 // density_vert.glsl:35-44
 __device__ __forceinline__ int estimator_radius_of(float density, const density_params& p) {
     int r = (int)((float)p.estimator_radius / powf(density, p.estimator_curve));
@@ -435,6 +443,11 @@ void spatial_downsample(const float4* in, float4* out, int W, int H, int ss, flo
     t.offset = (t.n - ss) / 2;
     dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
     spatial_downsample_kernel<<<grid, block, 0, s>>>(in, out, W, H, ss, t);
+}
+
+void pack_rgba8(const float4* in, uchar4* out, std::size_t count, cudaStream_t s) {
+    if (!count) return;
+    pack_rgba8_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(in, out, count);
 }
 
 void downsample2x(const float4* in, float4* out, int W, int H, cudaStream_t s) {

@@ -46,6 +46,8 @@ void downsample2x(const float4* in, float4* out, int W, int H, cudaStream_t s);
 // returned in `taps_out` (host, may be null). in is (W*ss) x (H*ss), out is W x H; taps outside the image are dropped
 // and the weights of the remaining ones renormalised.
 int spatial_filter_taps(int ss, float filter_radius, float* taps_out);
+// float4 in [0, 1] -> RGBA8, round to nearest (the GL UNORM conversion of buffer_objects.hpp:113-119)
+void pack_rgba8(const float4* in, uchar4* out, std::size_t count, cudaStream_t s);
 void spatial_downsample(const float4* in, float4* out, int W, int H, int ss, float filter_radius, cudaStream_t s);
 
 }  // namespace rfk::kernels

@@ -354,3 +354,22 @@ def test_spatial_downsample_matches_numpy(gpu_ready, rfk, ss, radius):
         box = torch.empty_like(d_out)
         rfk.downsample2x(d_in.data_ptr(), box.data_ptr(), W, H)
         assert torch.allclose(box, torch.from_numpy(got).cuda(), atol=1e-6)
+
+
+def test_render_frame_supersampled(gpu_ready, rfk, flame):
+    """supersample 2: histogram at twice the image size, tonemapped image reduced with the spatial filter; the result is
+    the same picture as the plain render (same genome, far more samples than noise)"""
+    W, H, P, TS = 160, 90, 256 * 16 * 32, 32
+    rfk.set_sim_parameters(P, TS, 64, seed=5)
+    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1)
+    plain = np.empty((H, W, 4), dtype=np.float32)
+    _, s1 = flame.render_frame(W, H, target_binned=400 * W * H, drawing_passes=32, image_out=plain)
+    ss_img = np.empty((H, W, 4), dtype=np.float32)
+    ss_u8 = np.empty((H, W, 4), dtype=np.uint8)
+    _, s2 = flame.render_frame(W, H, target_binned=400 * W * H * 4, drawing_passes=32, image_out=ss_img, rgba8_out=ss_u8, supersample=2, filter_radius=0.5)
+    assert s2.binned >= 4 * 400 * W * H and np.isfinite(ss_img).all() and (ss_img[..., 3] > 0.99).all()
+    assert np.abs(ss_u8.astype(int) - np.rint(np.clip(ss_img, 0, 1) * 255).astype(int)).max() <= 0
+    # same scene: the brightness depends on samples per bin (SURVEY §9 item 14), equal here, so means agree
+    assert abs(float(plain[..., :3].mean()) - float(ss_img[..., :3].mean())) < 0.08
+    corr = np.corrcoef(plain[..., :3].ravel(), ss_img[..., :3].ravel())[0, 1]
+    assert corr > 0.6, corr
