@@ -108,3 +108,60 @@ def test_xform_selection_frequencies_full_size(rfk, big):
         assert np.abs(picks / picks.sum() - weights).max() <= 1e-3
     finally:
         big.set_options(count_xforms=0)
+
+
+def test_config1_histogram_and_image_parity_full_size(rfk, big, oracle, oracle_mod):
+    """BASELINE configs[0] at its true size (1280x720, P = 2 097 152, TS = 512, warmup 16, one draw_to_bins of 128 passes =
+    268 435 456 iterations): GPU against two independent oracle runs on the host cores — BASELINE.md §5 'histogram' and
+    'final image' rows with their self-noise terms measured here"""
+    W, H = 1280, 720
+    refs = []
+    for rng_seed, shuf, pas in ((0, 0x5EED0000, 0x5EED0001), (P, 0x77, 0x78)):
+        oracle.set_sim_parameters(P, TS, 64, shuffle_seed=shuf, rng_seed=rng_seed, pass_seed=pas)
+        oracle.warmup(16, TSS)
+        bins = np.zeros((H, W, 4), dtype=np.float32)
+        n = oracle.draw_to_bins(bins, W, 128)
+        refs.append((bins, n))
+    rfk.set_sim_parameters(P, TS, 1024, seed=2 * P)
+    big.warmup(16, TSS)
+    d_bins = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
+    binned = big.draw_to_bins(d_bins.data_ptr(), W * H, W, 128)
+    got = d_bins.view(H, W, 4).cpu().numpy()
+
+    def pooled(b, k=4):
+        d = b[: H // k * k, : W // k * k, 3].astype(np.float64)
+        return d.reshape(H // k, k, W // k, k).sum(axis=(1, 3))
+
+    def l1(a, b):
+        return 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+
+    self_l1 = l1(pooled(refs[0][0]), pooled(refs[1][0]))
+    gpu_l1 = l1(pooled(got), pooled(refs[0][0]))
+    assert gpu_l1 <= max(0.02, 1.5 * self_l1), (gpu_l1, self_l1)
+    total = 128 * P
+    assert abs(binned / total - refs[0][1] / total) <= 0.002 * refs[0][1] / total, (binned / total, refs[0][1] / total, refs[1][1] / total)
+
+    def image(b):
+        return oracle_mod.to_rgba8(oracle.tonemap(oracle.density_estimate(b, W, H)))
+
+    ref_imgs = [image(refs[0][0]), image(refs[1][0])]
+    p = big.post_params()
+    u8 = torch.empty(W * H * 4, dtype=torch.uint8, device="cuda")
+    rfk.density_tonemap(d_bins.data_ptr(), None, u8.data_ptr(), W, H, p)
+    gpu_img = u8.view(H, W, 4).cpu().numpy()
+    # the GPU post-processing of the ORACLE's histogram matches the oracle's own image to 1 LSB
+    d_ref = torch.from_numpy(refs[0][0]).cuda()
+    rfk.density_tonemap(d_ref.data_ptr(), None, u8.data_ptr(), W, H, p)
+    assert np.abs(u8.view(H, W, 4).cpu().numpy().astype(int) - ref_imgs[0].astype(int)).max() <= 1
+
+    def psnr(a, b):
+        mse = np.mean((a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)) ** 2)
+        return 10 * np.log10(255.0 ** 2 / mse)
+
+    self_psnr, gpu_psnr = psnr(ref_imgs[0], ref_imgs[1]), psnr(gpu_img, ref_imgs[0])
+    assert gpu_psnr >= min(30.0, self_psnr - 1.0), (gpu_psnr, self_psnr)
+    mae = np.mean(np.abs(gpu_img[..., :3].astype(np.float64) - ref_imgs[0][..., :3].astype(np.float64)))
+    self_mae = np.mean(np.abs(ref_imgs[1][..., :3].astype(np.float64) - ref_imgs[0][..., :3].astype(np.float64)))
+    assert mae <= max(2.0, 1.25 * self_mae), (mae, self_mae)
+    print("config 1 parity: L1 gpu %.4f self %.4f | in-bounds gpu %.5f ref %.5f %.5f | PSNR gpu %.2f self %.2f | MAE gpu %.3f self %.3f" % (
+        gpu_l1, self_l1, binned / total, refs[0][1] / total, refs[1][1] / total, gpu_psnr, self_psnr, mae, self_mae))
