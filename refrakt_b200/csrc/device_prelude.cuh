@@ -130,9 +130,25 @@ __device__ __forceinline__ float cos(float v) { return ::cosf(v); }
 __device__ __forceinline__ void rfk_sincos(float v, float* s, float* c) { ::sincosf(v, s, c); }
 __device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
 #endif
+#if RFK_MATH_MODE == 1
+// tan stays on libdevice: next to its poles the SFU sine / cosine quotient loses too much (popcorn, sin(tan(3y)))
+__device__ __forceinline__ float tan(float v) { return ::tanf(v); }
+// sinh / cosh from one exponential and its reciprocal: relative error ~|x| * 1e-7 for |x| >= 1, absolute error ~1e-7
+// below (sinh(x) loses relative accuracy to cancellation there; the parity contract is absolute for small outputs)
+__device__ __forceinline__ void rfk_sinhcosh(float v, float* sh, float* ch) {
+    float e = ::expf(v);
+    float inv = 1.0f / e;
+    *sh = ::fabsf(v) < 0.125f ? v * ::fmaf(v * v, 0.16666667f, 1.0f) : 0.5f * (e - inv);
+    *ch = 0.5f * (e + inv);
+}
+__device__ __forceinline__ float sinh(float v) { float s, c; rfk_sinhcosh(v, &s, &c); return s; }
+__device__ __forceinline__ float cosh(float v) { float s, c; rfk_sinhcosh(v, &s, &c); return c; }
+#else
 __device__ __forceinline__ float tan(float v) { return ::tanf(v); }
 __device__ __forceinline__ float sinh(float v) { return ::sinhf(v); }
 __device__ __forceinline__ float cosh(float v) { return ::coshf(v); }
+__device__ __forceinline__ void rfk_sinhcosh(float v, float* sh, float* ch) { *sh = ::sinhf(v); *ch = ::coshf(v); }
+#endif
 __device__ __forceinline__ float exp(float v) { return ::expf(v); }
 __device__ __forceinline__ float log(float v) { return ::logf(v); }
 __device__ __forceinline__ float sqrt(float v) { return ::sqrtf(v); }
@@ -170,7 +186,11 @@ __device__ __forceinline__ vec2 sincos(float v) {
     rfk_sincos(v, &s, &c);
     return vec2(s, c);
 }
-__device__ __forceinline__ vec2 sinhcosh(float v) { return vec2(::sinhf(v), ::coshf(v)); }
+__device__ __forceinline__ vec2 sinhcosh(float v) {
+    float s, c;
+    rfk_sinhcosh(v, &s, &c);
+    return vec2(s, c);
+}
 __device__ __forceinline__ float mod2(float x, float y) { return x - y * ::truncf(x / y); }
 __device__ __forceinline__ float log10(float x) { return ::logf(x) * 0.434294481903251827651128918916f; }
 __device__ __forceinline__ bool badval(float x) { return (x != x) || (x > 1e10f) || (x < -1e10f); }
