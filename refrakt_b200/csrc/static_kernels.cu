@@ -316,16 +316,16 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
                     const float4 col = s_col[e];
                     const float4 k = s_k[e];
                     const int i = ox - g.x + 1;
-                    const bool lane_in = i >= -sr && i <= sr;
+                    // weight = (1 - n(i)^2 - n(m)^2) * norm, kept when >= 0 (density_frag.glsl:17 discards distance > 1).
+                    // Lane part c_i = n(i)^2 * norm (+inf outside the footprint columns), row part a_m = norm - n(m)^2 * norm.
                     const float ni = fmaf((float)i, k.x, k.y);
-                    const float ni2 = ni * ni;
+                    const float ci = (i >= -sr && i <= sr) ? ni * ni * k.z : INFINITY;
 #pragma unroll
                     for (int q = 0; q < DE_ROWS_PER_WARP; q++) {
                         const int m = m0 + q;
                         const float nm = fmaf((float)m, k.x, k.y);
-                        const float dist = fmaf(nm, nm, ni2);
-                        const bool ok = lane_in && m >= -sr && m <= sr && dist <= 1.0f;  // density_frag.glsl:17
-                        const float wgt = ok ? (1.0f - dist) * k.z : 0.0f;
+                        const float am = (m >= -sr && m <= sr) ? fmaf(-nm * nm, k.z, k.z) : -INFINITY;
+                        const float wgt = fmaxf(am - ci, 0.0f);
                         acc[q].x = fmaf(col.x, wgt, acc[q].x); acc[q].y = fmaf(col.y, wgt, acc[q].y);
                         acc[q].z = fmaf(col.z, wgt, acc[q].z); acc[q].w = fmaf(col.w, wgt, acc[q].w);
                     }
