@@ -255,6 +255,17 @@ int rfk_set_rng_states(const uint32_t* states, size_t first, size_t count); /* h
 /* ---- output: the reference's screenshot (src/main.cpp:590-593, stbi_write_png of get_pixels()) ---- */
 int rfk_write_png(const char* path, const uint8_t* rgba8, size_t width, size_t height); /* host pixels, rows top to bottom */
 
+/* ---- reference pass mode: the reference's own dispatch structure on the GPU (flame.cpp:252-280, :317-325 driving
+ * flame.glsl:41-90: ONE iteration per launch on a (PPT/256, TS) grid, particle and RNG state through global memory, one
+ * xform per 256-thread workgroup, shuffle-buffer gather / scatter). Not the product path: a same-hardware baseline for
+ * the register-resident kernels and a pass-level parity hook (fed the oracle's shuffle tables and pass ids it reproduces
+ * the oracle's RNG states bit for bit). shuffle_ids: one (in, out) pair per pass — 1 + num_passes pairs for warmup,
+ * num_iter pairs for draw — or NULL to draw them from a seeded std::mt19937. ---- */
+int rfk_set_shuffle_buffers(const uint32_t* tables, size_t count, uint64_t seed); /* count x (P/TS) permutations; NULL = device-generated */
+int rfk_flame_reference_warmup(rfk_flame* f, size_t num_passes, float tss_width, const uint32_t* shuffle_ids);
+int64_t rfk_flame_reference_draw_to_bins(rfk_flame* f, float* bins_dev, size_t bins_len, size_t bins_width, int num_iter, const uint32_t* shuffle_ids);
+int rfk_flame_copy_particles(rfk_flame* f, float* out_px4); /* the particle buffer (x, y, colour, 0), to host */
+
 /* ---- test hooks: the generated device functions on host-supplied vectors ---- */
 /* one dispatch(v, xid) per element (variation_table.cpp:222-263). xyz: n x 3 in, xid: n, rng: n x 4 in/out,
  * fp: 1024 floats or NULL for the flame's current values, out: n x 4 (x, y, colour, opacity) */

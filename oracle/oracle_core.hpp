@@ -137,6 +137,7 @@ struct sim {
     std::mt19937 pass_rng{0x5EED0001u};   // the per-pass shuffle ids (flame.cpp:231-233: random_device-seeded)
     unsigned long long counter = 0;       // flame_atomic_counters[0]
     unsigned long long xform_picks[64] = {0};
+    std::vector<uint32_t> id_log;         // every (shuf_buf_idx_in, shuf_buf_idx_out) pair drawn, in order
 };
 
 // src/flame.cpp:105-158

@@ -652,6 +652,23 @@ class Oracle:
         self.lib.orc_get_rng_states(_p(out, ctypes.c_uint32), ctypes.c_size_t(first), ctypes.c_size_t(count))
         return out
 
+    def shuffle_table(self, shuffle_count):
+        """the nshuf x PPT permutation table (binding 4)"""
+        out = np.zeros((shuffle_count, self.P // self.TS), dtype=np.uint32)
+        self.lib.orc_get_shuffle_table(_p(out, ctypes.c_uint32))
+        return out
+
+    def id_log(self, clear=False):
+        """every (shuf_buf_idx_in, shuf_buf_idx_out) pair the host loops drew so far (flame.cpp:261-262, :274-275, :320-321)"""
+        self.lib.orc_id_log_size.restype = ctypes.c_size_t
+        n = self.lib.orc_id_log_size()
+        out = np.zeros(n, dtype=np.uint32)
+        if n:
+            self.lib.orc_get_id_log(_p(out, ctypes.c_uint32))
+        if clear:
+            self.lib.orc_clear_id_log()
+        return out.reshape(-1, 2)
+
     def particles(self):
         out = np.zeros((self.P, 4), dtype=np.float32)
         self.lib.orc_get_particles(_p(out, ctypes.c_float))

@@ -140,6 +140,10 @@ SIGNATURES = {
     "rfk_import_rng_states": (_i, [_cp, _cp]),
     "rfk_set_rng_states": (_i, [_upp, _sz, _sz]),
     "rfk_write_png": (_i, [_cp, _vp, _sz, _sz]),
+    "rfk_set_shuffle_buffers": (_i, [_upp, _sz, C.c_uint64]),
+    "rfk_flame_reference_warmup": (_i, [_vp, _sz, _f, _upp]),
+    "rfk_flame_reference_draw_to_bins": (C.c_int64, [_vp, _vp, _sz, _sz, _i, _upp]),
+    "rfk_flame_copy_particles": (_i, [_vp, _fpp]),
     "rfk_flame_single_step": (_i, [_vp, _i, _fpp, _ipp, _upp, _fpp, _i, _fpp]),
     "rfk_flame_select_xform": (_i, [_vp, _i, _fpp, _fpp, _ipp]),
     "rfk_flame_bucket_index": (_i, [_vp, _i, _fpp, _fpp, _i, _i, _ipp, _ipp]),
@@ -182,6 +186,14 @@ def _ptr(a, t=C.c_float):
 def set_sim_parameters(total_particles: int, temporal_samples: int, shuffle_count: int = 1024, seed: int = 0):
     """flame::set_sim_parameters (src/flame.hpp:77)"""
     _check(lib().rfk_set_sim_parameters(total_particles, temporal_samples, shuffle_count, seed), "set_sim_parameters")
+
+
+def set_shuffle_buffers(tables: Optional[np.ndarray] = None, count: int = 64, seed: int = 0):
+    """shuffle buffers of the reference pass mode (binding 4): `tables` is count x (P/TS) uint32, or None for device-generated"""
+    if tables is not None:
+        tables = np.ascontiguousarray(tables, dtype=np.uint32)
+        count = tables.shape[0]
+    _check(lib().rfk_set_shuffle_buffers(None if tables is None else _ptr(tables, C.c_uint32), count, seed), "set_shuffle_buffers")
 
 
 def kernel_launch_count() -> int:
@@ -375,6 +387,22 @@ class Flame:
 
     def draw_to_bins_async(self, bins_ptr, bins_len, bins_width, num_iter):
         _check(lib().rfk_flame_draw_to_bins_async(self.handle, bins_ptr, bins_len, bins_width, num_iter), "draw_to_bins_async")
+
+    # --- reference pass mode (same-hardware baseline, pass-level parity hook)
+    def reference_warmup(self, num_passes: int, tss_width: float, shuffle_ids=None):
+        ids = None if shuffle_ids is None else np.ascontiguousarray(shuffle_ids, dtype=np.uint32).reshape(-1)
+        assert ids is None or ids.size == 2 * (1 + num_passes)
+        _check(lib().rfk_flame_reference_warmup(self.handle, num_passes, tss_width, None if ids is None else _ptr(ids, C.c_uint32)), "reference_warmup")
+
+    def reference_draw_to_bins(self, bins_ptr, bins_len, bins_width, num_iter, shuffle_ids=None) -> int:
+        ids = None if shuffle_ids is None else np.ascontiguousarray(shuffle_ids, dtype=np.uint32).reshape(-1)
+        assert ids is None or ids.size == 2 * num_iter
+        return int(_check(lib().rfk_flame_reference_draw_to_bins(self.handle, bins_ptr, bins_len, bins_width, num_iter, None if ids is None else _ptr(ids, C.c_uint32)), "reference_draw_to_bins"))
+
+    def copy_particles(self, total_particles: int) -> np.ndarray:
+        out = np.zeros((total_particles, 4), dtype=np.float32)
+        _check(lib().rfk_flame_copy_particles(self.handle, _ptr(out)), "copy_particles")
+        return out
 
     def binned_total(self) -> int: return int(_check(lib().rfk_flame_binned_total(self.handle), "binned_total"))
     def reset_animation(self): _check(lib().rfk_flame_reset_animation(self.handle), "reset_animation")

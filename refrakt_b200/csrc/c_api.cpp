@@ -711,6 +711,35 @@ int rfk_write_png(const char* path, const uint8_t* rgba8, size_t width, size_t h
     } catch (const std::exception& e) { return fail(RFK_E_INVALID, e.what()); }
 }
 
+// ---- reference pass mode ----
+int rfk_set_shuffle_buffers(const uint32_t* tables, size_t count, uint64_t seed) {
+    return guarded([&]() -> int { flame::set_shuffle_buffers(tables, count, seed); return RFK_OK; });
+}
+int rfk_flame_reference_warmup(rfk_flame* f, size_t num_passes, float tss_width, const uint32_t* ids) {
+    return guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        F(f)->reference_warmup(num_passes, tss_width, ids);
+        return RFK_OK;
+    });
+}
+int64_t rfk_flame_reference_draw_to_bins(rfk_flame* f, float* bins, size_t bins_len, size_t bins_width, int num_iter, const uint32_t* ids) {
+    int64_t result = 0;
+    int rc = guarded([&]() -> int {
+        if (!f || num_iter < 0) throw std::invalid_argument("bad argument");
+        if (F(f)->needs_warmup()) return fail(RFK_E_STATE, "reference_draw_to_bins: warmup has not been run for the current parameters");
+        result = (int64_t)F(f)->reference_draw_to_bins(bins, bins_len, bins_width, num_iter, ids);
+        return RFK_OK;
+    });
+    return rc == RFK_OK ? result : rc;
+}
+int rfk_flame_copy_particles(rfk_flame* f, float* out) {
+    return guarded([&]() -> int {
+        if (!f || !out) throw std::invalid_argument("null argument");
+        flame_copy_particles(*F(f), out);
+        return RFK_OK;
+    });
+}
+
 // ---- test hooks ----
 int rfk_flame_single_step(rfk_flame* f, int n, const float* xyz, const int* xid, uint32_t* rng, const float* fp, int first_run, float* out) {
     return guarded([&]() -> int {

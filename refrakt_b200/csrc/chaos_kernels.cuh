@@ -264,6 +264,70 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_warm(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<false>(p); }
 extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_draw(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<true>(p); }
 
+// The reference's own dispatch structure, restated for the GPU: shaders/flame.glsl:41-90 as ONE iteration per launch
+// on a (PPT / 256, TS) grid, particle and RNG state through global memory, one xform per 256-thread workgroup picked
+// by its first thread, shuffle-buffer gather / scatter (flame.glsl:31-37, :55-61). Not the product path: it is the
+// same-hardware baseline the register-resident kernels are measured against, and — fed the oracle's shuffle tables and
+// pass ids — it reproduces the oracle's RNG states bit for bit and its particle buffers to rounding.
+struct rfk_pass_params {
+    const float4* pos_in;               // binding 0
+    float4* pos_out;                    // binding 1
+    uint4* rng;                         // binding 11
+    const unsigned int* shuf_buf;       // binding 4: [num_shuffle][PPT]
+    const float* fp_inflated;           // binding 9
+    const float4* palette;              // binding 6
+    float4* bins;                       // binding 8
+    unsigned long long* counters;       // binding 10
+    float ss_affine[6];
+    int bin_w, bin_h;
+    float bin_wf, bin_hf;
+    int ppt;
+    unsigned int shuf_buf_idx_in, shuf_buf_idx_out;
+    int random_read, random_write, first_run, do_draw;
+};
+
+extern "C" __global__ void __launch_bounds__(256) rfk_reference_pass(const __grid_constant__ rfk_pass_params p) {
+    __shared__ int xid;
+    __shared__ float4 pal[256];
+    const unsigned int gid = blockIdx.x * 256 + threadIdx.x;        // gl_GlobalInvocationID.x
+    const size_t base = (size_t)blockIdx.y * p.ppt;                 // gl_WorkGroupID.y * gl_WorkGroupSize.x * gl_NumWorkGroups.x
+    rfk_rng rs = p.rng[base + gid];                                 // load_random_state()
+    for (int k = threadIdx.x; k < RFK_TOTAL_PARAMS; k += 256) rfk_glsl::fp[k] = p.fp_inflated[(size_t)blockIdx.y * RFK_TOTAL_PARAMS + k];
+    pal[threadIdx.x] = p.palette[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) xid = get_xform_id(rfk_randf(rs));      // flame.glsl:51-53
+    const unsigned int i_idx = p.random_read ? p.shuf_buf[gid + (size_t)p.ppt * p.shuf_buf_idx_in] : gid;
+    const unsigned int o_idx = p.random_write ? p.shuf_buf[gid + (size_t)p.ppt * p.shuf_buf_idx_out] : gid;
+    const float4 part = p.pos_in[(p.first_run ? 0 : base) + i_idx];
+    float x = part.x, y = part.y;
+    if (p.first_run) {
+        float r0 = rfk_randf(rs);
+        float r1 = rfk_randf(rs);
+        vec2 sc = sincos(sqrtf(r1));
+        float m = r0 * .1f * PI * 2.0f;
+        x += m * sc.x; y += m * sc.y;
+    }
+    __syncthreads();
+    vec4 r = p.first_run ? dispatch<true>(vec3(x, y, part.z), xid, rs) : dispatch<false>(vec3(x, y, part.z), xid, rs);
+    p.pos_out[base + o_idx] = make_float4(r.x, r.y, r.z, 0.0f);
+    if (p.do_draw) {
+        float fx = r.x, fy = r.y, fc = r.z, fw = r.w;
+#if RFK_HAS_FINAL
+        {
+            vec4 q = dispatch<false>(vec3(r.x, r.y, r.z), -1, rs);
+            fx = q.x; fy = q.y; fc = q.z; fw = q.w * r.w;
+        }
+#endif
+        const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf);
+        if (idx >= 0) {
+            float4 col = pal[rfk_palette_index(fc)];
+            rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);  // the reference's racy +=, made atomic
+            atomicAdd(p.counters, 1ull);                             // flame.glsl:85
+        }
+    }
+    p.rng[base + gid] = rs;                                         // save_random_state()
+}
+
 // Test hook: one dispatch(v, xid) per thread on caller-supplied particles, RNG states
 // and parameter block — the single-step level of the parity contract.
 extern "C" __global__ void rfk_single_step(int n, const float* __restrict__ xyz, const int* __restrict__ xid, uint4* rng,

@@ -118,6 +118,17 @@ struct flame {
     // Same without the blocking counter read-back; collect with binned_total().
     void draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter);
     std::uint64_t binned_total();  // all draw calls since the last warmup
+
+    // The reference's own dispatch structure on the GPU (one iteration per launch, particle / RNG state through global
+    // memory, one xform per 256-thread workgroup, shuffle-buffer gather / scatter: flame.cpp:252-280, :317-325 driving
+    // flame.glsl:41-90). A same-hardware baseline and a pass-level parity hook, not the product path. `shuffle_ids` holds
+    // one (in, out) pair per pass — 1 + num_passes pairs for warmup, num_iter pairs for draw — or nullptr to draw them
+    // from a seeded std::mt19937 (the reference seeds it from std::random_device).
+    void reference_warmup(std::size_t num_passes, float tss_width, const std::uint32_t* shuffle_ids);
+    std::size_t reference_draw_to_bins(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter, const std::uint32_t* shuffle_ids);
+    // uploads `count` permutations of [0, particles per temporal sample) as the shuffle buffers of the reference mode
+    // (binding 4); nullptr generates them on the device from `seed`
+    static void set_shuffle_buffers(const std::uint32_t* host_tables, std::size_t count, std::uint64_t seed);
     void reset_animation();                                    // src/flame.cpp:332-336
 
     ~flame();

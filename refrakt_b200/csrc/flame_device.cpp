@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <random>
 #include <set>
 #include <stdexcept>
 #include <unordered_map>
@@ -86,6 +87,12 @@ struct sim_state {
     std::uint64_t generation = 0;  // bumped by set_sim_parameters: invalidates per-flame buffers (flame.cpp:153-157)
     cudaStream_t stream = nullptr;
     std::uint64_t launches = 0;
+    // reference pass mode only
+    std::uint32_t* shuffle = nullptr;      // [shuffle_tables][PPT]
+    std::size_t shuffle_tables = 0;
+    float4* samples = nullptr;             // [PPT] Hammersley points (sample_buffer_)
+    std::uint64_t samples_generation = ~0ull, shuffle_generation = ~0ull;
+    std::mt19937 pass_ids{0x5EED0001u};
 };
 sim_state g_sim;
 std::set<flame*> g_active_flames;  // src/flame.hpp:173
@@ -171,10 +178,28 @@ struct rfk_iter_params_host {  // must match rfk_iter_params in chaos_kernels.cu
     float hammersley_inv_max;
 };
 
+struct rfk_pass_params_host {  // must match rfk_pass_params in chaos_kernels.cuh
+    const float4* pos_in;
+    float4* pos_out;
+    uint4* rng;
+    const unsigned int* shuf_buf;
+    const float* fp_inflated;
+    const float4* palette;
+    float4* bins;
+    unsigned long long* counters;
+    float ss_affine[6];
+    int bin_w, bin_h;
+    float bin_wf, bin_hf;
+    int ppt;
+    unsigned int shuf_buf_idx_in, shuf_buf_idx_out;
+    int random_read, random_write, first_run, do_draw;
+};
+
 struct flame_device {
     CUmodule module = nullptr;
-    CUfunction warm = nullptr, draw = nullptr, single_step = nullptr, select_xform = nullptr, bucket_index = nullptr;
+    CUfunction warm = nullptr, draw = nullptr, single_step = nullptr, select_xform = nullptr, bucket_index = nullptr, reference_pass = nullptr;
     float4* particles = nullptr;
+    float4* swap = nullptr;  // reference pass mode: swap_buffer_
     float* fp = nullptr;
     float* fp_inflated = nullptr;
     float4* palette = nullptr;
@@ -190,7 +215,7 @@ struct flame_device {
 
     ~flame_device() {
         if (module) driver().ModuleUnload(module);
-        cudaFree(particles); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
+        cudaFree(particles); cudaFree(swap); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
         cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
     }
 };
@@ -321,6 +346,7 @@ static void ensure_module(flame& f) {
     cu_check(api.ModuleGetFunction(&d.single_step, d.module, "rfk_single_step"), "rfk_single_step");
     cu_check(api.ModuleGetFunction(&d.select_xform, d.module, "rfk_select_xform"), "rfk_select_xform");
     cu_check(api.ModuleGetFunction(&d.bucket_index, d.module, "rfk_bucket_index"), "rfk_bucket_index");
+    cu_check(api.ModuleGetFunction(&d.reference_pass, d.module, "rfk_reference_pass"), "rfk_reference_pass");
 }
 
 static void ensure_buffers(flame& f) {
@@ -350,6 +376,7 @@ static void ensure_buffers(flame& f) {
     }
     if (d.sim_generation != g_sim.generation) {
         cudaFree(d.particles); d.particles = nullptr;
+        cudaFree(d.swap); d.swap = nullptr;
         cudaFree(d.fp_inflated); d.fp_inflated = nullptr;
         cuda_check(cudaMalloc(&d.particles, g_sim.total_particles * sizeof(float4)), "cudaMalloc(particles)");
         cuda_check(cudaMalloc(&d.fp_inflated, g_sim.temporal_samples * (std::size_t)total_params * sizeof(float)), "cudaMalloc(fp_inflated)");
@@ -410,6 +437,127 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
     cuda_check(cudaStreamSynchronize(g_sim.stream), "warmup");
     d.binned_reported = 0;
     d.warmed = true;
+}
+
+// ---------------------------------------------------------------------------------
+// reference pass mode (same-hardware baseline + pass-level parity hook)
+// ---------------------------------------------------------------------------------
+void flame::set_shuffle_buffers(const std::uint32_t* host_tables, std::size_t count, std::uint64_t seed) {
+    if (g_sim.total_particles == 0) throw std::runtime_error("set_sim_parameters has not been called");
+    if (count == 0) throw std::invalid_argument("set_shuffle_buffers: no tables");
+    const std::size_t ppt = g_sim.total_particles / g_sim.temporal_samples;
+    cudaFree(g_sim.shuffle); g_sim.shuffle = nullptr;
+    cuda_check(cudaMalloc(&g_sim.shuffle, count * ppt * sizeof(std::uint32_t)), "cudaMalloc(shuffle buffers)");
+    if (host_tables) {
+        cuda_check(cudaMemcpyAsync(g_sim.shuffle, host_tables, count * ppt * sizeof(std::uint32_t), cudaMemcpyHostToDevice, g_sim.stream), "upload shuffle buffers");
+        cuda_check(cudaStreamSynchronize(g_sim.stream), "upload shuffle buffers");
+    } else {
+        kernels::make_shuffle_buffers(g_sim.shuffle, (std::uint32_t)ppt, (std::uint32_t)count, seed, g_sim.stream);
+        count_launch(1);
+    }
+    g_sim.shuffle_tables = count;
+    g_sim.shuffle_generation = g_sim.generation;
+    g_sim.pass_ids.seed(0x5EED0001u ^ (unsigned)seed);
+}
+
+static void ensure_reference_buffers(flame& f) {
+    ensure_buffers(f);
+    flame_device& d = *f.device();
+    const std::size_t ppt = g_sim.total_particles / g_sim.temporal_samples;
+    if (ppt % 256 != 0) throw std::invalid_argument("reference pass mode: particles per temporal sample must be a multiple of 256");
+    if (!g_sim.shuffle || g_sim.shuffle_generation != g_sim.generation) flame::set_shuffle_buffers(nullptr, g_sim.shuffle_count ? g_sim.shuffle_count : 64, g_sim.seed);
+    if (!g_sim.samples || g_sim.samples_generation != g_sim.generation) {
+        cudaFree(g_sim.samples); g_sim.samples = nullptr;
+        cuda_check(cudaMalloc(&g_sim.samples, ppt * sizeof(float4)), "cudaMalloc(sample points)");
+        kernels::make_sample_points(g_sim.samples, (std::uint32_t)ppt, g_sim.stream);
+        count_launch(1);
+        g_sim.samples_generation = g_sim.generation;
+    }
+    if (!d.swap) cuda_check(cudaMalloc(&d.swap, g_sim.total_particles * sizeof(float4)), "cudaMalloc(swap buffer)");
+}
+
+static void launch_pass(flame& f, rfk_pass_params_host& p) {
+    flame_device& d = *f.device();
+    void* args[] = {&p};
+    const unsigned gx = (unsigned)(p.ppt / 256), gy = (unsigned)g_sim.temporal_samples;
+    cu_check(driver().LaunchKernel(d.reference_pass, gx, gy, 1, 256, 1, 1, 0, (CUstream)g_sim.stream, args, nullptr), "cuLaunchKernel(rfk_reference_pass)");
+    count_launch(1);
+}
+
+static std::uint32_t next_pass_id(const std::uint32_t* ids, std::size_t& cursor) {
+    if (ids) return ids[cursor++];
+    std::uniform_int_distribution<int> dist(0, int(g_sim.shuffle_tables - 1));  // flame.cpp:233
+    return (std::uint32_t)dist(g_sim.pass_ids);
+}
+
+void flame::reference_warmup(std::size_t num_passes, float tss_width, const std::uint32_t* shuffle_ids) {
+    ensure_reference_buffers(*this);
+    flame_device& d = *device_;
+    needs_update_ = false;
+    auto buf = copy_flame_data_to_buffer();
+    cuda_check(cudaMemcpyAsync(d.fp, buf.data(), PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
+    cuda_check(cudaMemcpyAsync(d.palette, palette.data(), 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
+    cuda_check(cudaMemsetAsync(d.counters, 0, 64 * sizeof(unsigned long long), g_sim.stream), "clear counters");
+    kernels::animate(d.fp, d.fp_inflated, buffer_map_.size, (int)g_sim.temporal_samples, tss_width, d.anim, d.anim_count, g_sim.stream);
+    count_launch(1);
+
+    rfk_pass_params_host p{};
+    p.rng = g_sim.rng; p.shuf_buf = g_sim.shuffle; p.fp_inflated = d.fp_inflated; p.palette = d.palette; p.counters = d.counters;
+    p.ppt = (int)(g_sim.total_particles / g_sim.temporal_samples);
+    p.random_read = 1; p.random_write = 1; p.first_run = 1; p.do_draw = 0;
+    std::size_t cursor = 0;
+    p.shuf_buf_idx_in = next_pass_id(shuffle_ids, cursor);
+    p.shuf_buf_idx_out = next_pass_id(shuffle_ids, cursor);
+    p.pos_in = g_sim.samples; p.pos_out = d.particles;
+    launch_pass(*this, p);  // flame.cpp:252-264
+    p.first_run = 0;
+    float4* names[2] = {d.particles, d.swap};
+    for (std::size_t i = 0; i < num_passes; i++) {  // flame.cpp:269-280
+        p.pos_in = names[i % 2]; p.pos_out = names[(i + 1) % 2];
+        p.shuf_buf_idx_in = next_pass_id(shuffle_ids, cursor);
+        p.shuf_buf_idx_out = next_pass_id(shuffle_ids, cursor);
+        launch_pass(*this, p);
+    }
+    if (num_passes % 2) std::swap(d.particles, d.swap);
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "reference_warmup");
+    d.binned_reported = 0;
+    d.warmed = true;
+}
+
+std::size_t flame::reference_draw_to_bins(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter, const std::uint32_t* shuffle_ids) {
+    if (needs_warmup()) throw std::runtime_error("reference_draw_to_bins: warmup has not been run for the current parameters");
+    ensure_reference_buffers(*this);
+    if (!bins || bins_width == 0 || bins_len < bins_width) throw std::invalid_argument("reference_draw_to_bins: bad bins buffer");
+    flame_device& d = *device_;
+    const std::size_t W = bins_width, H = bins_len / bins_width;
+    if (W >= (1u << 24) || H >= (1u << 24) || W * H > 0x7fffffffull) throw std::invalid_argument("reference_draw_to_bins: histogram too large");
+    rfk_pass_params_host p{};
+    p.rng = g_sim.rng; p.shuf_buf = g_sim.shuffle; p.fp_inflated = d.fp_inflated; p.palette = d.palette; p.counters = d.counters;
+    p.bins = reinterpret_cast<float4*>(bins);
+    p.ppt = (int)(g_sim.total_particles / g_sim.temporal_samples);
+    auto ss = screen_space_affine(W, H);
+    for (int i = 0; i < 6; i++) p.ss_affine[i] = ss[i];
+    p.bin_w = (int)W; p.bin_h = (int)H; p.bin_wf = (float)W; p.bin_hf = (float)H;
+    p.random_read = 1; p.random_write = 0; p.first_run = 0; p.do_draw = 1;  // flame.cpp:301-304
+    float4* names[2] = {d.particles, d.swap};
+    std::size_t cursor = 0;
+    for (int i = 0; i < num_iter; i++) {  // flame.cpp:317-325
+        p.pos_in = names[i % 2]; p.pos_out = names[(i + 1) % 2];
+        p.shuf_buf_idx_in = next_pass_id(shuffle_ids, cursor);
+        p.shuf_buf_idx_out = next_pass_id(shuffle_ids, cursor);
+        launch_pass(*this, p);
+    }
+    if (num_iter % 2) std::swap(d.particles, d.swap);
+    std::uint64_t total = binned_total();
+    std::uint64_t delta = total - d.binned_reported;
+    d.binned_reported = total;
+    return (std::size_t)delta;
+}
+
+void flame_copy_particles(flame& f, float* out) {
+    if (!f.device() || !f.device()->particles) throw std::runtime_error("no particle buffer (warmup first)");
+    cuda_check(cudaMemcpyAsync(out, f.device()->particles, g_sim.total_particles * sizeof(float4), cudaMemcpyDeviceToHost, g_sim.stream), "copy particles");
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "copy particles");
 }
 
 void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter) {

@@ -254,3 +254,74 @@ def test_sim_cache_export_import_round_trip(gpu_ready, rfk, oracle, tmp_path):
     assert np.array_equal(rfk.copy_rng_states(0, P), states)
     rfk.set_rng_states(states[:4][::-1].copy(), first=10)
     assert np.array_equal(rfk.copy_rng_states(10, 4), states[:4][::-1])
+
+
+def test_reference_pass_mode_reproduces_the_oracle(gpu_ready, rfk, compiler, oracle):
+    """flame.glsl:41-90 pass by pass (load RNG, first thread picks the workgroup's xform, shuffle-buffer gather / scatter,
+    first-run jitter, dispatch, histogram update, save RNG) driven by the host loops of flame.cpp:228-330, with the oracle's
+    own shuffle tables and pass ids. RNG consumption depends only on the picked xforms, so after warmup AND draw the RNG
+    states must be bit-identical; particle buffers agree to rounding while orbits are short, histograms bin for bin
+    except where a discontinuous variation flips."""
+    from conftest import GENOME
+    import torch
+    f = rfk.Flame.load_flame(GENOME, compiler)
+    P, TS, NSHUF, W, H = 256 * 2 * 4, 4, 8, 160, 90
+    oracle.set_threads(1)
+    oracle.set_sim_parameters(P, TS, NSHUF, shuffle_seed=11, rng_seed=0, pass_seed=5)
+    oracle.id_log(clear=True)
+    rfk.set_sim_parameters(P, TS, NSHUF, seed=0)
+    rfk.set_shuffle_buffers(oracle.shuffle_table(NSHUF))
+
+    # warmup: first-run pass + 2 passes
+    oracle.warmup(2, 1.2 / 60)
+    ids = oracle.id_log(clear=True)
+    assert ids.shape == (3, 2)
+    f.reference_warmup(2, 1.2 / 60, ids)
+    assert np.array_equal(rfk.copy_rng_states(0, P), oracle.rng_states(0, P))
+    got, want = f.copy_particles(P), oracle.particles()
+    ok = np.isfinite(want).all(axis=1)
+    err = np.linalg.norm(got[ok, :2] - want[ok, :2], axis=1) / np.maximum(1.0, np.linalg.norm(want[ok, :2], axis=1))
+    assert (err <= 1e-4).mean() > 0.97, (err <= 1e-4).mean()   # three chained iterations: rounding differences start to grow
+    assert np.abs(got[ok, 2] - want[ok, 2]).max() <= 1e-5 and (got[:, 3] == 0).all()
+
+    # one drawn pass from the oracle's exact particle state
+    bins_o = np.zeros((H, W, 4), dtype=np.float32)
+    n_o = oracle.draw_to_bins(bins_o, W, 3)
+    ids = oracle.id_log(clear=True)
+    assert ids.shape == (3, 2)
+    d_bins = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
+    n_g = f.reference_draw_to_bins(d_bins.data_ptr(), W * H, W, 3, ids)
+    assert np.array_equal(rfk.copy_rng_states(0, P), oracle.rng_states(0, P))  # still bit-identical after 6 passes
+    bins_g = d_bins.view(H, W, 4).cpu().numpy()
+    assert abs(n_g - n_o) <= 0.01 * n_o and abs(float(bins_g[..., 3].sum()) - n_g) < 0.5
+    assert np.abs(bins_g - bins_o).sum() / np.abs(bins_o).sum() < 0.25  # same samples up to chaotic drift of 4-6 chained steps
+    # the product kernels continue from the same particle buffers (state layout is shared)
+    assert not f.needs_warmup()
+    assert f.draw_to_bins(d_bins.data_ptr(), W * H, W, 4) > 0
+    oracle.set_threads(oracle.max_threads())
+
+
+def test_reference_pass_mode_statistics(gpu_ready, rfk, compiler, oracle_mod):
+    """the baseline mode and the product kernels sample the same measure"""
+    from conftest import GENOME
+    import torch
+    f = rfk.Flame.load_flame(GENOME, compiler)
+    P, TS, W, H = 256 * 16 * 32, 32, 320, 180
+    rfk.set_sim_parameters(P, TS, 64, seed=21)
+    hists = []
+    for mode in ("reference", "product"):
+        bins = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
+        if mode == "reference":
+            f.reference_warmup(16, 1.2 / 60)
+            n = f.reference_draw_to_bins(bins.data_ptr(), W * H, W, 64)
+        else:
+            f.warmup(16, 1.2 / 60)
+            n = f.draw_to_bins(bins.data_ptr(), W * H, W, 64)
+        hists.append((bins.view(H, W, 4).cpu().numpy(), n))
+    (a, na), (b, nb) = hists
+    assert abs(na - nb) / nb < 0.004
+
+    def pooled(x):
+        return x[:, :, 3].astype(np.float64).reshape(H // 4, 4, W // 4, 4).sum(axis=(1, 3))
+    l1 = 0.5 * np.abs(pooled(a) / pooled(a).sum() - pooled(b) / pooled(b).sum()).sum()
+    assert l1 < 0.03, l1

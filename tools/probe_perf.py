@@ -69,6 +69,23 @@ def main():
             print(json.dumps(rec), flush=True)
             out.append(rec)
             del bins
+    # same-hardware baseline: the reference's structure (one iteration per launch, state through global memory)
+    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1)
+    for W, H in sizes:
+        bins = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
+        flame.reference_warmup(16, 1.2 / 60)
+        flame.reference_draw_to_bins(bins.data_ptr(), W * H, W, 8)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        flame.reference_draw_to_bins(bins.data_ptr(), W * H, W, 128)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rec = dict(variant="reference_pass_mode (flame.glsl structure in CUDA: 128 launches, state in HBM)", W=W, H=H, ms_per_call=ms, giter_s=P * 128 / ms / 1e6)
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+        del bins
     # warm kernel (no histogram): the pure iteration rate
     flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1)
     torch.cuda.synchronize()
