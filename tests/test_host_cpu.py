@@ -312,3 +312,95 @@ def test_buffer_cache_is_the_reference_file_format(rfk, tmp_path):
     assert np.array_equal(g2.read_buffer("00000000DEADBEEF00000000CAFEF00D", np.uint32), states)
     with pytest.raises(rfk.RefraktError):
         g2.read_buffer("missing")
+
+
+def test_yaml_subset_reader_matches_pyyaml_on_edge_cases(rfk, oracle_mod, tmp_path):
+    """the product's own YAML reader (csrc/yaml_lite.cpp, standing in for yaml-cpp) against PyYAML (the oracle's reader)
+    on the constructs variations.yaml uses: literal blocks with inner indentation and trailing spaces, quoted scalars with
+    ': ', flow collections, comments, an entry without a body"""
+    text = '''# leading comment
+common:
+  r: length($v)   # trailing comment
+  rsq: $x * $x + $y * ($y)
+
+variations:
+  first:
+    # a comment between keys
+    result: "vec2($x, ($y < 0)? 1: -1)"
+  second:
+    param:
+      second_a: {}
+      second_b: {}
+    flags: [no_weight_mul]
+    src: |-
+      float t = $second_a;   
+      if(t > 0.0) {
+            t = -t;
+      }
+
+      t += $second_b;
+    result: |-
+      vec2(
+        t * $x,
+        $weight * $y
+      )
+  empty_one:
+
+  third:
+    flags: [pre_xform, other]
+    result: 'vec2($x * 0.5, 0.0)'
+'''
+    path = tmp_path / "v.yaml"
+    path.write_text(text)
+    c = rfk.FlameCompiler(str(path))
+    vt2 = oracle_mod.VariationTable(str(path))
+    assert c.variations() == sorted(vt2.vars) == ["empty_one", "first", "second", "third"]
+    assert c.get_parameters_for_variation("second") == ["second_a", "second_b"] and c.param_owner("second_b") == "second"
+    assert c.is_common("r") and c.is_common("rsq") and not c.is_common("first")
+    xml = GENOME_TEMPLATE % ('<xform weight="1" color="0" color_speed="0.5" first="0.5" second="0.25" second_a="1.5" second_b="-2" coefs="1 0 0 1 0 0" opacity="1"/>'
+                             '<xform weight="1" color="1" color_speed="0.5" first="1" third="0.125" coefs="0.5 0 0 0.5 0.1 0" opacity="1"/>')
+    f = rfk.Flame.load_flame_string(xml, c)
+    assert f is not None, rfk.Flame.last_error()
+    of = oracle_mod.load_flame_string(xml, vt2)
+    assert f.glsl_source() == oracle_mod.compile_flame_xforms(of, vt2)  # literal blocks, trailing spaces and all
+    assert "v.xy += fp[" in f.glsl_source()                            # the pre_xform flag of `third`
+    assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(of).view(np.uint32))
+
+
+def test_xml_reader_edge_cases(rfk, compiler, oracle_mod, vt):
+    """the product's own XML reader (csrc/xml_lite.cpp, standing in for pugixml): prolog, comments, entities, single quotes,
+    nested <edit> history, attribute order, a <flames> wrapper; values parsed like pugixml / std::stof do"""
+    body = """<?xml version="1.0"?>
+<!-- a comment with <xform> inside -->
+<flames name='pack'>
+<flame name="a &amp; b" size='640 480' center="0.5 -0.25" scale="  100.5" rotate="1e1" brightness="4.0x" gamma="4" vibrancy="1"
+   estimator_radius="9" estimator_curve=".4" unknown_flame_attr="ignored">
+   <xform weight=".5" color="0.25" color_speed="0.5" animate="0" linear="1" coefs="1 0 0 1 1e-1 -.5" opacity="1"   />
+   <xform weight="1.5" color="1" color_speed="0.5" spherical="0.5" linear="0.5" coefs="0.5 0.1 -0.1 0.5 0 0" post="1 0 0 1 0.25 0" opacity="0.5">
+      <motion motion_frequency="1" linear="2"/>
+   </xform>
+   <color index="0" rgb="255.9 128 0"/>
+   <color index="255" rgb="1 2 3"/>
+   <edit nick="x"><edit action="nested &lt;stuff&gt;"/></edit>
+</flame>
+</flames>"""
+    f = rfk.Flame.load_flame_string(body, compiler)
+    assert f is not None, rfk.Flame.last_error()
+    i = f.info()
+    assert list(i.size) == [640, 480] and list(i.center) == [0.5, -0.25] and i.scale == 100.5 and i.rotate == 10.0
+    assert i.brightness == 4.0 and i.num_xforms == 2 and not i.has_final_xform and i.estimator_curve == np.float32(0.4)
+    x0, x1 = f.xform(0), f.xform(1)
+    assert x0.rotation_frequency == 0.0 and x1.rotation_frequency == 0.0 and x1.has_post and list(x1.post) == [1, 0, 0, 1, 0.25, 0]
+    assert list(x0.affine)[4:] == [np.float32(0.1), -0.5] and x1.opacity == 0.5
+    assert f.variations(1) == {"linear": 0.5, "spherical": 0.5}  # std::map order
+    pal = f.palette()
+    assert pal[0].tolist() == [255 / 256.0, 0.5, 0.0, 1.0] and pal[255].tolist() == [1 / 256.0, 2 / 256.0, 3 / 256.0, 1.0] and pal[7].tolist() == [0, 0, 0, 0]
+    of = oracle_mod.load_flame_string(body[body.index("<flames"):], vt)
+    assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(of).view(np.uint32))
+    assert f.glsl_source() == oracle_mod.compile_flame_xforms(of, vt)
+    for bad in ("", "<flame", "<flame><xform coefs='1 0 0 1 0 0' linear='1' weight='1' /></flam>", "<notflame/>",
+                GENOME_TEMPLATE % '<xform weight="abc" linear="1" coefs="x y" opacity="1"/>'):
+        got = rfk.Flame.load_flame_string(bad, compiler)
+        assert got is None or isinstance(got, rfk.Flame)  # never crashes; malformed input is reported
+    assert rfk.Flame.load_flame_string("<flame", compiler) is None and rfk.Flame.last_error() != ""
+    assert rfk.Flame.load_flame_string(GENOME_TEMPLATE % '<xform weight="1" linear="1" coefs="x y" opacity="1"/>', compiler) is None
