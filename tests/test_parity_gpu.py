@@ -325,3 +325,42 @@ def test_reference_pass_mode_statistics(gpu_ready, rfk, compiler, oracle_mod):
         return x[:, :, 3].astype(np.float64).reshape(H // 4, 4, W // 4, 4).sum(axis=(1, 3))
     l1 = 0.5 * np.abs(pooled(a) / pooled(a).sum() - pooled(b) / pooled(b).sum()).sum()
     assert l1 < 0.03, l1
+
+
+def _random_genome(seed, vt):
+    """2-6 xforms of 1-4 random compile-clean variations each, random post affines, optional final xform"""
+    from conftest import COMPILE_CLEAN, GENOME_TEMPLATE, xform_xml
+    rng = np.random.default_rng(1000 + seed)
+    xf = []
+    for k in range(int(rng.integers(2, 7))):
+        names = sorted(set(str(n) for n in rng.choice(COMPILE_CLEAN, int(rng.integers(1, 5)), replace=False)))
+        if all("pre_xform" in vt.vars[n].flags for n in names):
+            names.append("linear")
+        x = xform_xml(names, vt, rng)
+        if rng.random() < 0.3:
+            x = x.replace(" opacity=", ' post="%s" opacity=' % " ".join("%.3f" % v for v in rng.normal(0, 0.5, 6)))
+        xf.append(x)
+    if rng.random() < 0.5:
+        xf.append(xform_xml(["linear", str(rng.choice(["bubble", "spherical", "eyefish", "julia"]))], vt, rng, tag="finalxform"))
+    return GENOME_TEMPLATE % "\n".join(xf)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_genomes(gpu_ready, rfk, oracle_mod, compiler, vt, seed):
+    """random genomes over the whole variation table: identical generated text, single-step parity (pole-aware), and a small
+    render whose histogram conserves mass"""
+    xml = _random_genome(seed, vt)
+    report = _parity_over_genome(rfk, oracle_mod, compiler, vt, xml, 10000, 3000 + seed)
+    _check_report(report)
+    f = rfk.Flame.load_flame_string(xml, compiler)
+    of = oracle_mod.load_flame_string(xml, vt)
+    assert f.glsl_source() == oracle_mod.compile_flame_xforms(of, vt)
+    P, TS, W, H = 256 * 2 * 8, 8, 128, 96
+    rfk.set_sim_parameters(P, TS, 8, seed=seed)
+    f.warmup(8, 1.2 / 60)
+    buf = rfk.DeviceBuffer(W * H * 16)
+    buf.zero_out()
+    binned = f.draw_to_bins(buf.ptr, W * H, W, 32)
+    bins = buf.download(np.float32, (H, W, 4))
+    buf.free()
+    assert np.isfinite(bins).all() and (bins >= 0).all() and abs(float(bins[..., 3].sum()) - binned) < 0.5
