@@ -1,5 +1,6 @@
-"""Per-variation single-step parity table (GPU vs oracle), one single-variation genome per name.
-Usage: python tools/diag_variations.py [math_mode ...]  -> gpurun_out/variation_parity.json"""
+"""Per-variation single-step parity table (GPU vs oracle), one single-variation genome per name. A test-side
+diagnostic (it drives the oracle as the checker), kept under tests/ for that reason.
+Usage: python tests/diag_variations.py [math_mode ...]  -> gpurun_out/variation_parity.json"""
 import json
 import os
 import sys
@@ -7,7 +8,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 
 import refrakt_b200 as r

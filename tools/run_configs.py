@@ -131,10 +131,14 @@ def main():
             emit(4, "animation, 1280x720, frames round-robin over ranks, each warmup(16) + 128 passes + DE + tonemap + read-back", res, res["iterations"] * world, ms)
             flame = r.Flame.load_flame(GENOME, compiler)  # undo the rotation
         elif cfg == 5:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            from conftest import stress_genome
-            import refrakt_oracle as ro  # only its variation table, for the genome generator
-            vt = ro.VariationTable(VARIATIONS, overlay=r.OVERLAY_YAML)
+            from conftest import stress_genome  # genome generator only
+
+            class _Params:  # the generator needs each variation's parameter names: taken from the product's compiler
+                def __init__(self, names): self.param = names
+
+            class _Table:
+                def __init__(self, comp): self.vars = {n: _Params(comp.get_parameters_for_variation(n)) for n in comp.variations()}
+            vt = _Table(compiler)
             stress = r.Flame.load_flame_string(stress_genome(vt), compiler)
             assert stress is not None, r.Flame.last_error()
             render_still(stress, 3840, 2160, draw_calls=2)
