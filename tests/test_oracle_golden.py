@@ -143,3 +143,29 @@ def test_macro_grammar_matches_reference_compiled_util_cpp(oracle_mod, vt, rfk):
             assert n >= 0 and buf.value.decode() == oracle_mod.replace_macro(t, name, "fp[7]"), (t, name)
             assert buf.value.decode() == rfk.replace_macro(t, name, "fp[7]"), (t, name)  # the product's own (csrc/textutil.cpp)
         assert rfk.find_macros(t) == oracle_mod.find_macros(t), t
+
+
+@pytest.mark.skipif(not os.path.exists(PINS), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_macro_grammar_property_based(oracle_mod, rfk):
+    """hypothesis-generated strings over the macro alphabet: reference util.cpp == oracle == product"""
+    from hypothesis import given, settings, strategies as st
+    ref = ctypes.CDLL(PINS)
+    if not hasattr(ref, "ref_replace_macro"):
+        pytest.skip("prebuilt pins predate the util.cpp wrappers")
+    buf = ctypes.create_string_buffer(1 << 14)
+    alphabet = st.sampled_from(list("$$$xyvrc01_ab ()*;.\n"))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.text(alphabet, max_size=40), st.sampled_from(["x", "y", "v", "r", "c1", "c10", "a", "ab", "x_1"]), st.sampled_from(["fp[3]", "v.x", "", "$x"]))
+    def check(text, name, value):
+        n = ref.ref_replace_macro(text.encode(), name.encode(), value.encode(), buf, len(buf))
+        assert n >= 0
+        want = buf.value.decode()
+        assert oracle_mod.replace_macro(text, name, value) == want
+        assert rfk.replace_macro(text, name, value) == want
+        n = ref.ref_find_macros(text.encode(), buf, len(buf))
+        assert n >= 0
+        found = set(buf.value.decode().split("\n")) - {""}
+        assert oracle_mod.find_macros(text) == found and rfk.find_macros(text) == found
+
+    check()
