@@ -169,3 +169,26 @@ def test_macro_grammar_property_based(oracle_mod, rfk):
         assert oracle_mod.find_macros(text) == found and rfk.find_macros(text) == found
 
     check()
+
+
+@pytest.mark.skipif(not os.path.exists(PINS), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_cache_files_are_readable_by_the_reference_reader(rfk, tmp_path, monkeypatch):
+    """files written by the product's buffer cache, read back by the reference's own buffer_group::cached_buffers /
+    read_buffer (src/buffer_cache.hpp:27-50, compiled from the reference header)"""
+    ref = ctypes.CDLL(PINS)
+    if not hasattr(ref, "ref_cache_list"):
+        pytest.skip("prebuilt pins predate the buffer_cache wrappers")
+    ref.ref_cache_read_u32.restype = ctypes.c_long
+    perm = np.random.default_rng(3).permutation(4096).astype(np.uint32)
+    states = np.random.default_rng(4).integers(0, 2**32, (64, 4), dtype=np.uint64).astype(np.uint32)
+    name_p = rfk.BufferGroup(str(tmp_path), "shuffle", "4096").write_buffer(perm)
+    name_s = rfk.BufferGroup(str(tmp_path), "rand_state", "64").write_buffer(states)
+    monkeypatch.chdir(tmp_path)  # the reference resolves "cache/" against the working directory
+    buf = ctypes.create_string_buffer(4096)
+    assert ref.ref_cache_list(b"shuffle", b"4096", buf, len(buf)) > 0 and buf.value.decode().split() == [name_p]
+    out = np.zeros(4096, dtype=np.uint32)
+    n = ref.ref_cache_read_u32(b"shuffle", b"4096", name_p.encode(), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), 4096)
+    assert n == 4096 and np.array_equal(out, perm)
+    out = np.zeros(256, dtype=np.uint32)
+    n = ref.ref_cache_read_u32(b"rand_state", b"64", name_s.encode(), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), 256)
+    assert n == 256 and np.array_equal(out.reshape(64, 4), states)
