@@ -16,11 +16,13 @@
 // output (restated in refrakt_oracle.py) pasted ahead of this header by the generator,
 // compiled against glsl_shim.hpp.
 //
-// PARITY UNPINNED: the reference has no tests, golden vectors or fixtures
-// (SURVEY.md §4), and it cannot be built or run here (GL + 12 fetched dependencies).
-// The pieces that DO compile from /root/reference (jsf32, hammersley, the affine helpers of flame.hpp —
-// oracle/Makefile -> oracle/_ref/) pin the corresponding functions; everything else is pinned only
-// by reading the reference source.
+// PARITY UNPINNED for this file: the reference has no tests, golden vectors or fixtures
+// (SURVEY.md §4), and its shaders cannot be run here (no GL context, 12 fetched dependencies).
+// The host-side pieces that DO compile from /root/reference (jsf32, hammersley, the affine helpers,
+// and the whole of flame.cpp + variation_table.cpp against stand-in headers — oracle/Makefile ->
+// oracle/_ref/) pin the functions marked util.hpp / hammersley.cpp above and the generated
+// get_xform_id()/dispatch() text this header is compiled with (tests/test_reference_golden.py);
+// the shader restatements below are pinned only by reading the reference source.
 //
 // Where the reference leaves behaviour open, the oracle fixes it and says so:
 //   * operand evaluation order of several randf() in one statement: textual order

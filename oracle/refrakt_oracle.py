@@ -19,11 +19,17 @@ reference source function by function:
 The generated GLSL is compiled for the CPU against glsl_shim.hpp with g++ (-ffp-contract=off)
 into oracle/_build/ and driven through ctypes.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
-and cannot be built or run here. Pins that exist: jsf32, hammersley and the affine helpers of
-flame.hpp compile from the reference sources (oracle/Makefile -> oracle/_ref/libref_pins*.so)
-and are compared with this restatement, together with the SURVEY.md Appendix A/B values, by
-tests/test_oracle_golden.py.
+PARITY: HOST HALF PINNED, DEVICE HALF UNPINNED. The reference ships no tests, golden vectors or
+fixtures and cannot be built or run as a whole here (GL + 12 fetched dependencies).
+What compiles from the reference sources where they lie (oracle/Makefile -> oracle/_ref/):
+  libref_pins*.so   jsf32, hammersley, replace_macro/find_macros, the buffer_cache reader, the
+                    affine helpers of flame.hpp  -> tests/test_oracle_golden.py
+  libref_host.so    the reference's own flame.cpp + variation_table.cpp (parser, buffer map, fp[],
+                    compile_flame_xforms, screen-space affine) against stand-in third-party headers
+                    (oracle/stubs/) -> tests/golden/reference_host_*.json.gz
+                    -> tests/test_reference_golden.py compares this restatement AND the product.
+Everything in this file up to and including the generated GLSL text is therefore pinned against
+reference outputs; the GLSL as executed (oracle_core.hpp) is pinned only by reading the shaders.
 """
 from __future__ import annotations
 

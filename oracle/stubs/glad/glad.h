@@ -24,14 +24,14 @@ RFK_GLC(GL_SHADER_STORAGE_BUFFER, 0x90D2) RFK_GLC(GL_DRAW_FRAMEBUFFER, 0x8CA9) R
 RFK_GLC(GL_TEXTURE_BORDER_COLOR, 0x1004) RFK_GLC(GL_REPEAT, 0x2901) RFK_GLC(GL_FRAMEBUFFER_COMPLETE, 0x8CD5)
 // any GL call in an inline body of the reference's headers resolves to an empty variadic template
 #define RFK_GLF(name) template <typename... A> void name(A...) {}
-RFK_GLF(glCreateBuffers) RFK_GLF(glNamedBufferStorage) RFK_GLF(glNamedBufferData) RFK_GLF(glDeleteBuffers) RFK_GLF(glNamedBufferSubData)
+RFK_GLF(glCreateBuffers) RFK_GLF(glNamedBufferStorage) RFK_GLF(glNamedBufferData) RFK_GLF(glDeleteBuffers) 
 RFK_GLF(glGetNamedBufferSubData) RFK_GLF(glClearNamedBufferData) RFK_GLF(glBindBufferBase) RFK_GLF(glCreateTextures) RFK_GLF(glTextureStorage2D)
 RFK_GLF(glDeleteTextures) RFK_GLF(glGetTextureImage) RFK_GLF(glTextureParameteri) RFK_GLF(glTextureParameterfv) RFK_GLF(glCreateFramebuffers) RFK_GLF(glDeleteFramebuffers)
 RFK_GLF(glBindFramebuffer) RFK_GLF(glNamedFramebufferTexture) RFK_GLF(glFramebufferTexture) RFK_GLF(glFramebufferTexture2D) RFK_GLF(glUniform1i) RFK_GLF(glUniform1ui) RFK_GLF(glUniform1f)
 RFK_GLF(glUniform2fv) RFK_GLF(glUniform3fv) RFK_GLF(glUniform4fv) RFK_GLF(glUniform2uiv) RFK_GLF(glUniform3uiv) RFK_GLF(glUniform4uiv)
-RFK_GLF(glUniform2iv) RFK_GLF(glUniform3iv) RFK_GLF(glUniform4iv) RFK_GLF(glUniformMatrix4fv) RFK_GLF(glUniform1fv) RFK_GLF(glUseProgram)
-RFK_GLF(glShaderSource) RFK_GLF(glCompileShader) RFK_GLF(glGetShaderiv) RFK_GLF(glGetShaderInfoLog) RFK_GLF(glDeleteShader)
-RFK_GLF(glAttachShader) RFK_GLF(glLinkProgram) RFK_GLF(glGetProgramiv) RFK_GLF(glGetProgramInfoLog) RFK_GLF(glDeleteProgram) RFK_GLF(glDetachShader)
+RFK_GLF(glUniform2iv) RFK_GLF(glUniform3iv) RFK_GLF(glUniform4iv) RFK_GLF(glUniformMatrix4fv) RFK_GLF(glUseProgram)
+RFK_GLF(glCompileShader) RFK_GLF(glGetShaderInfoLog) RFK_GLF(glDeleteShader)
+RFK_GLF(glAttachShader) RFK_GLF(glLinkProgram) RFK_GLF(glGetProgramInfoLog) RFK_GLF(glDeleteProgram) RFK_GLF(glDetachShader)
 RFK_GLF(glDrawBuffers) RFK_GLF(glBindTexture) RFK_GLF(glClearTexImage) RFK_GLF(glBindBuffer) RFK_GLF(glGenFramebuffers) RFK_GLF(glTexImage2D) RFK_GLF(glGenTextures)
 template <typename... A> GLuint glCreateShader(A...) { return 0; }
 template <typename... A> GLuint glCreateProgram(A...) { return 0; }
@@ -50,3 +50,26 @@ RFK_GLF(glGetIntegerv)
 RFK_GLF(glMapNamedBuffer)
 RFK_GLF(glTexParameteri)
 RFK_GLF(glUnmapNamedBuffer)
+
+RFK_GLC(GL_ALL_BARRIER_BITS, 0)
+RFK_GLF(glDispatchCompute)
+RFK_GLF(glFinish)
+RFK_GLF(glMemoryBarrier)
+
+// Capturing entry points: what the reference hands to GL is recorded so that the text of the shader it generated and the
+// parameter buffer it uploads can be read back by oracle/ref_host.cpp. Compilation and linking "succeed".
+#include <string>
+#include <cstring>
+namespace rfk_gl_capture {
+inline std::vector<std::string> shader_sources;            // every glShaderSource string, in call order
+inline std::vector<std::vector<unsigned char>> uploads;    // every glNamedBufferSubData payload
+inline std::vector<std::vector<float>> uniform_arrays;     // every glUniform1fv payload
+}
+template <typename A, typename B, typename C, typename D> void glShaderSource(A, B, C strings, D) { rfk_gl_capture::shader_sources.emplace_back(strings[0]); }
+template <typename A, typename B, typename C> void glGetShaderiv(A, B, C out) { *out = 1; }
+template <typename A, typename B, typename C> void glGetProgramiv(A, B, C out) { *out = 1; }
+template <typename A, typename B, typename C, typename D> void glNamedBufferSubData(A, B, C size, D ptr) {
+    const unsigned char* p = static_cast<const unsigned char*>(static_cast<const void*>(ptr));
+    rfk_gl_capture::uploads.emplace_back(p, p + (std::size_t)size);
+}
+template <typename A, typename B, typename C> void glUniform1fv(A, B n, C ptr) { rfk_gl_capture::uniform_arrays.emplace_back(ptr, ptr + n); }

@@ -1,0 +1,100 @@
+"""Product and oracle against golden fixtures produced by the REFERENCE'S OWN host code (tests/golden/reference_host_*.json.gz,
+written by tests/golden/make_reference_golden.py from src/flame.cpp + src/variation_table.cpp + src/util.cpp compiled from
+/root/reference; oracle/ref_host.cpp says which dependencies are stand-ins). Pins SURVEY §8 rows a1-a7 and a15:
+load_flame's attribute handling, make_shader_buffer_map, copy_flame_data_to_buffer, compile_flame_xforms, the
+screen-space affine."""
+import glob
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "reference_host_*.json.gz")))
+
+
+def _load(path):
+    with gzip.open(path, "rt") as fh:
+        return json.load(fh)
+
+
+def _defined_palette_rows(xml):
+    """palette entries the genome sets; the reference leaves the others uninitialised (`new flame{}` runs a user-provided
+    constructor, src/flame.hpp:136-138, so the array is not zeroed) — product and oracle zero them"""
+    import re
+    return sorted({int(m) for m in re.findall(r'<color index="(\d+)"', xml)})
+
+
+def _bits(values):
+    return [("%08x" % v) for v in np.asarray(values, dtype=np.float32).reshape(-1).view(np.uint32)]
+
+
+def test_fixture_set_is_complete():
+    names = {os.path.basename(p)[len("reference_host_"):-len(".json.gz")] for p in FIXTURES}
+    assert {"electricsheep", "bad_attribute"} | {"chunk%d" % i for i in range(6)} <= names
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[15:-8] for p in FIXTURES])
+def test_product_matches_reference_host_code(rfk, compiler, path):
+    g = _load(path)
+    f = rfk.Flame.load_flame_string(g["genome_xml"], compiler)
+    if not g["loaded"]:
+        assert f is None and "Unknown attribute" in rfk.Flame.last_error()
+        return
+    assert f is not None, rfk.Flame.last_error()
+    assert g["iterate_shader_contains_generated_text"]
+    i = f.info()
+    assert list(i.size) == g["size"] and _bits(i.center) == g["center"]
+    assert _bits([i.scale, i.rotate, i.estimator_curve, i.gamma, i.vibrancy, i.brightness]) == [g[k] for k in ("scale", "rotate", "estimator_curve", "gamma", "vibrancy", "brightness")]
+    assert (i.estimator_min, i.estimator_radius) == (g["estimator_min"], g["estimator_radius"])
+    for gx in g["xforms"]:
+        x = f.xform(gx["index"])
+        assert _bits(x.affine) == gx["affine"] and bool(x.has_post) == ("post" in gx)
+        if "post" in gx:
+            assert _bits(x.post) == gx["post"]
+        assert _bits([x.weight, x.color, x.color_speed, x.rotation_frequency, x.opacity]) == [gx[k] for k in ("weight", "color", "color_speed", "rotation_frequency", "opacity")]
+        assert {k: _bits([v])[0] for k, v in f.variations(gx["index"]).items()} == gx.get("variations", {})
+        assert {k: _bits([v])[0] for k, v in f.params_of(gx["index"]).items()} == gx.get("var_param", {})
+    assert i.num_xforms + i.has_final_xform == len(g["xforms"])
+    rows = _defined_palette_rows(g["genome_xml"])
+    gp = np.array(g["palette"]).reshape(256, 4)
+    assert np.array_equal(np.array(_bits(f.palette())).reshape(256, 4)[rows], gp[rows])
+    assert json.loads(f.buffer_map_json()) == g["buffer_map"]
+    n = g["buffer_map"]["size"]
+    assert _bits(f.copy_flame_data_to_buffer()[:n]) == g["fp"]
+    ref_text = g["compile_flame_xforms"]
+    assert ref_text.startswith("/*inja:int get_xform_id(float ratio) {")  # the template itself is not rendered by the stand-in
+    mine = f.glsl_source()
+    assert mine[mine.index("vec4 dispatch(vec3 v, int xform){"):] == ref_text[ref_text.index("vec4 dispatch(vec3 v, int xform){"):]
+    W, H = g["ss_affine_dims"]
+    assert _bits(f.screen_space_affine(W, H)) == g["ss_affine"]
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[15:-8] for p in FIXTURES])
+def test_oracle_matches_reference_host_code(oracle_mod, vt, path):
+    g = _load(path)
+    of = oracle_mod.load_flame_string(g["genome_xml"], vt)
+    if not g["loaded"]:
+        assert of is None
+        return
+    assert of.size == g["size"] and _bits(of.center) == g["center"]
+    assert _bits([of.scale, of.rotate, of.estimator_curve, of.gamma, of.vibrancy, of.brightness]) == [g[k] for k in ("scale", "rotate", "estimator_curve", "gamma", "vibrancy", "brightness")]
+    xs = list(of.xforms) + ([of.final_xform] if of.final_xform is not None else [])
+    for gx in g["xforms"]:
+        x = of.final_xform if gx["index"] == -1 else of.xforms[gx["index"]]
+        assert _bits(x.affine) == gx["affine"] and (x.post is not None) == ("post" in gx)
+        assert {k: _bits([v])[0] for k, v in x.variations.items()} == gx.get("variations", {})
+        assert {k: _bits([v])[0] for k, v in x.var_param.items()} == gx.get("var_param", {})
+        assert _bits([x.weight, x.color, x.color_speed, x.rotation_frequency, x.opacity]) == [gx[k] for k in ("weight", "color", "color_speed", "rotation_frequency", "opacity")]
+    rows = _defined_palette_rows(g["genome_xml"])
+    assert len(xs) == len(g["xforms"])
+    assert np.array_equal(np.array(_bits(of.palette)).reshape(256, 4)[rows], np.array(g["palette"]).reshape(256, 4)[rows])
+    assert of.buffer_map == g["buffer_map"]
+    assert _bits(oracle_mod.copy_flame_data_to_buffer(of)[: g["buffer_map"]["size"]]) == g["fp"]
+    ref_text, mine = g["compile_flame_xforms"], oracle_mod.compile_flame_xforms(of, vt)
+    assert mine[mine.index("vec4 dispatch(vec3 v, int xform){"):] == ref_text[ref_text.index("vec4 dispatch(vec3 v, int xform){"):]
+    W, H = g["ss_affine_dims"]
+    assert _bits(oracle_mod.screen_space_affine(of, W, H)) == g["ss_affine"]
