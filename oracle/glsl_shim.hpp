@@ -48,32 +48,81 @@ template <int A, int B> swz2<A, B>& swz2<A, B>::operator+=(const vec2& v) { floa
 template <int A, int B> swz2<A, B>& swz2<A, B>::operator-=(const vec2& v) { float a = v.x, b = v.y; d[A] -= a; d[B] -= b; return *this; }
 template <int A, int B> swz2<A, B>& swz2<A, B>::operator*=(float s) { d[A] *= s; d[B] *= s; return *this; }
 
+struct uvec2 {
+    uint x, y;
+    uvec2() : x(0), y(0) {}
+    uvec2(uint a, uint b) : x(a), y(b) {}
+};
+
 struct ivec2 {
     int x, y;
     ivec2() : x(0), y(0) {}
     ivec2(int a, int b) : x(a), y(b) {}
+    explicit ivec2(const vec2& v) : x(int(v.x)), y(int(v.y)) {}
+    explicit ivec2(const uvec2& v) : x(int(v.x)), y(int(v.y)) {}
+};
+
+struct vec3;
+template <int A, int B, int C>
+struct swz3 {  // three-component swizzle proxy (.xyz / .rgb of a vec4)
+    float d[4];
+    operator vec3() const;
+    swz3& operator=(const vec3& v);
 };
 
 struct vec3 {
     union {
         struct { float x, y, z; };
+        struct { float r, g, b; };
         swz2<0, 1> xy;
     };
     vec3() : x(0), y(0), z(0) {}
     vec3(float a, float b, float c) : x(a), y(b), z(c) {}
+    explicit vec3(float a) : x(a), y(a), z(a) {}
     vec3(const vec2& a, float c) : x(a.x), y(a.y), z(c) {}
     vec3(const vec3& o) : x(o.x), y(o.y), z(o.z) {}
     vec3& operator=(const vec3& o) { x = o.x; y = o.y; z = o.z; return *this; }
 };
+template <int A, int B, int C> swz3<A, B, C>::operator vec3() const { return vec3(d[A], d[B], d[C]); }
+template <int A, int B, int C> swz3<A, B, C>& swz3<A, B, C>::operator=(const vec3& v) { float a = v.x, b = v.y, c = v.z; d[A] = a; d[B] = b; d[C] = c; return *this; }
 
 struct vec4 {
-    float x, y, z, w;
+    union {
+        struct { float x, y, z, w; };
+        struct { float r, g, b, a; };
+        swz2<0, 1> xy;
+        swz3<0, 1, 2> xyz;
+        swz3<0, 1, 2> rgb;
+    };
     vec4() : x(0), y(0), z(0), w(0) {}
-    vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
-    vec4(const vec2& a, float c, float d) : x(a.x), y(a.y), z(c), w(d) {}
-    vec3 xyz() const { return vec3(x, y, z); }
+    vec4(float a_, float b_, float c_, float d_) : x(a_), y(b_), z(c_), w(d_) {}
+    vec4(const vec2& a_, float c_, float d_) : x(a_.x), y(a_.y), z(c_), w(d_) {}
+    vec4(const vec3& a_, float d_) : x(a_.x), y(a_.y), z(a_.z), w(d_) {}
+    vec4(const vec4& o) : x(o.x), y(o.y), z(o.z), w(o.w) {}
+    vec4& operator=(const vec4& o) { x = o.x; y = o.y; z = o.z; w = o.w; return *this; }
+    vec4& operator+=(const vec4& o) { x += o.x; y += o.y; z += o.z; w += o.w; return *this; }
+    vec4& operator*=(float s) { x *= s; y *= s; z *= s; w *= s; return *this; }
 };
+static_assert(sizeof(vec4) == 16, "vec4 must match the std430 layout of the reference's buffers");
 inline vec4 operator*(const vec4& a, const vec4& b) { return vec4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+inline vec4 operator*(const vec4& a, float s) { return vec4(a.x * s, a.y * s, a.z * s, a.w * s); }
+inline vec3 operator*(float s, const vec3& a) { return vec3(s * a.x, s * a.y, s * a.z); }
+
+struct uvec3 {
+    struct xy_t { uint d[4]; operator uvec2() const { return uvec2(d[0], d[1]); } };
+    union {
+        struct { uint x, y, z; };
+        xy_t xy;
+    };
+    uvec3() : x(0), y(0), z(0) {}
+    uvec3(uint a, uint b, uint c) : x(a), y(b), z(c) {}
+};
+struct uvec4 { uint x, y, z, w; };
+struct mat4 { float m[16]; };  // column-major, as glUniformMatrix4fv(transpose = false) stores it
+inline vec4 operator*(const mat4& M, const vec4& v) {
+    return vec4(M.m[0] * v.x + M.m[4] * v.y + M.m[8] * v.z + M.m[12] * v.w, M.m[1] * v.x + M.m[5] * v.y + M.m[9] * v.z + M.m[13] * v.w,
+                M.m[2] * v.x + M.m[6] * v.y + M.m[10] * v.z + M.m[14] * v.w, M.m[3] * v.x + M.m[7] * v.y + M.m[11] * v.z + M.m[15] * v.w);
+}
 
 #define GLSL_BINOP(op)                                                                       \
     inline vec2 operator op(const vec2& a, const vec2& b) { return vec2(a.x op b.x, a.y op b.y); } \
@@ -86,10 +135,12 @@ GLSL_BINOP(/)
 #undef GLSL_BINOP
 inline vec2 operator-(const vec2& a) { return vec2(-a.x, -a.y); }
 
+#ifndef GLSL_SHIM_NO_MATH_GLSL  // the shader-text build (oracle/softgl) compiles math.glsl itself
 // math.glsl:1-4
 static const float PI = 3.141592653589793f;
 static const float PI_2 = PI / 2.0f;
 static const float EPS = (1e-10f);
+#endif
 
 inline float sin(float v) { return ::sinf(v); }
 inline float cos(float v) { return ::cosf(v); }
@@ -128,11 +179,21 @@ inline vec2 cos(const vec2& v) { return vec2(::cosf(v.x), ::cosf(v.y)); }
 inline vec2 abs(const vec2& v) { return vec2(::fabsf(v.x), ::fabsf(v.y)); }
 inline vec2 mix(const vec2& a, const vec2& b, float t) { return vec2(mix(a.x, b.x, t), mix(a.y, b.y, t)); }
 
+inline vec2 floor(const vec2& v) { return vec2(::floorf(v.x), ::floorf(v.y)); }
+inline vec3 pow(const vec3& a, const vec3& b) { return vec3(::powf(a.x, b.x), ::powf(a.y, b.y), ::powf(a.z, b.z)); }
+inline vec3 mix(const vec3& a, const vec3& b, float t) { return vec3(mix(a.x, b.x, t), mix(a.y, b.y, t), mix(a.z, b.z, t)); }
+inline vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+inline uint min(int a, uint b) { return uint(a) < b ? uint(a) : b; }  // GLSL converts the int operand to uint
+inline uint min(uint a, uint b) { return a < b ? a : b; }
+inline uint atomicAdd(uint& mem, int v) { return __atomic_fetch_add(&mem, uint(v), __ATOMIC_RELAXED); }
+
+#ifndef GLSL_SHIM_NO_MATH_GLSL
 // math.glsl:6-22
 inline vec2 sincos(float v) { return vec2(sin(v), cos(v)); }
 inline vec2 sinhcosh(float v) { return vec2(sinh(v), cosh(v)); }
 inline float mod2(float x, float y) { return x - y * trunc(x / y); }
 inline float log10(float x) { return log(x) * 0.434294481903251827651128918916f; }
 inline bool badval(float x) { return (x != x) || (x > 1e10f) || (x < -1e10f); }
+#endif
 
 }  // namespace glsl

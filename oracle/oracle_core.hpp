@@ -207,7 +207,7 @@ inline void iterate_pass(sim& S, const pass_uniforms& u, const float* pos_in, fl
                 float* po = pos_out + 4 * (base + o_idx);
                 po[0] = result.x; po[1] = result.y; po[2] = result.z; po[3] = 0.0f;
                 if (u.do_draw) {
-                    if (S.has_final) result = dispatch(result.xyz(), -1) * vec4(1.0f, 1.0f, 1.0f, result.w);
+                    if (S.has_final) result = dispatch(result.xyz, -1) * vec4(1.0f, 1.0f, 1.0f, result.w);
                     int idx = bin_index(result.x, result.y, result.w, u.ss_affine, u.bin_w, u.bin_h);
                     if (idx >= 0) {
                         const float* pal = S.palette.data() + 4 * palette_index(result.z);

@@ -3,7 +3,6 @@
 #pragma once
 #include "glsl_shim.hpp"
 namespace glsl {
-struct uvec4 { uint x, y, z, w; };
 static thread_local uvec4 local_random_state;  // random.glsl:19
 static thread_local const float* fp;           // flame.glsl:27 (shared float fp[1024])
 static thread_local bool first_run;            // flame.glsl:13

@@ -1,0 +1,45 @@
+"""Small exercise of every kernel of the library, meant to be run under compute-sanitizer
+(tools/sanitize.sh): warm-up, draw in every kernel mode, density estimation + tonemap, supersampled
+frame, reference pass mode, seeding kernels. Sizes are tiny: the sanitizer tools slow kernels 10-100x."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import refrakt_b200 as r  # noqa: E402
+
+FIX = os.path.join(ROOT, "tests", "fixtures")
+compiler = r.FlameCompiler(os.path.join(FIX, "variations.yaml"))
+flame = r.Flame.load_flame(os.path.join(FIX, "electricsheep.247.11256.flam3"), compiler)
+assert flame is not None, r.Flame.last_error()
+
+P, TS = 256 * 32, 16
+r.set_sim_parameters(P, TS, 16, seed=3)
+W, H = 96, 54
+modes = [dict(), dict(warp_aggregate=1), dict(per_lane_xform=1), dict(deterministic=1), dict(count_xforms=1),
+         dict(block_width=128), dict(block_width=512), dict(deal_period=4), dict(math_mode=0), dict(math_mode=2)]
+base = flame.options()
+defaults = {k: getattr(base, k) for k, _ in base._fields_}
+for kw in modes:
+    flame.set_options(**defaults)
+    flame.set_options(**kw)
+    flame.warmup(3, 1.2 / 60)
+    img, stats = flame.render_frame(W, H, max_draw_calls=1, drawing_passes=4, warmup_passes=3)
+    assert stats.binned > 0, kw
+    print("mode", kw, "binned", stats.binned)
+flame.set_options(**defaults)
+
+img, stats = flame.render_frame(W, H, max_draw_calls=1, drawing_passes=4, warmup_passes=3, supersample=2, filter_radius=0.75)
+print("supersampled frame", img.shape, stats.binned)
+
+r.set_shuffle_buffers(count=8, seed=5)
+flame.reference_warmup(3, 1.2 / 60, shuffle_ids=np.arange(8, dtype=np.uint32) % 8)
+bins = r.DeviceBuffer(W * H * 16)
+bins.zero_out()
+n = flame.reference_draw_to_bins(bins.ptr, W * H, W, 3, shuffle_ids=np.arange(6, dtype=np.uint32) % 8)
+print("reference pass mode binned", n)
+
+print("seed", r.seed_rng_states(1024, 0)[-1], "hammersley", r.make_sample_points(512)[-1], "shuffle", r.make_shuffle_buffers(512, 2, 1)[0, :4])
+print("launches", r.kernel_launch_count())
