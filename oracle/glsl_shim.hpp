@@ -185,6 +185,7 @@ inline vec3 mix(const vec3& a, const vec3& b, float t) { return vec3(mix(a.x, b.
 inline vec3 clamp(const vec3& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
 inline uint min(int a, uint b) { return uint(a) < b ? uint(a) : b; }  // GLSL converts the int operand to uint
 inline uint min(uint a, uint b) { return a < b ? a : b; }
+inline float uintBitsToFloat(uint u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 inline uint atomicAdd(uint& mem, int v) { return __atomic_fetch_add(&mem, uint(v), __ATOMIC_RELAXED); }
 
 #ifndef GLSL_SHIM_NO_MATH_GLSL

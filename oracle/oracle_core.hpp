@@ -140,6 +140,8 @@ struct sim {
     unsigned long long counter = 0;       // flame_atomic_counters[0]
     unsigned long long xform_picks[64] = {0};
     std::vector<uint32_t> id_log;         // every (shuf_buf_idx_in, shuf_buf_idx_out) pair drawn, in order
+    std::vector<uint32_t> forced_ids;     // when non-empty, the host loops take their shuffle ids from here (replaying a recorded run)
+    size_t forced_pos = 0;
 };
 
 // src/flame.cpp:105-158

@@ -664,6 +664,21 @@ class Oracle:
         self.lib.orc_get_shuffle_table(_p(out, ctypes.c_uint32))
         return out
 
+    def set_shuffle_table(self, tables):
+        tables = np.ascontiguousarray(tables, dtype=np.uint32)
+        assert tables.size == self.shuffle_table(tables.shape[0]).size
+        self.lib.orc_set_shuffle_table(_p(tables, ctypes.c_uint32))
+
+    def force_pass_ids(self, ids):
+        """the next host loops take their (in, out) shuffle ids from `ids` (flattened pairs) instead of the seeded generator"""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32).reshape(-1)
+        self.lib.orc_force_pass_ids(_p(ids, ctypes.c_uint32), ctypes.c_size_t(ids.size))
+
+    def fp_inflated(self):
+        out = np.zeros((self.TS, self.total_params), dtype=np.float32)
+        self.lib.orc_get_fp_inflated(_p(out, ctypes.c_float))
+        return out
+
     def id_log(self, clear=False):
         """every (shuf_buf_idx_in, shuf_buf_idx_out) pair the host loops drew so far (flame.cpp:261-262, :274-275, :320-321)"""
         self.lib.orc_id_log_size.restype = ctypes.c_size_t

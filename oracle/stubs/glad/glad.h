@@ -24,18 +24,11 @@ RFK_GLC(GL_SHADER_STORAGE_BUFFER, 0x90D2) RFK_GLC(GL_DRAW_FRAMEBUFFER, 0x8CA9) R
 RFK_GLC(GL_TEXTURE_BORDER_COLOR, 0x1004) RFK_GLC(GL_REPEAT, 0x2901) RFK_GLC(GL_FRAMEBUFFER_COMPLETE, 0x8CD5)
 // any GL call in an inline body of the reference's headers resolves to an empty variadic template
 #define RFK_GLF(name) template <typename... A> void name(A...) {}
-RFK_GLF(glCreateBuffers) RFK_GLF(glNamedBufferStorage) RFK_GLF(glNamedBufferData) RFK_GLF(glDeleteBuffers) 
-RFK_GLF(glGetNamedBufferSubData) RFK_GLF(glClearNamedBufferData) RFK_GLF(glBindBufferBase) RFK_GLF(glCreateTextures) RFK_GLF(glTextureStorage2D)
+RFK_GLF(glCreateTextures) RFK_GLF(glTextureStorage2D)
 RFK_GLF(glDeleteTextures) RFK_GLF(glGetTextureImage) RFK_GLF(glTextureParameteri) RFK_GLF(glTextureParameterfv) RFK_GLF(glCreateFramebuffers) RFK_GLF(glDeleteFramebuffers)
-RFK_GLF(glBindFramebuffer) RFK_GLF(glNamedFramebufferTexture) RFK_GLF(glFramebufferTexture) RFK_GLF(glFramebufferTexture2D) RFK_GLF(glUniform1i) RFK_GLF(glUniform1ui) RFK_GLF(glUniform1f)
-RFK_GLF(glUniform2fv) RFK_GLF(glUniform3fv) RFK_GLF(glUniform4fv) RFK_GLF(glUniform2uiv) RFK_GLF(glUniform3uiv) RFK_GLF(glUniform4uiv)
-RFK_GLF(glUniform2iv) RFK_GLF(glUniform3iv) RFK_GLF(glUniform4iv) RFK_GLF(glUniformMatrix4fv) RFK_GLF(glUseProgram)
-RFK_GLF(glCompileShader) RFK_GLF(glGetShaderInfoLog) RFK_GLF(glDeleteShader)
-RFK_GLF(glAttachShader) RFK_GLF(glLinkProgram) RFK_GLF(glGetProgramInfoLog) RFK_GLF(glDeleteProgram) RFK_GLF(glDetachShader)
+RFK_GLF(glBindFramebuffer) RFK_GLF(glNamedFramebufferTexture) RFK_GLF(glFramebufferTexture) RFK_GLF(glFramebufferTexture2D) RFK_GLF(glCompileShader) RFK_GLF(glGetShaderInfoLog) RFK_GLF(glDeleteShader)
+RFK_GLF(glDeleteProgram) RFK_GLF(glDetachShader)
 RFK_GLF(glDrawBuffers) RFK_GLF(glBindTexture) RFK_GLF(glClearTexImage) RFK_GLF(glBindBuffer) RFK_GLF(glGenFramebuffers) RFK_GLF(glTexImage2D) RFK_GLF(glGenTextures)
-template <typename... A> GLuint glCreateShader(A...) { return 0; }
-template <typename... A> GLuint glCreateProgram(A...) { return 0; }
-template <typename... A> GLint glGetUniformLocation(A...) { return 0; }
 template <typename... A> GLenum glCheckFramebufferStatus(A...) { return 0; }
 template <typename... A> GLenum glCheckNamedFramebufferStatus(A...) { return 0; }
 // further names the reference's headers mention (values are never used)
@@ -47,19 +40,30 @@ RFK_GLC(GL_RGB, 0)
 RFK_GLC(GL_TEXTURE_BINDING_2D, 0)
 RFK_GLF(glGenerateMipmap)
 RFK_GLF(glGetIntegerv)
-RFK_GLF(glMapNamedBuffer)
 RFK_GLF(glTexParameteri)
 RFK_GLF(glUnmapNamedBuffer)
 
 RFK_GLC(GL_ALL_BARRIER_BITS, 0)
-RFK_GLF(glDispatchCompute)
 RFK_GLF(glFinish)
 RFK_GLF(glMemoryBarrier)
 
-// Capturing entry points: what the reference hands to GL is recorded so that the text of the shader it generated and the
-// parameter buffer it uploads can be read back by oracle/ref_host.cpp. Compilation and linking "succeed".
+// ---------------------------------------------------------------------------------------------------------------
+// The entry points of the render path. Two builds:
+//  * default: empty / capturing templates — what the reference hands to GL is recorded (shader text, parameter upload),
+//    nothing executes (libref_pins_flame.so);
+//  * RFK_SOFTGL: forwarded to the software GL of oracle/softgl/, which executes the reference's shaders on the CPU
+//    (libref_host.so).
 #include <string>
 #include <cstring>
+#ifndef RFK_SOFTGL
+RFK_GLF(glCreateBuffers) RFK_GLF(glNamedBufferStorage) RFK_GLF(glNamedBufferData) RFK_GLF(glDeleteBuffers) RFK_GLF(glGetNamedBufferSubData) RFK_GLF(glClearNamedBufferData) 
+RFK_GLF(glBindBufferBase) RFK_GLF(glUniform1i) RFK_GLF(glUniform1ui) RFK_GLF(glUniform1f) RFK_GLF(glUniform2fv) RFK_GLF(glUniform3fv) 
+RFK_GLF(glUniform4fv) RFK_GLF(glUniform2uiv) RFK_GLF(glUniform3uiv) RFK_GLF(glUniform4uiv) RFK_GLF(glUniform2iv) RFK_GLF(glUniform3iv) 
+RFK_GLF(glUniform4iv) RFK_GLF(glUniformMatrix4fv) RFK_GLF(glUseProgram) RFK_GLF(glAttachShader) RFK_GLF(glLinkProgram) RFK_GLF(glGetProgramInfoLog) 
+RFK_GLF(glMapNamedBuffer) RFK_GLF(glDispatchCompute) 
+template <typename... A> GLuint glCreateShader(A...) { return 0; }
+template <typename... A> GLuint glCreateProgram(A...) { return 0; }
+template <typename... A> GLint glGetUniformLocation(A...) { return 0; }
 namespace rfk_gl_capture {
 inline std::vector<std::string> shader_sources;            // every glShaderSource string, in call order
 inline std::vector<std::vector<unsigned char>> uploads;    // every glNamedBufferSubData payload
@@ -73,3 +77,41 @@ template <typename A, typename B, typename C, typename D> void glNamedBufferSubD
     rfk_gl_capture::uploads.emplace_back(p, p + (std::size_t)size);
 }
 template <typename A, typename B, typename C> void glUniform1fv(A, B n, C ptr) { rfk_gl_capture::uniform_arrays.emplace_back(ptr, ptr + n); }
+
+#else
+#include "../../softgl/softgl.hpp"
+template <typename N> void glCreateBuffers(int n, N* names) { softgl::create_buffers(n, names); }
+template <typename S, typename D, typename F> void glNamedBufferStorage(GLuint name, S bytes, D data, F) { softgl::buffer_storage(name, (std::ptrdiff_t)bytes, (const void*)data); }
+template <typename S, typename D, typename F> void glNamedBufferData(GLuint name, S bytes, D data, F) { softgl::buffer_storage(name, (std::ptrdiff_t)bytes, (const void*)data); }
+template <typename O, typename S, typename D> void glNamedBufferSubData(GLuint name, O offset, S bytes, D data) { softgl::buffer_sub_data(name, (std::ptrdiff_t)offset, (std::ptrdiff_t)bytes, (const void*)data); }
+template <typename O, typename S, typename D> void glGetNamedBufferSubData(GLuint name, O offset, S bytes, D out) { softgl::get_buffer_sub_data(name, (std::ptrdiff_t)offset, (std::ptrdiff_t)bytes, (void*)out); }
+template <typename... A> void glClearNamedBufferData(GLuint name, A...) { softgl::clear_buffer(name); }
+template <typename N> void glDeleteBuffers(int n, N* names) { softgl::delete_buffers(n, names); }
+template <typename A> void* glMapNamedBuffer(GLuint name, A) { return softgl::map_buffer(name); }
+inline void glBindBufferBase(GLenum, GLuint index, GLuint name) { softgl::bind_buffer_base(index, name); }
+inline GLuint glCreateShader(GLenum type) { return softgl::create_shader(type); }
+template <typename C, typename D> void glShaderSource(GLuint shader, int, C strings, D) { softgl::shader_source(shader, strings[0]); }
+inline void glGetShaderiv(GLuint, GLenum, int* out) { *out = 1; }  // compilation happens at link time
+inline GLuint glCreateProgram() { return softgl::create_program(); }
+inline void glAttachShader(GLuint program, GLuint shader) { softgl::attach_shader(program, shader); }
+inline void glLinkProgram(GLuint program) { softgl::link_program(program); }
+inline void glGetProgramiv(GLuint program, GLenum, int* out) { *out = softgl::link_status(program); }
+template <typename L> void glGetProgramInfoLog(GLuint program, int cap, L, char* out) { std::string l = softgl::program_log(program); std::strncpy(out, l.c_str(), cap - 1); out[cap - 1] = 0; }
+inline void glUseProgram(GLuint program) { softgl::use_program(program); }
+inline GLint glGetUniformLocation(GLuint program, const char* name) { return softgl::uniform_location(program, name); }
+inline void glUniform1i(GLint l, int v) { softgl::set_uniform(l, &v, 4); }
+inline void glUniform1ui(GLint l, unsigned v) { softgl::set_uniform(l, &v, 4); }
+inline void glUniform1f(GLint l, float v) { softgl::set_uniform(l, &v, 4); }
+template <typename P> void glUniform1fv(GLint l, int n, P v) { softgl::set_uniform(l, v, 4 * (std::size_t)n); }
+template <typename P> void glUniform2fv(GLint l, int n, P v) { softgl::set_uniform(l, v, 8 * (std::size_t)n); }
+template <typename P> void glUniform3fv(GLint l, int n, P v) { softgl::set_uniform(l, v, 12 * (std::size_t)n); }
+template <typename P> void glUniform4fv(GLint l, int n, P v) { softgl::set_uniform(l, v, 16 * (std::size_t)n); }
+template <typename P> void glUniform2uiv(GLint l, int n, P v) { softgl::set_uniform(l, v, 8 * (std::size_t)n); }
+template <typename P> void glUniform3uiv(GLint l, int n, P v) { softgl::set_uniform(l, v, 12 * (std::size_t)n); }
+template <typename P> void glUniform4uiv(GLint l, int n, P v) { softgl::set_uniform(l, v, 16 * (std::size_t)n); }
+template <typename P> void glUniform2iv(GLint l, int n, P v) { softgl::set_uniform(l, v, 8 * (std::size_t)n); }
+template <typename P> void glUniform3iv(GLint l, int n, P v) { softgl::set_uniform(l, v, 12 * (std::size_t)n); }
+template <typename P> void glUniform4iv(GLint l, int n, P v) { softgl::set_uniform(l, v, 16 * (std::size_t)n); }
+template <typename T, typename P> void glUniformMatrix4fv(GLint l, int n, T, P v) { softgl::set_uniform(l, v, 64 * (std::size_t)n); }
+inline void glDispatchCompute(GLuint x, GLuint y, GLuint z) { softgl::dispatch_compute(x, y, z); }
+#endif
