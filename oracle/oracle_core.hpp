@@ -16,13 +16,12 @@
 // output (restated in refrakt_oracle.py) pasted ahead of this header by the generator,
 // compiled against glsl_shim.hpp.
 //
-// PARITY UNPINNED for this file: the reference has no tests, golden vectors or fixtures
-// (SURVEY.md §4), and its shaders cannot be run here (no GL context, 12 fetched dependencies).
-// The host-side pieces that DO compile from /root/reference (jsf32, hammersley, the affine helpers,
-// and the whole of flame.cpp + variation_table.cpp against stand-in headers — oracle/Makefile ->
-// oracle/_ref/) pin the functions marked util.hpp / hammersley.cpp above and the generated
-// get_xform_id()/dispatch() text this header is compiled with (tests/test_reference_golden.py);
-// the shader restatements below are pinned only by reading the reference source.
+// PARITY PINNED against the reference's own code run here: the reference has no tests, golden vectors or fixtures
+//  and needs a GL context, but its host sources compile unmodified against stand-in headers and a software GL
+// that executes its GLSL text on the CPU (oracle/ref_host.cpp, oracle/softgl/, built by oracle/Makefile into oracle/_ref/).
+// Replaying recorded runs of that build, this restatement reproduces RNG states, particle buffers, histogram and
+// fp_inflated bit for bit and density estimation to 1e-4 (tests/test_reference_device_golden.py, fixtures under
+// tests/golden/reference_device_*.npz). Caveat stated there: shaders run through g++ and glibc's libm, not a GLSL compiler.
 //
 // Where the reference leaves behaviour open, the oracle fixes it and says so:
 //   * operand evaluation order of several randf() in one statement: textual order

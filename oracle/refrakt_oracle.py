@@ -19,17 +19,16 @@ reference source function by function:
 The generated GLSL is compiled for the CPU against glsl_shim.hpp with g++ (-ffp-contract=off)
 into oracle/_build/ and driven through ctypes.
 
-PARITY: HOST HALF PINNED, DEVICE HALF UNPINNED. The reference ships no tests, golden vectors or
-fixtures and cannot be built or run as a whole here (GL + 12 fetched dependencies).
-What compiles from the reference sources where they lie (oracle/Makefile -> oracle/_ref/):
+PARITY PINNED against the reference's own code run here. The reference ships no tests, golden vectors or fixtures
+ and cannot be built as a whole (GL + 12 fetched dependencies). What compiles from the reference sources
+where they lie (oracle/Makefile -> oracle/_ref/):
   libref_pins*.so   jsf32, hammersley, replace_macro/find_macros, the buffer_cache reader, the
                     affine helpers of flame.hpp  -> tests/test_oracle_golden.py
-  libref_host.so    the reference's own flame.cpp + variation_table.cpp (parser, buffer map, fp[],
-                    compile_flame_xforms, screen-space affine) against stand-in third-party headers
-                    (oracle/stubs/) -> tests/golden/reference_host_*.json.gz
-                    -> tests/test_reference_golden.py compares this restatement AND the product.
-Everything in this file up to and including the generated GLSL text is therefore pinned against
-reference outputs; the GLSL as executed (oracle_core.hpp) is pinned only by reading the shaders.
+  libref_host.so    the reference's own flame.cpp + variation_table.cpp + ... against stand-in third-party headers
+                    (oracle/stubs/) and a software GL that runs its GLSL on the CPU (oracle/softgl/)
+                    -> tests/golden/reference_host_*.json.gz, reference_device_*.npz
+                    -> tests/test_reference_golden.py, tests/test_reference_device_golden.py compare this restatement
+                       AND the product, bit for bit where the arithmetic is the same.
 """
 from __future__ import annotations
 
