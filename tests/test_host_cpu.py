@@ -404,3 +404,57 @@ def test_xml_reader_edge_cases(rfk, compiler, oracle_mod, vt):
         assert got is None or isinstance(got, rfk.Flame)  # never crashes; malformed input is reported
     assert rfk.Flame.load_flame_string("<flame", compiler) is None and rfk.Flame.last_error() != ""
     assert rfk.Flame.load_flame_string(GENOME_TEMPLATE % '<xform weight="1" linear="1" coefs="x y" opacity="1"/>', compiler) is None
+
+
+def _mutate(text, rng, inserts, n_edits):
+    s = list(text)
+    for _ in range(n_edits):
+        i, op = rng.randrange(len(s)), rng.random()
+        if op < 0.35:
+            del s[i:i + rng.choice([1, 3, 10, 200])]
+        elif op < 0.7:
+            s.insert(i, rng.choice(inserts))
+        else:
+            s[i] = rng.choice(inserts)
+    return "".join(s)
+
+
+def test_genome_parser_survives_mutated_input(rfk, compiler):
+    """load_flame returns NULL + a message or a usable flame, never crashes (seeded mutation fuzz of the shipped genome:
+    deletions, stray markup, NUL and non-ASCII bytes, out-of-range numbers)"""
+    import random
+    from conftest import GENOME
+    xml, rng = open(GENOME).read(), random.Random(1)
+    inserts = ["<", ">", '"', "/", "=", " ", "&", "\x00", "é", "-1e999", "nan", "999999999999999999999", "<xform ", "/>"]
+    loaded = rejected = 0
+    for _ in range(600):
+        f = rfk.Flame.load_flame_string(_mutate(xml, rng, inserts, rng.choice([1, 2, 5, 20])), compiler)
+        if f is None:
+            assert rfk.Flame.last_error()
+            rejected += 1
+        else:
+            assert f.copy_flame_data_to_buffer().shape == (1024,) and "vec4 dispatch" in f.glsl_source()
+            loaded += 1
+    assert loaded > 50 and rejected > 50
+
+
+def test_variation_table_reader_survives_mutated_input(rfk, tmp_path):
+    """rfk_compiler_create on a damaged variations.yaml: an error or a table that still compiles the shipped genome's text"""
+    import random
+    from conftest import GENOME, VARIATIONS
+    text, rng = open(VARIATIONS).read(), random.Random(2)
+    inserts = [":", "-", "\n", "  ", "|", "$", '"', "'", "#", "\t", "{", "[", "x"]
+    ok = bad = 0
+    for k in range(120):
+        p = tmp_path / ("v%d.yaml" % k)
+        p.write_text(_mutate(text, rng, inserts, rng.choice([1, 3, 10])))
+        try:
+            c = rfk.FlameCompiler(str(p))
+        except rfk.RefraktError:
+            bad += 1
+            continue
+        ok += 1
+        f = rfk.Flame.load_flame(GENOME, c)
+        if f is not None:
+            assert "vec4 dispatch" in f.glsl_source() and "rfk_draw" in f.cuda_source()
+    assert ok > 10 and bad > 10
