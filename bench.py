@@ -186,7 +186,7 @@ def main():
     rgba8 = torch.empty(nbins * 4, dtype=torch.uint8, device="cuda")
     host_rgba8 = torch.empty(nbins * 4, dtype=torch.uint8).pin_memory()
     post = flame.post_params()
-    draw_events = []
+    draw_events, post_events = [], []
 
     def barrier():
         if world > 1:
@@ -212,7 +212,13 @@ def main():
             calls += 1
         sharding.reduce_histogram(bins, dst=0)  # the one exchange step (NCCL, 132.7 MB per rank)
         if rank == 0:
+            if record:
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
             r.density_tonemap(bins.data_ptr(), image.data_ptr(), rgba8.data_ptr(), W, H, post)
+            if record:
+                p1.record()
+                post_events.append((p0, p1))
         return P * (1 + WARMUP_PASSES + DRAW_PASSES * calls), binned, calls
 
     def e2e_step():
@@ -287,6 +293,14 @@ def main():
                          "binding_limit": "fp32/alu issue, not memory: see DESIGN.md and profiles/",
                          "iterations_per_s_kernel": P * DRAW_PASSES / (mean_draw_ms * 1e-3)},
         }
+        if post_events:
+            # density estimation + tonemap: 16 B/pixel histogram read + 16 B/pixel float image + 4 B/pixel RGBA8 written (32 B
+            # for the float image alone); HBM-bound by design, instruction-bound as measured (profiles/r01_density_tonemap.md)
+            post_ms = sum(a.elapsed_time(b) for a, b in post_events) / len(post_events)
+            post_bytes = 36.0 * nbins
+            line["roofline"]["post"] = {"kernel": "density_tonemap_kernel", "bound": "hbm", "launch_ms": post_ms, "algorithmic_bytes_per_launch": post_bytes,
+                                        "achieved": post_bytes / (post_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": post_bytes / (post_ms * 1e-3) / 1e9 / peak,
+                                        "share_of_step": post_ms * len(post_events) / ms}
         probes = roofline_probes()
         if probes:
             kernel_iters_s = P * DRAW_PASSES / (mean_draw_ms * 1e-3)
