@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RFK_ABI_VERSION 1
+#define RFK_ABI_VERSION 2
 
 enum {
     RFK_OK = 0,
@@ -146,6 +146,8 @@ typedef struct rfk_kernel_options {
     int32_t min_blocks;     /* __launch_bounds__ minBlocksPerSM, 0 = unset */
     int32_t block_width;    /* threads per CTA = particles per re-deal pool: 128, 256 (default, the reference's workgroup) or 512 */
     int32_t deal_period;    /* re-deal the CTA's particles across warps every n-th iteration; default 1 */
+    int32_t l2_hints;       /* histograms several times larger than L2: reductions outside the hot map (rfk_flame_build_hot_map)
+                               carry an L2 evict-first hint; default 0 */
 } rfk_kernel_options;
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* out);
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* in);
@@ -165,6 +167,22 @@ int64_t rfk_flame_draw_to_bins(rfk_flame* f, float* bins_dev, size_t bins_len, s
 /* Same without the read-back; rfk_flame_binned_total() returns the count since the last warmup. */
 int rfk_flame_draw_to_bins_async(rfk_flame* f, float* bins_dev, size_t bins_len, size_t bins_width, int num_iter);
 int64_t rfk_flame_binned_total(rfk_flame* f);
+/* Hot map for histograms much larger than the L2 (no reference counterpart; kernel option l2_hints). Cuts the histogram
+ * into 16 x 16-bin tiles, sums the density accumulated so far per tile and marks the densest tiles, at most budget_bytes
+ * of histogram (0 = half the device's L2), as worth keeping in L2. Later draw calls into a histogram of the same
+ * dimensions then send the reductions of every other tile with an evict-first hint, so that the one-off misses stop
+ * evicting the tiles most samples land in. Results are unchanged (it is a cache hint); call it after the first draw call
+ * of a frame. rfk_render_frame does so by itself when the option is set and the histogram exceeds twice the L2. */
+typedef struct rfk_hot_map_info {
+    int32_t tiles_x, tiles_y;
+    uint32_t hot_tiles;          /* tiles marked hot */
+    uint32_t threshold_bucket;   /* density bucket (upper 13 bits of the binary32 tile sum) a tile must exceed */
+    uint64_t budget_bytes;       /* the budget actually used */
+} rfk_hot_map_info;
+int rfk_flame_build_hot_map(rfk_flame* f, const float* bins_dev, size_t bins_len, size_t bins_width, uint64_t budget_bytes, rfk_hot_map_info* info_out);
+int rfk_flame_clear_hot_map(rfk_flame* f);
+/* copies the map (one bit per tile, row-major, tiles_x tiles per row) into out[0..n_words); returns the words it holds */
+int64_t rfk_flame_copy_hot_map(rfk_flame* f, uint32_t* out, size_t n_words);
 int rfk_flame_reset_animation(rfk_flame* f); /* flame::reset_animation, src/flame.hpp:95 */
 /* per-xform selection counts since the last warmup (count_xforms option); the reference's read-out is
  * src/main.cpp:595-611 */

@@ -39,7 +39,11 @@ class XformInfo(C.Structure):
 
 class KernelOptions(C.Structure):
     _fields_ = [("math_mode", C.c_int32), ("fmad", C.c_int32), ("per_lane_xform", C.c_int32), ("warp_aggregate", C.c_int32),
-                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32)]
+                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32), ("l2_hints", C.c_int32)]
+
+
+class HotMapInfo(C.Structure):
+    _fields_ = [("tiles_x", C.c_int32), ("tiles_y", C.c_int32), ("hot_tiles", C.c_uint32), ("threshold_bucket", C.c_uint32), ("budget_bytes", C.c_uint64)]
 
 
 class PostParams(C.Structure):
@@ -114,6 +118,9 @@ SIGNATURES = {
     "rfk_flame_draw_to_bins": (C.c_int64, [_vp, _vp, _sz, _sz, _i]),
     "rfk_flame_draw_to_bins_async": (_i, [_vp, _vp, _sz, _sz, _i]),
     "rfk_flame_binned_total": (C.c_int64, [_vp]),
+    "rfk_flame_build_hot_map": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_uint64, C.POINTER(HotMapInfo)]),
+    "rfk_flame_clear_hot_map": (C.c_int, [_vp]),
+    "rfk_flame_copy_hot_map": (C.c_int64, [_vp, C.POINTER(C.c_uint32), C.c_size_t]),
     "rfk_flame_reset_animation": (_i, [_vp]),
     "rfk_flame_xform_counts": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "rfk_flame_screen_affine": (_i, [_vp, _sz, _sz, _fpp]),
@@ -403,6 +410,22 @@ class Flame:
         out = np.zeros((total_particles, 4), dtype=np.float32)
         _check(lib().rfk_flame_copy_particles(self.handle, _ptr(out)), "copy_particles")
         return out
+
+    def build_hot_map(self, bins_ptr, bins_len, bins_width, budget_bytes=0) -> HotMapInfo:
+        """kernel option l2_hints: mark the densest 16 x 16-bin tiles of the histogram as worth keeping in L2"""
+        info = HotMapInfo()
+        _check(lib().rfk_flame_build_hot_map(self.handle, bins_ptr, bins_len, bins_width, budget_bytes, C.byref(info)), "build_hot_map")
+        return info
+
+    def clear_hot_map(self): _check(lib().rfk_flame_clear_hot_map(self.handle), "clear_hot_map")
+
+    def hot_map(self) -> np.ndarray:
+        """the map as a (tiles_y, tiles_x) bool array; empty when none is active"""
+        n = int(_check(lib().rfk_flame_copy_hot_map(self.handle, None, 0), "copy_hot_map"))
+        words = np.zeros(n, dtype=np.uint32)
+        if n:
+            _check(lib().rfk_flame_copy_hot_map(self.handle, _ptr(words, C.c_uint32), n), "copy_hot_map")
+        return np.unpackbits(words.view(np.uint8), bitorder="little").astype(bool)
 
     def binned_total(self) -> int: return int(_check(lib().rfk_flame_binned_total(self.handle), "binned_total"))
     def reset_animation(self): _check(lib().rfk_flame_reset_animation(self.handle), "reset_animation")

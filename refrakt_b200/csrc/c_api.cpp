@@ -336,7 +336,7 @@ int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size) {
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* o) {
     if (!f || !o) return fail(RFK_E_INVALID, "null argument");
     const auto& k = F(f)->options();
-    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks, k.block_width, k.deal_period};
+    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks, k.block_width, k.deal_period, k.l2_hints};
     return RFK_OK;
 }
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
@@ -347,6 +347,7 @@ int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
     k.min_blocks = i->min_blocks;
     k.block_width = i->block_width;
     k.deal_period = i->deal_period;
+    k.l2_hints = i->l2_hints ? 1 : 0;
     if (k.block_width != 128 && k.block_width != 256 && k.block_width != 512) return fail(RFK_E_INVALID, "block_width must be 128, 256 or 512");
     if (k.deal_period < 1) return fail(RFK_E_INVALID, "deal_period must be >= 1");
     if (k.math_mode < 0 || k.math_mode > 2) return fail(RFK_E_INVALID, "math_mode must be 0, 1 or 2");
@@ -390,6 +391,32 @@ int rfk_flame_draw_to_bins_async(rfk_flame* f, float* bins, size_t bins_len, siz
         F(f)->draw_to_bins_async(bins, bins_len, bins_width, num_iter);
         return RFK_OK;
     });
+}
+int rfk_flame_build_hot_map(rfk_flame* f, const float* bins, size_t bins_len, size_t bins_width, uint64_t budget_bytes, rfk_hot_map_info* info_out) {
+    return guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        auto i = F(f)->build_hot_map(bins, bins_len, bins_width, budget_bytes);
+        if (info_out) *info_out = rfk_hot_map_info{i.tiles_x, i.tiles_y, i.hot_tiles, i.threshold_bucket, i.budget_bytes};
+        return RFK_OK;
+    });
+}
+int rfk_flame_clear_hot_map(rfk_flame* f) {
+    return guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        F(f)->clear_hot_map();
+        return RFK_OK;
+    });
+}
+int64_t rfk_flame_copy_hot_map(rfk_flame* f, uint32_t* out, size_t n_words) {
+    int64_t result = 0;
+    int rc = guarded([&]() -> int {
+        if (!f) throw std::invalid_argument("null flame");
+        auto m = F(f)->copy_hot_map();
+        if (out) std::memcpy(out, m.data(), std::min(n_words, m.size()) * sizeof(uint32_t));
+        result = (int64_t)m.size();
+        return RFK_OK;
+    });
+    return rc == RFK_OK ? result : rc;
 }
 int64_t rfk_flame_binned_total(rfk_flame* f) {
     int64_t result = 0;
@@ -570,11 +597,21 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
 
         uint64_t binned = 0, iterations = 0;
         uint32_t calls = 0;
+        // kernel option l2_hints: a histogram more than twice the L2 gets its hot map after the first draw call
+        bool want_hot_map = false;
+        fl->clear_hot_map();
+        if (fl->options().l2_hints) {
+            int dev = 0, l2 = 0;
+            cuda_ok(cudaGetDevice(&dev), "cudaGetDevice");
+            cuda_ok(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev), "query L2 size");
+            want_hot_map = n * sizeof(float4) > 2 * (size_t)l2;
+        }
         while ((req->max_draw_calls == 0 || calls < req->max_draw_calls) && (req->target_binned == 0 || binned < req->target_binned)) {
             size_t got = fl->draw_to_bins(reinterpret_cast<float*>(b.bins), n, W, (int)req->drawing_passes);
             binned += got;
             iterations += (uint64_t)req->drawing_passes * sim_total_particles();
             calls++;
+            if (want_hot_map && calls == 1 && got > 0) fl->build_hot_map(reinterpret_cast<const float*>(b.bins), n, W, 0);
             if (req->target_binned && got == 0 && calls >= 4 && binned == 0) throw std::runtime_error("rfk_render_frame: nothing lands in the histogram");
         }
         cuda_ok(cudaEventRecord(b.ev[2], s), "event");

@@ -39,6 +39,8 @@ struct rfk_iter_params {
     unsigned int deal_seed;             // key of this call's re-deal permutations
     int hammersley_bits;                // log2 of the sample-point count (src/hammersley.cpp:37-42)
     float hammersley_inv_max;
+    const unsigned int* hot_map;        // RFK_L2_HINTS: one bit per 16 x 16-bin tile, set = keep in L2; null = no hints
+    int hot_tiles_x;                    // tiles per histogram row
 };
 
 #define RFK_FIXED_SCALE 16777216.0f  // 2^24
@@ -73,6 +75,29 @@ __device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const fl
     if (!(px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f)) return -1;
     return (H - __float2int_rz(py) - 1) * W + __float2int_rz(px);
 }
+
+#if RFK_L2_HINTS
+// The same test and index as rfk_bin_index, also returning the bit of the bin's 16 x 16 tile in the hot map.
+__device__ __forceinline__ int rfk_bin_index_hot(float x, float y, float w, const float* ss, int W, int H, float Wf, float Hf,
+                                                 const unsigned int* hot_map, int tiles_x, bool& hot) {
+    const float px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
+    const float py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
+    hot = true;
+    if (!(px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f)) return -1;
+    const int row = H - __float2int_rz(py) - 1, col = __float2int_rz(px);
+    if (hot_map) {
+        const unsigned int tile = (unsigned int)(row >> 4) * (unsigned int)tiles_x + (unsigned int)(col >> 4);
+        hot = (__ldg(hot_map + (tile >> 5)) >> (tile & 31u)) & 1u;
+    }
+    return row * W + col;
+}
+
+// Reduction into a bin of a tile that is NOT worth keeping in L2: the sector is marked evict-first, so the flood of
+// one-off misses of a histogram many times larger than L2 stops evicting the densely hit tiles ("hot map").
+__device__ __forceinline__ void rfk_red_add_v4_evict_first(float4* addr, float r, float g, float b, float a, unsigned long long policy) {
+    asm volatile("red.relaxed.gpu.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(r), "f"(g), "f"(b), "f"(a), "l"(policy) : "memory");
+}
+#endif
 
 __device__ __forceinline__ unsigned int rfk_palette_index(float z) {
     // min(255, uint(ceil(z * 255))): one saturating convert (negative and NaN -> 0; uint(negative) is undefined in GLSL)
@@ -139,6 +164,10 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 
     unsigned int binned = 0;
     int parity = 0;
+#if RFK_L2_HINTS
+    unsigned long long evict_first_policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first_policy));
+#endif
 
     // flame.glsl:51-53: the first thread of a workgroup burns one randf() per pass to pick the group's xform. Here
     // every lane burns one every 32 iterations and iteration i uses lane (i mod 32)'s draw: the same number of extra
@@ -211,7 +240,12 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
                 fx = q.x; fy = q.y; fc = q.z; fw = q.w * r.w;
             }
 #endif
+#if RFK_L2_HINTS
+            bool hot;
+            const int idx = rfk_bin_index_hot(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf, p.hot_map, p.hot_tiles_x, hot);
+#else
             const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf);
+#endif
 #if RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC
             const unsigned int hit = __ballot_sync(0xffffffffu, idx >= 0);
             if (idx >= 0) {
@@ -231,6 +265,9 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
                 atomicAdd(b + 1, (unsigned long long)__float2ll_rn(col.y * RFK_FIXED_SCALE));
                 atomicAdd(b + 2, (unsigned long long)__float2ll_rn(col.z * RFK_FIXED_SCALE));
                 atomicAdd(b + 3, (unsigned long long)__float2ll_rn(fw * RFK_FIXED_SCALE));
+  #elif RFK_L2_HINTS
+                if (hot) rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);
+                else rfk_red_add_v4_evict_first(p.bins + idx, col.x, col.y, col.z, fw, evict_first_policy);
   #else
                 rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);
   #endif

@@ -66,6 +66,7 @@ struct kernel_options {
     int min_blocks = 0;           // __launch_bounds__ second argument, 0 = compiler's choice
     int block_width = 256;        // threads per CTA = particles per re-deal pool (128, 256 or 512; the reference's workgroup is 256)
     int deal_period = 1;          // re-deal particles across warps every n-th iteration
+    int l2_hints = 0;             // histograms much larger than L2: evict-first reductions outside the hot map
     bool operator==(const kernel_options&) const = default;
 };
 
@@ -118,6 +119,13 @@ struct flame {
     // Same without the blocking counter read-back; collect with binned_total().
     void draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bins_width, int num_iter);
     std::uint64_t binned_total();  // all draw calls since the last warmup
+    // Kernel option l2_hints: classify the 16 x 16-bin tiles of `bins` by the density accumulated so far and mark the densest
+    // ones (at most budget_bytes of histogram; 0 = half the device's L2) as worth keeping in L2. Later draw calls into a
+    // histogram of the same dimensions send the reductions of all other tiles with an evict-first hint.
+    struct hot_map_info { int tiles_x = 0, tiles_y = 0; std::uint32_t hot_tiles = 0, threshold_bucket = 0; std::uint64_t budget_bytes = 0; };
+    hot_map_info build_hot_map(const float* bins, std::size_t bins_len, std::size_t bins_width, std::uint64_t budget_bytes);
+    void clear_hot_map();
+    std::vector<std::uint32_t> copy_hot_map();  // one bit per tile, row-major
 
     // The reference's own dispatch structure on the GPU (one iteration per launch, particle / RNG state through global
     // memory, one xform per 256-thread workgroup, shuffle-buffer gather / scatter: flame.cpp:252-280, :317-325 driving

@@ -176,6 +176,8 @@ struct rfk_iter_params_host {  // must match rfk_iter_params in chaos_kernels.cu
     unsigned int deal_seed;
     int hammersley_bits;
     float hammersley_inv_max;
+    const unsigned int* hot_map;
+    int hot_tiles_x;
 };
 
 struct rfk_pass_params_host {  // must match rfk_pass_params in chaos_kernels.cuh
@@ -212,8 +214,15 @@ struct flame_device {
     unsigned int deal_counter = 0x5EED0001u;
     std::uint64_t binned_reported = 0;
     bool warmed = false;
+    // hot map (kernel option l2_hints)
+    float* hot_sums = nullptr;
+    unsigned int* hot_scratch = nullptr;
+    unsigned int* hot_bitmap = nullptr;
+    std::size_t hot_capacity_tiles = 0;
+    int hot_W = 0, hot_H = 0, hot_tiles_x = 0;  // dimensions the current map was built for; 0 = no map
 
     ~flame_device() {
+        cudaFree(hot_sums); cudaFree(hot_scratch); cudaFree(hot_bitmap);
         if (module) driver().ModuleUnload(module);
         cudaFree(particles); cudaFree(swap); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
         cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
@@ -240,6 +249,7 @@ void flame::rebuild_cuda_source() {
     s += "#define RFK_WARP_AGGREGATE " + std::to_string(options_.warp_aggregate ? 1 : 0) + "\n";
     s += "#define RFK_DETERMINISTIC " + std::to_string(options_.deterministic ? 1 : 0) + "\n";
     s += "#define RFK_COUNT_XFORMS " + std::to_string(options_.count_xforms ? 1 : 0) + "\n";
+    s += "#define RFK_L2_HINTS " + std::to_string(options_.l2_hints ? 1 : 0) + "\n";
     if (options_.min_blocks > 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(options_.min_blocks) + ")\n";
     else s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK)\n";
     s += embedded::device_prelude;
@@ -577,6 +587,10 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
     p.bins = reinterpret_cast<float4*>(bins);
     p.num_iter = num_iter;
     p.first_run = 0;
+    if (options_.l2_hints && d.hot_W == (int)W && d.hot_H == (int)H) {
+        p.hot_map = d.hot_bitmap;
+        p.hot_tiles_x = d.hot_tiles_x;
+    }
 
     if (options_.deterministic) {
         if (d.fixed_len != W * H) {
@@ -593,6 +607,60 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         kernels::fixed_to_float(d.fixed_bins, p.bins, W * H, g_sim.stream);
         count_launch(1);
     }
+}
+
+flame::hot_map_info flame::build_hot_map(const float* bins, std::size_t bins_len, std::size_t bins_width, std::uint64_t budget_bytes) {
+    if (!bins || bins_width == 0 || bins_len < bins_width) throw std::invalid_argument("build_hot_map: bad bins buffer");
+    ensure_buffers(*this);
+    flame_device& d = *device_;
+    const std::size_t W = bins_width, H = bins_len / bins_width;
+    if (W >= (1u << 24) || H >= (1u << 24) || W * H > 0x7fffffffull) throw std::invalid_argument("build_hot_map: histogram too large");
+    if (budget_bytes == 0) {
+        int dev = 0, l2 = 0;
+        cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+        cuda_check(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev), "query L2 size");
+        budget_bytes = (std::uint64_t)l2 / 2;
+    }
+    const int T = kernels::HOT_MAP_TILE;
+    hot_map_info info;
+    info.tiles_x = (int)((W + T - 1) / T);
+    info.tiles_y = (int)((H + T - 1) / T);
+    info.budget_bytes = budget_bytes;
+    const std::size_t n_tiles = (std::size_t)info.tiles_x * info.tiles_y;
+    if (n_tiles > d.hot_capacity_tiles) {
+        cudaFree(d.hot_sums); cudaFree(d.hot_bitmap); d.hot_sums = nullptr; d.hot_bitmap = nullptr; d.hot_capacity_tiles = 0;
+        cuda_check(cudaMalloc(&d.hot_sums, n_tiles * sizeof(float)), "cudaMalloc(hot map tile sums)");
+        cuda_check(cudaMalloc(&d.hot_bitmap, ((n_tiles + 31) / 32) * sizeof(unsigned int)), "cudaMalloc(hot map)");
+        d.hot_capacity_tiles = n_tiles;
+    }
+    if (!d.hot_scratch) cuda_check(cudaMalloc(&d.hot_scratch, kernels::HOT_MAP_SCRATCH_WORDS * sizeof(unsigned int)), "cudaMalloc(hot map scratch)");
+    const std::uint64_t budget_tiles = budget_bytes / ((std::uint64_t)T * T * sizeof(float4));
+    kernels::build_hot_map(reinterpret_cast<const float4*>(bins), (int)W, (int)H, (unsigned int)std::min<std::uint64_t>(budget_tiles, 0xffffffffull),
+                           d.hot_sums, d.hot_scratch, d.hot_bitmap, g_sim.stream);
+    count_launch(3);
+    unsigned int tail[2] = {0, 0};
+    cuda_check(cudaMemcpyAsync(tail, d.hot_scratch + kernels::HOT_MAP_BUCKETS, sizeof(tail), cudaMemcpyDeviceToHost, g_sim.stream), "read hot map summary");
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "build_hot_map");
+    info.threshold_bucket = tail[0];
+    info.hot_tiles = tail[1];
+    d.hot_W = (int)W; d.hot_H = (int)H; d.hot_tiles_x = info.tiles_x;
+    return info;
+}
+
+void flame::clear_hot_map() {
+    if (device_) { device_->hot_W = device_->hot_H = device_->hot_tiles_x = 0; }
+}
+
+std::vector<std::uint32_t> flame::copy_hot_map() {
+    std::vector<std::uint32_t> out;
+    if (!device_ || device_->hot_W == 0) return out;
+    flame_device& d = *device_;
+    const int T = kernels::HOT_MAP_TILE;
+    const std::size_t n_tiles = (std::size_t)d.hot_tiles_x * ((d.hot_H + T - 1) / T);
+    out.resize((n_tiles + 31) / 32);
+    cuda_check(cudaMemcpyAsync(out.data(), d.hot_bitmap, out.size() * sizeof(std::uint32_t), cudaMemcpyDeviceToHost, g_sim.stream), "copy hot map");
+    cuda_check(cudaStreamSynchronize(g_sim.stream), "copy hot map");
+    return out;
 }
 
 std::uint64_t flame::binned_total() {

@@ -98,6 +98,46 @@ __global__ void fixed_to_float_kernel(const unsigned long long* __restrict__ fix
     bins[i] = b;
 }
 
+// ---- hot map (see static_kernels.cuh) ---------------------------------------------------------------------------------
+// Density buckets: the upper 13 bits of the binary32 pattern of a non-negative float, i.e. 16 buckets per octave.
+__device__ __forceinline__ unsigned int hot_bucket(float v) { return v > 0.0f ? (__float_as_uint(v) >> 19) : 0u; }
+
+// one warp per tile: sum of the density channel over its 16 x 16 bins, and the population of its bucket
+__global__ void hot_tile_sums_kernel(const float4* __restrict__ bins, int W, int H, int tiles_x, int n_tiles, float* __restrict__ sums, unsigned int* counts) {
+    const int tile = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
+    const int row = (tile / tiles_x) * HOT_MAP_TILE + (lane >> 1), col0 = (tile % tiles_x) * HOT_MAP_TILE + (lane & 1) * 8;
+    float sum = 0.0f;
+    if (row < H)
+        for (int k = 0; k < 8; k++)
+            if (col0 + k < W) sum += __ldg(&bins[(size_t)row * W + col0 + k].w);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+        sums[tile] = sum;
+        atomicAdd(&counts[hot_bucket(sum)], 1u);
+    }
+}
+
+// densest buckets first until the budget is spent: tiles whose bucket is ABOVE the threshold are hot
+__global__ void hot_threshold_kernel(unsigned int* counts, unsigned int budget_tiles) {
+    unsigned int acc = 0;
+    int b = HOT_MAP_BUCKETS - 1;
+    for (; b >= 1; b--) {
+        if (acc + counts[b] > budget_tiles) break;
+        acc += counts[b];
+    }
+    counts[HOT_MAP_BUCKETS] = (unsigned int)b;  // 0 when every non-empty tile fits
+    counts[HOT_MAP_BUCKETS + 1] = acc;
+}
+
+__global__ void hot_bitmap_kernel(const float* __restrict__ sums, int n_tiles, const unsigned int* __restrict__ counts, unsigned int* __restrict__ bitmap) {
+    const int tile = (int)(blockIdx.x * (size_t)blockDim.x + threadIdx.x);
+    const unsigned int threshold = counts[HOT_MAP_BUCKETS];
+    const bool hot = tile < n_tiles && hot_bucket(sums[tile]) > threshold;
+    const unsigned int word = __ballot_sync(0xffffffffu, hot);
+    if ((threadIdx.x & 31) == 0 && tile < ((n_tiles + 31) & ~31)) bitmap[tile >> 5] = word;
+}
+
 __global__ void downsample2x_kernel(const float4* __restrict__ in, float4* __restrict__ out, int W, int H) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -413,6 +453,16 @@ void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, dens
     if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, rad_bytes, s>>>(bins, out_f4, out_rgba8, p);
     else if (do_density) density_tonemap_kernel<true, false><<<grid, block, rad_bytes, s>>>(bins, out_f4, out_rgba8, p);
     else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
+}
+
+void build_hot_map(const float4* bins, int W, int H, unsigned int budget_tiles, float* tile_sums, unsigned int* scratch, unsigned int* bitmap, cudaStream_t s) {
+    const int tiles_x = (W + HOT_MAP_TILE - 1) / HOT_MAP_TILE, tiles_y = (H + HOT_MAP_TILE - 1) / HOT_MAP_TILE, n_tiles = tiles_x * tiles_y;
+    if (n_tiles <= 0) return;
+    cudaMemsetAsync(scratch, 0, HOT_MAP_SCRATCH_WORDS * sizeof(unsigned int), s);
+    hot_tile_sums_kernel<<<(unsigned)(((size_t)n_tiles * 32 + 255) / 256), 256, 0, s>>>(bins, W, H, tiles_x, n_tiles, tile_sums, scratch);
+    hot_threshold_kernel<<<1, 1, 0, s>>>(scratch, budget_tiles);
+    const int padded = (n_tiles + 31) & ~31;
+    hot_bitmap_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, s>>>(tile_sums, n_tiles, scratch, bitmap);
 }
 
 void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s) {

@@ -34,6 +34,17 @@ struct density_params {
 // (tonemap.glsl:18-39) in one pass. out_f4 / out_rgba8 may each be null.
 void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, density_params p, bool do_density, bool do_tonemap, cudaStream_t s);
 
+// Hot map of a histogram much larger than L2 (kernel option l2_hints; DESIGN.md "hot map"): the histogram is cut into
+// 16 x 16-bin tiles (4 KB each), every tile's accumulated density is summed, and the densest tiles — as many as fit in
+// `budget_tiles` — get their bit set in `bitmap` (one bit per tile, row-major, tiles_x = ceil(W/16) tiles per row).
+// `tile_sums` holds ceil(W/16) * ceil(H/16) floats, `scratch` HOT_MAP_SCRATCH_WORDS words, `bitmap` one word per 32 tiles.
+// After the call scratch[HOT_MAP_BUCKETS] is the density-bucket threshold and scratch[HOT_MAP_BUCKETS + 1] the number of
+// hot tiles.
+constexpr int HOT_MAP_TILE = 16;
+constexpr int HOT_MAP_BUCKETS = 4096;
+constexpr int HOT_MAP_SCRATCH_WORDS = HOT_MAP_BUCKETS + 2;
+void build_hot_map(const float4* bins, int W, int H, unsigned int budget_tiles, float* tile_sums, unsigned int* scratch, unsigned int* bitmap, cudaStream_t s);
+
 // deterministic mode: bins += fixed * 2^-24, one thread per bin
 void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s);
 

@@ -19,7 +19,7 @@ def test_abi_exports_every_declared_symbol(rfk):
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export " + name
     assert declared == set(rfk.SIGNATURES), declared ^ set(rfk.SIGNATURES)
-    assert lib.rfk_abi_version() == 1
+    assert lib.rfk_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", rfk.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     exported = set(re.findall(r"\bT (rfk_[a-z0-9_]+)", out))
     assert declared <= exported

@@ -373,3 +373,35 @@ def test_render_frame_supersampled(gpu_ready, rfk, flame):
     assert abs(float(plain[..., :3].mean()) - float(ss_img[..., :3].mean())) < 0.08
     corr = np.corrcoef(plain[..., :3].ravel(), ss_img[..., :3].ravel())[0, 1]
     assert corr > 0.6, corr
+
+
+def test_l2_hints_change_nothing_but_the_cache_policy(gpu_ready, rfk, flame):
+    """kernel option l2_hints + hot map: the density channel sums opacities of 1, exact in binary32 whatever the order, so it
+    must be bit-identical with and without the hints; the map marks the densest tiles and stays inside its budget."""
+    W, H, P, TS = 2048, 1152, 256 * 64, 16
+    hists = []
+    for hints in (0, 1):
+        flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1, l2_hints=hints)
+        rfk.set_sim_parameters(P, TS, 64, seed=9)
+        flame.warmup(16, TSS)
+        buf = rfk.DeviceBuffer(W * H * 16)
+        buf.zero_out()
+        n = flame.draw_to_bins(buf.ptr, W * H, W, 32)
+        if hints:
+            budget = 2 * 1024 * 1024  # 512 tiles of 4 KB
+            info = flame.build_hot_map(buf.ptr, W * H, W, budget)
+            assert (info.tiles_x, info.tiles_y) == (W // 16, H // 16) and 0 < info.hot_tiles <= budget // 4096
+            first = buf.download(np.float32, (H, W, 4))
+            tiles = first[..., 3].reshape(H // 16, 16, W // 16, 16).sum(axis=(1, 3))
+            hot = flame.hot_map()[: tiles.size].reshape(tiles.shape)
+            assert hot.sum() == info.hot_tiles
+            assert tiles[hot].min() >= tiles[~hot].max() * 0.999  # the densest tiles, bucket granularity aside
+            assert tiles[hot].sum() / tiles.sum() > 0.3           # a flame's hits are concentrated
+        n += flame.draw_to_bins(buf.ptr, W * H, W, 32)
+        hists.append((buf.download(np.float32, (H, W, 4)), n))
+        buf.free()
+    flame.clear_hot_map()
+    flame.set_options(l2_hints=0)
+    (a, na), (b, nb) = hists
+    assert na == nb and np.array_equal(a[..., 3], b[..., 3])
+    assert np.allclose(a[..., :3], b[..., :3], rtol=1e-5, atol=1e-5)

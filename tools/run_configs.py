@@ -23,6 +23,7 @@ GENOME = os.path.join(FIX, "electricsheep.247.11256.flam3")
 VARIATIONS = os.path.join(FIX, "variations.yaml")
 P, TS = 2048 * 1024, 512
 TSS = 1.2 / 60.0
+HOT_BUDGET = 0
 
 
 def timed(fn):
@@ -35,7 +36,7 @@ def timed(fn):
     return out, e0.elapsed_time(e1)
 
 
-def render_still(flame, W, H, target_binned=None, draw_calls=None, rank=0, world=1, downsample=False):
+def render_still(flame, W, H, target_binned=None, draw_calls=None, rank=0, world=1, downsample=False, hot_map=False):
     """warmup + draw + (reduce) + DE/tonemap; returns stage times in ms"""
     n = W * H
     bins = torch.zeros(n * 4, dtype=torch.float32, device="cuda")
@@ -46,6 +47,8 @@ def render_still(flame, W, H, target_binned=None, draw_calls=None, rank=0, world
         while (draw_calls is None or calls < draw_calls) and (target_binned is None or binned < target_binned):
             flame.draw_to_bins_async(bins.data_ptr(), n, W, 128)
             calls += 1
+            if hot_map and calls == 1:  # kernel option l2_hints: classify the tiles once the first call has landed (inside the timed region)
+                flame.build_hot_map(bins.data_ptr(), n, W, HOT_BUDGET)
             if target_binned is not None:
                 binned = flame.binned_total()
         return flame.binned_total(), calls
@@ -70,7 +73,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="+", type=int)
     ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--hot-budget-mb", type=float, default=0.0, help="config 3: hot-map budget (0 = the library default, half the L2)")
+    ap.add_argument("--no-l2-hints", action="store_true", help="config 3 without the hot map / evict-first reductions")
     args = ap.parse_args()
+    global HOT_BUDGET
+    HOT_BUDGET = int(args.hot_budget_mb * 1e6)
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     r.lib().rfk_set_device(local)
@@ -102,8 +109,13 @@ def main():
             ms = res["ms_warmup"] + res["ms_draw"] + res["ms_reduce"] + res["ms_post"]
             emit(2, "shipped genome, 3840x2160, 2000 spp, DE + tonemap (4K frame ms = ms_total)", res, res["iterations"] * world, ms)
         elif cfg == 3:
+            flame.set_options(l2_hints=0 if args.no_l2_hints else 1)
             render_still(flame, 15360, 8640, draw_calls=1)
-            res = render_still(flame, 15360, 8640, draw_calls=256, rank=rank, world=world, downsample=True)
+            res = render_still(flame, 15360, 8640, draw_calls=256, rank=rank, world=world, downsample=True, hot_map=not args.no_l2_hints)
+            res["l2_hints"] = 0 if args.no_l2_hints else 1
+            res["hot_budget_mb"] = args.hot_budget_mb
+            flame.set_options(l2_hints=0)
+            flame.clear_hot_map()
             ms = res["ms_warmup"] + res["ms_draw"] + res["ms_reduce"] + res["ms_post"]
             emit(3, "shipped genome, 15360x8640 histogram (2x supersampled 7680x4320), 256 draw calls per GPU, NCCL reduce, DE + tonemap + 2x2 box", res, res["iterations"] * world, ms)
         elif cfg == 4:

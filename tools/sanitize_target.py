@@ -31,6 +31,17 @@ for kw in modes:
     print("mode", kw, "binned", stats.binned)
 flame.set_options(**defaults)
 
+# L2 hints: hot map built from a first call, then a hinted call
+flame.set_options(l2_hints=1)
+flame.warmup(3, 1.2 / 60)
+hb = r.DeviceBuffer(W * H * 16)
+hb.zero_out()
+flame.draw_to_bins(hb.ptr, W * H, W, 2)
+info = flame.build_hot_map(hb.ptr, W * H, W, 64 * 1024)
+print("hot map", info.tiles_x, info.tiles_y, info.hot_tiles, "binned with hints", flame.draw_to_bins(hb.ptr, W * H, W, 2), int(flame.hot_map().sum()))
+flame.clear_hot_map()
+flame.set_options(**defaults)
+
 img, stats = flame.render_frame(W, H, max_draw_calls=1, drawing_passes=4, warmup_passes=3, supersample=2, filter_radius=0.75)
 print("supersampled frame", img.shape, stats.binned)
 
