@@ -10,6 +10,8 @@ together use every variation the reference's table compiles:
 
   reference_host_<name>.json.gz   load_flame only: parsed fields, buffer map, the fp[] upload, the generated
                                   get_xform_id() / dispatch() text, digest of the complete iterate shader, screen-space affine
+  reference_histogram_electricsheep.npz   (only with --histogram, ~2 minutes) two independent runs of warmup(16) + 64 draw passes
+                                  with 131072 particles into a 320 x 180 histogram: density channel, colour sums, binned counts
   reference_device_<name>.npz     set_sim_parameters + load_flame + warmup(2) + draw_to_bins(3 passes) + the density /
                                   tonemap sequence of main.cpp:490-535: the shuffle tables and per-pass shuffle ids the
                                   reference drew, RNG states, particle buffers, fp_inflated, bins, binned counter, density
@@ -108,6 +110,24 @@ def device_fixture(h, name, xml, full):
     print("device", name, "binned", r1["binned"], "finite particles %.4f" % np.isfinite(part_d).all(axis=1).mean())
 
 
+def histogram_fixture(h, genome_path):
+    """Two independent full-length runs (the reference reseeds tables and ids from the clock / random_device every time) at
+    the configuration of tests/test_render_gpu.py::oracle_hist: what the production kernel is compared with statistically."""
+    W, H, Ph, TSh, passes = 320, 180, 256 * 16 * 32, 32, 64
+    runs = []
+    for k in range(2):
+        r = h.run(genome_path, Ph, TSh, 64, 16, TSS, W, H, passes)
+        bins = h.buffer("bins", np.float32, (H, W, 4))
+        runs.append((bins, r["binned"]))
+        print("histogram run", k, "binned", r["binned"])
+    (b1, n1), (b2, n2) = runs
+    assert b1[..., 3].max() < 65536 and np.array_equal(b1[..., 3], np.rint(b1[..., 3]))
+    np.savez_compressed(os.path.join(HERE, "reference_histogram_electricsheep.npz"),
+                        density=b1[..., 3].astype(np.uint16), rgb_sum=b1[..., :3].sum(axis=(0, 1), dtype=np.float64), binned=np.int64(n1),
+                        density_second_run=b2[..., 3].astype(np.uint16), binned_second_run=np.int64(n2),
+                        config=np.array([W, H, Ph, TSh, passes, 16], dtype=np.int64))
+
+
 def main():
     import ref_host
     import refrakt_oracle as ro
@@ -122,6 +142,8 @@ def main():
     for name, xml in cases.items():
         host_fixture(h, name, xml)
         device_fixture(h, name, xml if name == "electricsheep" else with_full_palette(xml, shipped), full=(name == "electricsheep"))
+    if "--histogram" in sys.argv:
+        histogram_fixture(h, GENOME)
     host_fixture(h, "bad_attribute", cases["chunk0"].replace('opacity="1"/>', 'opacity="1" nonsense="3"/>', 1))
 
 

@@ -225,3 +225,48 @@ def test_product_density_and_tonemap_vs_the_reference_shaders(gpu_ready, rfk, co
     assert np.abs(u8[lit].astype(int) - oracle_mod.to_rgba8(ref_tm[lit]).astype(int)).max() <= 1
     _, fused_out, fused_u8 = _run_post(rfk, np.ascontiguousarray(g["bins"]), p, fused=True)
     assert np.array_equal(fused_out, out) and np.array_equal(fused_u8, u8)
+
+
+def _pooled(d, k=4):
+    H, W = d.shape
+    return d[: H // k * k, : W // k * k].astype(np.float64).reshape(H // k, k, W // k, k).sum(axis=(1, 3))
+
+
+def _norm_l1(a, b):
+    return 0.5 * np.abs(a / a.sum() - b / b.sum()).sum()
+
+
+def test_oracle_histogram_matches_the_reference_statistically(oracle):
+    """independent random streams: the oracle's histogram is as close to the reference's as two reference runs are to each other"""
+    z = np.load(os.path.join(GOLDEN, "reference_histogram_electricsheep.npz"))
+    W, H, P, TS, passes, warm = (int(v) for v in z["config"])
+    oracle.set_threads(oracle.max_threads())
+    oracle.set_sim_parameters(P, TS, 64, shuffle_seed=77, rng_seed=0, pass_seed=78)
+    oracle.warmup(warm, 1.2 / 60)
+    bins = np.zeros((H, W, 4), dtype=np.float32)
+    binned = oracle.draw_to_bins(bins, W, passes)
+    ref, ref2 = z["density"].astype(np.float64), z["density_second_run"].astype(np.float64)
+    self_l1 = _norm_l1(_pooled(ref), _pooled(ref2))
+    assert _norm_l1(_pooled(bins[..., 3]), _pooled(ref)) <= max(0.02, 1.5 * self_l1)
+    assert abs(binned - int(z["binned"])) <= 0.002 * int(z["binned"]) + 3 * abs(int(z["binned"]) - int(z["binned_second_run"]))
+    assert np.abs(bins[..., :3].sum(axis=(0, 1)) / bins[..., 3].sum() - z["rgb_sum"] / ref.sum()).max() <= 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [dict(), dict(warp_aggregate=1), dict(per_lane_xform=1), dict(deterministic=1)])
+def test_production_kernel_histogram_matches_the_reference_statistically(gpu_ready, rfk, flame, mode):
+    """rfk_warm + rfk_draw (the shipped path, own random streams and re-deal) against a histogram the reference's own code
+    produced with the same particle count, passes and dimensions: pooled normalised L1 within 1.5x the distance between two
+    reference runs, in-bounds fraction, mean colour"""
+    from test_render_gpu import _gpu_histogram
+    z = np.load(os.path.join(GOLDEN, "reference_histogram_electricsheep.npz"))
+    W, H, P, TS, passes, warm = (int(v) for v in z["config"])
+    assert warm == 16  # _gpu_histogram warms up with 16 passes
+    bins, binned = _gpu_histogram(rfk, flame, W, H, P, TS, passes, 1, seed=4242, **mode)
+    ref, ref2 = z["density"].astype(np.float64), z["density_second_run"].astype(np.float64)
+    self_l1 = _norm_l1(_pooled(ref), _pooled(ref2))
+    l1 = _norm_l1(_pooled(bins[..., 3]), _pooled(ref))
+    assert l1 <= max(0.02, 1.5 * self_l1), (l1, self_l1)
+    n_ref = int(z["binned"])
+    assert abs(binned - n_ref) <= 0.002 * n_ref + 3 * abs(n_ref - int(z["binned_second_run"])), (binned, n_ref)
+    assert np.abs(bins[..., :3].sum(axis=(0, 1)) / bins[..., 3].sum() - z["rgb_sum"] / ref.sum()).max() <= 0.01
