@@ -44,8 +44,8 @@ UNIT = "iterations/s"
 WORKLOAD = "configs[1]: electricsheep.247.11256 still, 3840x2160, 2000 samples/pixel, P=2097152, TS=512, warmup 16 + draw 128 passes/call, density estimation + tonemap"
 # From the committed ncu captures of rfk_draw (profiles/r01*_rfk_draw*.md): DRAM bytes of one launch
 # (dram__bytes_read.sum + dram__bytes_write.sum) and executed warp instructions per warp-iteration.
-DRAW_DRAM_TRAFFIC_BYTES = 432.5e6
-DRAW_WARP_INST_PER_WARP_ITERATION = 211.3
+DRAW_DRAM_TRAFFIC_BYTES = 435.7e6
+DRAW_WARP_INST_PER_WARP_ITERATION = 190.8
 
 
 def roofline_probes():

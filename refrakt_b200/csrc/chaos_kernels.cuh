@@ -266,10 +266,12 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
                 atomicAdd(b + 2, (unsigned long long)__float2ll_rn(col.z * RFK_FIXED_SCALE));
                 atomicAdd(b + 3, (unsigned long long)__float2ll_rn(fw * RFK_FIXED_SCALE));
   #elif RFK_L2_HINTS
-                if (hot) rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);
-                else rfk_red_add_v4_evict_first(p.bins + idx, col.x, col.y, col.z, fw, evict_first_policy);
+                col.w = fw;  // the palette row lands in the vector operand of the reduction; only the density lane is patched
+                if (hot) rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, col.w);
+                else rfk_red_add_v4_evict_first(p.bins + idx, col.x, col.y, col.z, col.w, evict_first_policy);
   #else
-                rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);
+                col.w = fw;  // the palette row lands in the vector operand of the reduction; only the density lane is patched
+                rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, col.w);
   #endif
                 binned++;
             }

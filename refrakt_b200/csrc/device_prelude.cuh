@@ -83,6 +83,25 @@ static constexpr float EPS = (1e-10f);
 //   (absolute error 1.3e-7), vec2 / scalar through one reciprocal.
 // RFK_MATH_MODE 2: --use_fast_math (SFU intrinsics with no range reduction; outside the parity contract).
 #if RFK_MATH_MODE == 1
+// Mode 1 is compiled with --use_fast_math for ONE of its effects: `a / b` becomes div.approx (one MUFU.RCP and a
+// multiply, 2 ulp for |b| in [2^-126, 2^126], 0 beyond) instead of the range-scaled div.full of --prec-div=false
+// (four more instructions per quotient). The flag would also turn expf / logf / tanf / powf into their SFU
+// intrinsics, which are outside the 1e-5 contract, so mode 1 calls the libdevice entry points by name.
+extern "C" __device__ float __nv_expf(float);
+extern "C" __device__ float __nv_logf(float);
+extern "C" __device__ float __nv_tanf(float);
+extern "C" __device__ float __nv_powf(float, float);
+#define RFK_EXPF(x) __nv_expf(x)
+#define RFK_LOGF(x) __nv_logf(x)
+#define RFK_TANF(x) __nv_tanf(x)
+#define RFK_POWF(x, y) __nv_powf(x, y)
+#else
+#define RFK_EXPF(x) ::expf(x)
+#define RFK_LOGF(x) ::logf(x)
+#define RFK_TANF(x) ::tanf(x)
+#define RFK_POWF(x, y) ::powf(x, y)
+#endif
+#if RFK_MATH_MODE == 1
 // x - rint(x / 2pi) * 2pi with 2pi split in two binary32 constants: the product k * hi is exact inside the
 // fma, so the reduced argument is good to ~3e-6 rad even at |x| = 1e9 (where binary32 itself resolves 64 rad);
 // no large-argument fallback branch is needed. Inf / NaN give NaN like sinf / cosf.
@@ -100,7 +119,7 @@ __device__ __forceinline__ void rfk_sincos(float v, float* s, float* c) {
 }
 __device__ __forceinline__ float pow(float a, float b) {
     if (a >= 0.0f && ::fabsf(b) <= 16.0f) return ::exp2f(b * ::__log2f(a));
-    return ::powf(a, b);
+    return RFK_POWF(a, b);
 }
 // atan2 from a degree-15 odd polynomial on [0, 1] (least-squares fit on Chebyshev nodes; absolute error 1.3e-7 in
 // binary32 Horner form) plus octant fix-ups: ~20 instructions instead of libdevice's ~35. atan2(0, 0) = 0.
@@ -132,11 +151,11 @@ __device__ __forceinline__ float pow(float a, float b) { return ::powf(a, b); }
 #endif
 #if RFK_MATH_MODE == 1
 // tan stays on libdevice: next to its poles the SFU sine / cosine quotient loses too much (popcorn, sin(tan(3y)))
-__device__ __forceinline__ float tan(float v) { return ::tanf(v); }
+__device__ __forceinline__ float tan(float v) { return RFK_TANF(v); }
 // sinh / cosh from one exponential and its reciprocal: relative error ~|x| * 1e-7 for |x| >= 1, absolute error ~1e-7
 // below (sinh(x) loses relative accuracy to cancellation there; the parity contract is absolute for small outputs)
 __device__ __forceinline__ void rfk_sinhcosh(float v, float* sh, float* ch) {
-    float e = ::expf(v);
+    float e = RFK_EXPF(v);
     float inv = 1.0f / e;
     *sh = ::fabsf(v) < 0.125f ? v * ::fmaf(v * v, 0.16666667f, 1.0f) : 0.5f * (e - inv);
     *ch = 0.5f * (e + inv);
@@ -149,8 +168,8 @@ __device__ __forceinline__ float sinh(float v) { return ::sinhf(v); }
 __device__ __forceinline__ float cosh(float v) { return ::coshf(v); }
 __device__ __forceinline__ void rfk_sinhcosh(float v, float* sh, float* ch) { *sh = ::sinhf(v); *ch = ::coshf(v); }
 #endif
-__device__ __forceinline__ float exp(float v) { return ::expf(v); }
-__device__ __forceinline__ float log(float v) { return ::logf(v); }
+__device__ __forceinline__ float exp(float v) { return RFK_EXPF(v); }
+__device__ __forceinline__ float log(float v) { return RFK_LOGF(v); }
 __device__ __forceinline__ float sqrt(float v) { return ::sqrtf(v); }
 __device__ __forceinline__ float atan(float a) { return ::atanf(a); }
 __device__ __forceinline__ float acos(float v) { return ::acosf(v); }
@@ -192,7 +211,7 @@ __device__ __forceinline__ vec2 sinhcosh(float v) {
     return vec2(s, c);
 }
 __device__ __forceinline__ float mod2(float x, float y) { return x - y * ::truncf(x / y); }
-__device__ __forceinline__ float log10(float x) { return ::logf(x) * 0.434294481903251827651128918916f; }
+__device__ __forceinline__ float log10(float x) { return RFK_LOGF(x) * 0.434294481903251827651128918916f; }
 __device__ __forceinline__ bool badval(float x) { return (x != x) || (x > 1e10f) || (x < -1e10f); }
 
 // random.glsl:29-41. The device generator returns `a` after the update (the host

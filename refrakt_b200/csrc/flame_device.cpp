@@ -134,7 +134,8 @@ std::vector<char> compile_cubin(const std::string& source, const kernel_options&
         throw std::runtime_error("nvrtcCreateProgram failed");
     std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--generate-line-info"};
     if (opt.math_mode == 2) opts.push_back("--use_fast_math");
-    if (opt.math_mode == 1) { opts.push_back("--prec-div=false"); opts.push_back("--prec-sqrt=false"); opts.push_back("--ftz=true"); }
+    // mode 1: --use_fast_math for its div.approx lowering of `/`; the prelude keeps expf / logf / tanf / powf on libdevice by name
+    if (opt.math_mode == 1) opts.push_back("--use_fast_math");
     if (!opt.fmad) opts.push_back("--fmad=false");
     nvrtcResult res = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
     std::size_t log_size = 0;
