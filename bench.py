@@ -170,6 +170,8 @@ def main():
     torch.cuda.set_device(local_rank)
     r.lib().rfk_set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     compiler = r.FlameCompiler(VARIATIONS)
