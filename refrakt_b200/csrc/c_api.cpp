@@ -350,6 +350,7 @@ int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
     k.l2_hints = i->l2_hints ? 1 : 0;
     if (k.block_width != 128 && k.block_width != 256 && k.block_width != 512) return fail(RFK_E_INVALID, "block_width must be 128, 256 or 512");
     if (k.deal_period < 1) return fail(RFK_E_INVALID, "deal_period must be >= 1");
+    if (k.min_blocks < -1 || k.min_blocks * k.block_width > 2048) return fail(RFK_E_INVALID, "min_blocks must be -1, 0 or at most 2048 / block_width");
     if (k.math_mode < 0 || k.math_mode > 2) return fail(RFK_E_INVALID, "math_mode must be 0, 1 or 2");
     if (k.count_xforms && F(f)->xforms.size() > 62) return fail(RFK_E_INVALID, "count_xforms supports at most 62 xforms");
     if (!F(f)->set_options(k)) return fail(RFK_E_CUDA, flame::last_error());

@@ -251,7 +251,10 @@ void flame::rebuild_cuda_source() {
     s += "#define RFK_DETERMINISTIC " + std::to_string(options_.deterministic ? 1 : 0) + "\n";
     s += "#define RFK_COUNT_XFORMS " + std::to_string(options_.count_xforms ? 1 : 0) + "\n";
     s += "#define RFK_L2_HINTS " + std::to_string(options_.l2_hints ? 1 : 0) + "\n";
+    // min_blocks 0 = aim at 1536 resident threads per SM (40 registers per thread): measured best or within 1 % of best on the
+    // shipped, stress and six synthetic genomes (tools/probe_min_blocks.py); -1 = leave the register budget to the compiler
     if (options_.min_blocks > 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(options_.min_blocks) + ")\n";
+    else if (options_.min_blocks == 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(1536 / options_.block_width) + ")\n";
     else s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK)\n";
     s += embedded::device_prelude;
     s += "\nnamespace rfk_glsl {\n#define randf() rfk_randf(rs)\n";

@@ -34,6 +34,7 @@ def main():
     r.set_sim_parameters(P, TS, 1024)
     variants = [
         ("default", {}),
+        ("min_blocks_compiler_choice", dict(min_blocks=-1)),
         ("min_blocks4", dict(min_blocks=4)),
         ("min_blocks6", dict(min_blocks=6)),
         ("min_blocks7", dict(min_blocks=7)),
