@@ -56,6 +56,10 @@ int rfk_device_zero(void* ptr_dev, size_t bytes);                         /* sto
 int rfk_memcpy_to_device(void* dst_dev, const void* src, size_t bytes);   /* storage_buffer::update_all, :43-45 */
 int rfk_memcpy_to_host(void* dst, const void* src_dev, size_t bytes);     /* storage_buffer::get_*, :24-37 */
 uint64_t rfk_kernel_launch_count(void); /* kernels launched by this library since load */
+/* Frees the device memory the library itself owns: the RNG states and shuffle tables of rfk_set_sim_parameters (class
+ * statics in the reference, src/flame.hpp:150-156) and the frame buffers rfk_render_frame keeps between calls (4.5 GB after
+ * one 15360 x 8640 frame). Flames stay valid; call rfk_set_sim_parameters and rfk_flame_warmup before drawing again. */
+int rfk_release_buffers(void);
 
 /* ---- global simulation parameters: flame::set_sim_parameters, src/flame.hpp:77, src/flame.cpp:105-158 ----
  * total_particles / temporal_samples must be a multiple of 256 (the reference dispatches

@@ -77,6 +77,7 @@ SIGNATURES = {
     "rfk_device_zero": (_i, [_vp, _sz]),
     "rfk_memcpy_to_device": (_i, [_vp, _vp, _sz]),
     "rfk_memcpy_to_host": (_i, [_vp, _vp, _sz]),
+    "rfk_release_buffers": (C.c_int, []),
     "rfk_kernel_launch_count": (C.c_uint64, []),
     "rfk_set_sim_parameters": (_i, [_sz, _sz, _sz, C.c_uint64]),
     "rfk_compiler_create": (_vp, [_cp]),
@@ -201,6 +202,11 @@ def set_shuffle_buffers(tables: Optional[np.ndarray] = None, count: int = 64, se
         tables = np.ascontiguousarray(tables, dtype=np.uint32)
         count = tables.shape[0]
     _check(lib().rfk_set_shuffle_buffers(None if tables is None else _ptr(tables, C.c_uint32), count, seed), "set_shuffle_buffers")
+
+
+def release_buffers():
+    """frees the library-owned device memory (simulation state, cached frame buffers); set_sim_parameters + warmup again before drawing"""
+    _check(lib().rfk_release_buffers(), "release_buffers")
 
 
 def kernel_launch_count() -> int:

@@ -560,6 +560,29 @@ int rfk_copy_rng_states(uint32_t* out, size_t first, size_t count) {
 }
 
 // ---- end to end ----
+namespace {
+// library-owned frame buffers of rfk_render_frame: kept between calls and regrown only when the frame gets larger
+struct frame_buffers {
+    float4* bins = nullptr; float4* image = nullptr; uchar4* rgba8 = nullptr; float4* small = nullptr;
+    size_t bins_n = 0, image_n = 0, rgba8_n = 0, small_n = 0;
+    cudaEvent_t ev[5] = {};
+    void release() {
+        cudaFree(bins); cudaFree(image); cudaFree(rgba8); cudaFree(small);
+        bins = image = small = nullptr; rgba8 = nullptr;
+        bins_n = image_n = rgba8_n = small_n = 0;
+    }
+};
+frame_buffers g_frame;
+}  // namespace
+
+int rfk_release_buffers(void) {
+    return guarded([&]() -> int {
+        g_frame.release();
+        release_sim_buffers();
+        return RFK_OK;
+    });
+}
+
 int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_out, float* image_out, rfk_frame_stats* stats) {
     return guarded([&]() -> int {
         if (!f || !req || (!rgba8_out && !image_out)) throw std::invalid_argument("rfk_render_frame: null argument");
@@ -572,13 +595,7 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         const size_t W = OW * ss, H = OH * ss, n = W * H;              // histogram (and full-resolution image)
         cudaStream_t s = current_stream();
 
-        // library-owned frame buffers: kept between calls and regrown only when the frame gets larger
-        struct buffers {
-            float4* bins = nullptr; float4* image = nullptr; uchar4* rgba8 = nullptr; float4* small = nullptr;
-            size_t bins_n = 0, image_n = 0, rgba8_n = 0, small_n = 0;
-            cudaEvent_t ev[5] = {};
-        };
-        static buffers b;
+        frame_buffers& b = g_frame;
         auto grow = [](auto*& ptr, size_t& have, size_t want, const char* what) {
             if (have >= want) return;
             cudaFree(ptr); ptr = nullptr; have = 0;

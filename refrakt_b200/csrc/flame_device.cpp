@@ -339,6 +339,20 @@ void flame::set_sim_parameters(std::size_t total_particles, std::size_t temporal
         if (f->device()) f->device()->sim_generation = ~0ull;
 }
 
+// Releases the class-static simulation buffers (the reference frees them when set_sim_parameters replaces them,
+// flame.cpp:107-149, and at process exit); live flames must call set_sim_parameters + warmup again.
+void release_sim_buffers() {
+    if (g_sim.stream) cudaStreamSynchronize(g_sim.stream);
+    cudaFree(g_sim.rng); g_sim.rng = nullptr;
+    cudaFree(g_sim.shuffle); g_sim.shuffle = nullptr; g_sim.shuffle_tables = 0;
+    cudaFree(g_sim.samples); g_sim.samples = nullptr;
+    g_sim.total_particles = g_sim.temporal_samples = g_sim.shuffle_count = 0;
+    g_sim.samples_generation = g_sim.shuffle_generation = ~0ull;
+    g_sim.generation++;
+    for (auto* f : g_active_flames)
+        if (f->device()) f->device()->sim_generation = ~0ull;
+}
+
 std::size_t sim_total_particles() { return g_sim.total_particles; }
 std::size_t sim_temporal_samples() { return g_sim.temporal_samples; }
 const uint4* sim_rng_states() { return g_sim.rng; }

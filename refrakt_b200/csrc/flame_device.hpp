@@ -15,6 +15,7 @@ void set_current_stream(cudaStream_t s);
 std::uint64_t kernel_launch_count();  // kernels launched by this library since load
 void count_launch(unsigned n);
 
+void release_sim_buffers();
 std::size_t sim_total_particles();
 std::size_t sim_temporal_samples();
 const uint4* sim_rng_states();

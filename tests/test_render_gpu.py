@@ -405,3 +405,22 @@ def test_l2_hints_change_nothing_but_the_cache_policy(gpu_ready, rfk, flame):
     (a, na), (b, nb) = hists
     assert na == nb and np.array_equal(a[..., 3], b[..., 3])
     assert np.allclose(a[..., :3], b[..., :3], rtol=1e-5, atol=1e-5)
+
+
+def test_release_buffers_frees_and_the_library_recovers(gpu_ready, rfk, flame):
+    """rfk_release_buffers: device memory owned by the library goes back to the driver; drawing without a new
+    set_sim_parameters fails loudly; after it, the same frame renders again"""
+    import torch
+    W, H = 1024, 576
+    rfk.set_sim_parameters(256 * 64, 16, 64, seed=3)
+    flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0, block_width=256, deal_period=1, l2_hints=0)
+    img1, st1 = flame.render_frame(W, H, max_draw_calls=1, drawing_passes=16)
+    free_before, _ = torch.cuda.mem_get_info()
+    rfk.release_buffers()
+    free_after, _ = torch.cuda.mem_get_info()
+    assert free_after - free_before >= W * H * 16  # at least the histogram came back
+    with pytest.raises(rfk.RefraktError):
+        flame.warmup(4, TSS)
+    rfk.set_sim_parameters(256 * 64, 16, 64, seed=3)
+    img2, st2 = flame.render_frame(W, H, max_draw_calls=1, drawing_passes=16)
+    assert st2.binned == st1.binned and np.abs(img1.astype(int) - img2.astype(int)).max() <= 1
