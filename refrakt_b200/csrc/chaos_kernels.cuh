@@ -153,15 +153,6 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     float x, y, c;
     __syncthreads();
 
-#if !RFK_PER_LANE_XFORM && RFK_NUM_XFORMS <= 33
-    // xform_select.tpl.glsl as one vote: lane i keeps the i-th running sum (same binary32 additions, same
-    // order as the template), the first lane whose sum >= ratio names the xform, the last xform is the fall-through
-    float cum = fp[rfk_weight_slot[0]];
-    for (int i = 1; i < RFK_NUM_XFORMS - 1; i++)
-        if (i <= (int)lane) cum += fp[rfk_weight_slot[i]];
-    const bool cum_valid = (int)lane < RFK_NUM_XFORMS - 1;
-#endif
-
     unsigned int binned = 0;
     int parity = 0;
 #if RFK_L2_HINTS
@@ -170,23 +161,19 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #endif
 
     // flame.glsl:51-53: the first thread of a workgroup burns one randf() per pass to pick the group's xform. Here
-    // every lane burns one every 32 iterations and iteration i uses lane (i mod 32)'s draw: the same number of extra
-    // draws per warp, all lanes active when they are made.
-    float pick_pool = 0.0f;
+    // every lane burns one every 32 iterations and runs it through get_xform_id() — the generated if-chain of
+    // xform_select.tpl.glsl, same binary32 additions in the same order — and iteration i uses lane (i mod 32)'s pick:
+    // the same number of extra draws per warp, all lanes active when they are made, one shuffle per iteration.
+    int pick_pool = 0;
     int pick_count = 0;
     auto pick_xform = [&]() -> int {
 #if RFK_PER_LANE_XFORM
         return get_xform_id(rfk_randf(rs));
 #else
-        if ((pick_count & 31) == 0) pick_pool = rfk_randf(rs);
-        const float u = __shfl_sync(0xffffffffu, pick_pool, pick_count & 31);
+        if ((pick_count & 31) == 0) pick_pool = get_xform_id(rfk_randf(rs));
+        const int xid = __shfl_sync(0xffffffffu, pick_pool, pick_count & 31);
         pick_count++;
-  #if RFK_NUM_XFORMS <= 33
-        unsigned int vote = __ballot_sync(0xffffffffu, cum_valid && cum >= u);
-        return vote ? __ffs(vote) - 1 : RFK_NUM_XFORMS - 1;
-  #else
-        return get_xform_id(u);
-  #endif
+        return xid;
 #endif
     };
     unsigned int deal_key = rfk_hash32(p.deal_seed ^ (blockIdx.x * 0x9E3779B9u));
@@ -387,24 +374,7 @@ extern "C" __global__ void rfk_select_xform(int n, const float* __restrict__ rat
     for (int k = threadIdx.x; k < RFK_TOTAL_PARAMS; k += blockDim.x) rfk_glsl::fp[k] = fp[k];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const float my_ratio = ratio[i < n ? i : n - 1];  // no early exit: the vote below needs whole warps
-    // both forms of the selection must agree: the template's if-chain and the hot kernels' vote
-    int chain = get_xform_id(my_ratio);
-    int result = chain;
-#if RFK_NUM_XFORMS <= 33
-    const int lane = threadIdx.x & 31;
-    float cum = rfk_glsl::fp[rfk_weight_slot[0]];
-    for (int k = 1; k < RFK_NUM_XFORMS - 1; k++)
-        if (k <= lane) cum += rfk_glsl::fp[rfk_weight_slot[k]];
-    int voted = RFK_NUM_XFORMS - 1;
-    for (int src = 0; src < 32; src++) {  // every lane's ratio in turn, so that each vote is warp-uniform
-        float u = __shfl_sync(0xffffffffu, my_ratio, src);
-        unsigned int vote = __ballot_sync(0xffffffffu, lane < RFK_NUM_XFORMS - 1 && cum >= u);
-        if (src == lane) voted = vote ? __ffs(vote) - 1 : RFK_NUM_XFORMS - 1;
-    }
-    if (voted != chain) result = -1000 - voted;
-#endif
-    if (i < n) out[i] = result;
+    if (i < n) out[i] = get_xform_id(ratio[i]);  // the generated if-chain, as the hot kernels call it
 }
 
 struct rfk_bucket_params { float ss_affine[6]; int bin_w, bin_h; };

@@ -258,7 +258,7 @@ def _linear_genome(n, final=False):
 
 @pytest.mark.parametrize("n,final", [(1, False), (2, True), (33, False), (34, True), (40, False)])
 def test_xform_count_edge_cases(gpu_ready, rfk, compiler, vt, oracle_mod, n, final):
-    """1 xform (the select template has no fall-through return), exactly 33 (largest warp-vote case), 34 and 40
+    """1 xform (the select template has no fall-through return), exactly 33, 34 and 40 xforms (the selection if-chain grows with the count)
     (if-chain fallback), with and without a final xform: selection bit-exact, single step within 1e-5, histogram mass conserved"""
     xml = _linear_genome(n, final)
     f = rfk.Flame.load_flame_string(xml, compiler)
