@@ -134,7 +134,7 @@ def run_reference_arm(args, rank, world):
     base = cpu_reference_run(args.steps, args.warmup)
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": base["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, "note": "CPU port of the reference's GLSL path (oracle/); the reference needs OpenGL + 12 fetched dependencies and cannot be built or run in this image"},
+            "data": "synthetic", "impl": "reference", "config": {"workload": WORKLOAD, "note": "CPU port of the reference's GLSL path (oracle/, OpenMP): bit-identical in output to the reference's own host code + shaders run over the software GL of oracle/softgl/, which is single-threaded and needs the reference's files, so it cannot be timed on this box (DESIGN.md sections 6-7)"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
