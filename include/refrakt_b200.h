@@ -147,7 +147,7 @@ typedef struct rfk_kernel_options {
     int32_t warp_aggregate; /* 1: match_any de-duplication of same-bin updates inside a warp */
     int32_t deterministic;  /* 1: fixed-point integer accumulation, bit-identical histograms run to run */
     int32_t count_xforms;   /* 1: count xform selections (rfk_flame_xform_counts) */
-    int32_t min_blocks;     /* __launch_bounds__ minBlocksPerSM; 0 = 1536 / block_width (default), -1 = leave it to the compiler */
+    int32_t min_blocks;     /* __launch_bounds__ minBlocksPerSM; 0 = automatic (2048 / block_width, or 1536 / block_width when that spills), -1 = leave it to the compiler */
     int32_t block_width;    /* threads per CTA = particles per re-deal pool: 128, 256 (default, the reference's workgroup) or 512 */
     int32_t deal_period;    /* re-deal the CTA's particles across warps every n-th iteration; default 1 */
     int32_t l2_hints;       /* histograms several times larger than L2: reductions outside the hot map (rfk_flame_build_hot_map)

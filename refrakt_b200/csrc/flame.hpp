@@ -63,7 +63,7 @@ struct kernel_options {
     bool warp_aggregate = false;  // match_any de-duplication of same-bin updates inside a warp
     bool deterministic = false;   // fixed-point (integer) accumulation: bit-identical histograms
     bool count_xforms = false;    // per-xform selection counters
-    int min_blocks = 0;           // __launch_bounds__ second argument; 0 = 1536 / block_width (default), -1 = compiler's choice
+    int min_blocks = 0;           // __launch_bounds__ second argument; 0 = automatic (2048 / block_width unless that spills, else 1536 / block_width), -1 = compiler's choice
     int block_width = 256;        // threads per CTA = particles per re-deal pool (128, 256 or 512; the reference's workgroup is 256)
     int deal_period = 1;          // re-deal particles across warps every n-th iteration
     int l2_hints = 0;             // histograms much larger than L2: evict-first reductions outside the hot map

@@ -39,6 +39,7 @@ struct driver_api {
     CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
     CUresult (*ModuleUnload)(CUmodule) = nullptr;
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
@@ -63,6 +64,7 @@ const driver_api& driver() {
         get("cuModuleLoadData", a.ModuleLoadData);
         get("cuModuleUnload", a.ModuleUnload);
         get("cuModuleGetFunction", a.ModuleGetFunction);
+        get("cuModuleGetGlobal", a.ModuleGetGlobal);
         get("cuLaunchKernel", a.LaunchKernel);
         get("cuFuncGetAttribute", a.FuncGetAttribute);
         get("cuOccupancyMaxActiveBlocksPerMultiprocessor", a.OccupancyMaxActiveBlocksPerMultiprocessor);
@@ -98,7 +100,7 @@ sim_state g_sim;
 std::set<flame*> g_active_flames;  // src/flame.hpp:173
 
 std::mutex g_cache_mutex;
-std::unordered_map<std::string, std::vector<char>> g_cubin_cache;  // source text -> cubin
+std::unordered_map<std::string, std::pair<std::vector<char>, std::string>> g_cubin_cache;  // source text + options -> cubin, compile log
 
 }  // namespace
 
@@ -110,11 +112,15 @@ void count_launch(unsigned n) { g_sim.launches += n; }
 // ---------------------------------------------------------------------------------
 // NVRTC
 // ---------------------------------------------------------------------------------
-std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out) {
+std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out, int auto_min_blocks) {
+    const std::string key = source + "#" + std::to_string(opt.math_mode) + (opt.fmad ? "" : "#M") + "#" + std::to_string(auto_min_blocks);
     {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
-        auto it = g_cubin_cache.find(source + "#" + std::to_string(opt.math_mode) + (opt.fmad ? "" : "#M"));
-        if (it != g_cubin_cache.end()) return it->second;
+        auto it = g_cubin_cache.find(key);
+        if (it != g_cubin_cache.end()) {
+            if (log_out) *log_out = it->second.second;
+            return it->second.first;
+        }
     }
     // RFK_SOURCE_DUMP_DIR: keep the generated translation unit on disk under the name the line info refers to
     // (lets `ncu --import-source on` and cuobjdump map SASS back to the generated code)
@@ -132,7 +138,10 @@ std::vector<char> compile_cubin(const std::string& source, const kernel_options&
     nvrtcProgram prog;
     if (nvrtcCreateProgram(&prog, source.c_str(), unit_name.c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
         throw std::runtime_error("nvrtcCreateProgram failed");
-    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--generate-line-info"};
+    // --ptxas-options=-v: the log carries registers and spill bytes per kernel (read by flame::cubin's launch-bounds choice)
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "--generate-line-info", "--ptxas-options=-v"};
+    const std::string auto_define = "-DRFK_AUTO_MIN_BLOCKS=" + std::to_string(auto_min_blocks);
+    if (auto_min_blocks > 0) opts.push_back(auto_define.c_str());
     if (opt.math_mode == 2) opts.push_back("--use_fast_math");
     // mode 1: --use_fast_math for its div.approx lowering of `/`; the prelude keeps expf / logf / tanf / powf on libdevice by name
     if (opt.math_mode == 1) opts.push_back("--use_fast_math");
@@ -153,7 +162,7 @@ std::vector<char> compile_cubin(const std::string& source, const kernel_options&
     nvrtcGetCUBIN(prog, cubin.data());
     nvrtcDestroyProgram(&prog);
     std::lock_guard<std::mutex> lock(g_cache_mutex);
-    g_cubin_cache[source + "#" + std::to_string(opt.math_mode) + (opt.fmad ? "" : "#M")] = cubin;
+    g_cubin_cache[key] = {cubin, log};
     return cubin;
 }
 
@@ -201,6 +210,8 @@ struct rfk_pass_params_host {  // must match rfk_pass_params in chaos_kernels.cu
 struct flame_device {
     CUmodule module = nullptr;
     CUfunction warm = nullptr, draw = nullptr, single_step = nullptr, select_xform = nullptr, bucket_index = nullptr, reference_pass = nullptr;
+    float* cfp = nullptr;         // the module's __constant__ rfk_cfp[]: parameter slots that do not depend on the temporal sample
+    std::size_t cfp_floats = 0;
     float4* particles = nullptr;
     float4* swap = nullptr;  // reference pass mode: swap_buffer_
     float* fp = nullptr;
@@ -251,10 +262,10 @@ void flame::rebuild_cuda_source() {
     s += "#define RFK_DETERMINISTIC " + std::to_string(options_.deterministic ? 1 : 0) + "\n";
     s += "#define RFK_COUNT_XFORMS " + std::to_string(options_.count_xforms ? 1 : 0) + "\n";
     s += "#define RFK_L2_HINTS " + std::to_string(options_.l2_hints ? 1 : 0) + "\n";
-    // min_blocks 0 = aim at 1536 resident threads per SM (40 registers per thread): measured best or within 1 % of best on the
-    // shipped, stress and six synthetic genomes (tools/probe_min_blocks.py); -1 = leave the register budget to the compiler
+    // min_blocks 0 = automatic (flame::cubin): 2048 resident threads per SM (32 registers) unless that spills, else 1536
+    // (40 registers) — tools/probe_min_blocks.py; -1 = leave the register budget to the compiler
     if (options_.min_blocks > 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(options_.min_blocks) + ")\n";
-    else if (options_.min_blocks == 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(1536 / options_.block_width) + ")\n";
+    else if (options_.min_blocks == 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, RFK_AUTO_MIN_BLOCKS)\n";  // chosen by flame::cubin()
     else s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK)\n";
     s += embedded::device_prelude;
     s += "\nnamespace rfk_glsl {\n#define randf() rfk_randf(rs)\n";
@@ -307,8 +318,33 @@ bool flame::set_options(const kernel_options& opt) {
     return true;
 }
 
+// bytes ptxas reports as spilled by the two hot kernels ("N bytes spill stores" after "Compiling entry function 'rfk_draw'")
+static std::size_t spilled_bytes(const std::string& log) {
+    std::size_t total = 0;
+    for (const char* kernel : {"'rfk_draw'", "'rfk_warm'"}) {
+        std::size_t at = log.find(std::string("Compiling entry function ") + kernel);
+        if (at == std::string::npos) continue;
+        std::size_t end = log.find("Compiling entry function", at + 10);
+        std::size_t sp = log.find("bytes spill stores", at);
+        if (sp == std::string::npos || (end != std::string::npos && sp > end)) continue;
+        std::size_t b = log.rfind(',', sp);
+        if (b == std::string::npos) continue;
+        total += std::strtoull(log.c_str() + b + 1, nullptr, 10);
+    }
+    return total;
+}
+
 const std::vector<char>& flame::cubin() {
-    if (cubin_.empty()) cubin_ = compile_cubin(cuda_source_, options_, nullptr);
+    if (!cubin_.empty()) return cubin_;
+    if (options_.min_blocks != 0) {
+        cubin_ = compile_cubin(cuda_source_, options_, nullptr, 0);
+        return cubin_;
+    }
+    // automatic launch bounds: full occupancy (2048 threads per SM, 32 registers per thread) when the genome's kernels fit
+    // without spilling, else 1536 threads per SM (40 registers)
+    std::string log;
+    std::vector<char> tight = compile_cubin(cuda_source_, options_, &log, 2048 / options_.block_width);
+    cubin_ = spilled_bytes(log) == 0 ? std::move(tight) : compile_cubin(cuda_source_, options_, nullptr, 1536 / options_.block_width);
     return cubin_;
 }
 
@@ -375,6 +411,11 @@ static void ensure_module(flame& f) {
     cu_check(api.ModuleGetFunction(&d.select_xform, d.module, "rfk_select_xform"), "rfk_select_xform");
     cu_check(api.ModuleGetFunction(&d.bucket_index, d.module, "rfk_bucket_index"), "rfk_bucket_index");
     cu_check(api.ModuleGetFunction(&d.reference_pass, d.module, "rfk_reference_pass"), "rfk_reference_pass");
+    CUdeviceptr cfp = 0;
+    std::size_t cfp_bytes = 0;
+    cu_check(api.ModuleGetGlobal(&cfp, &cfp_bytes, d.module, "rfk_cfp"), "rfk_cfp");
+    d.cfp = reinterpret_cast<float*>(cfp);
+    d.cfp_floats = cfp_bytes / sizeof(float);
 }
 
 static void ensure_buffers(flame& f) {
@@ -422,6 +463,12 @@ static void launch(CUfunction fn, unsigned grid, unsigned block, void** args) {
     count_launch(1);
 }
 
+// the kernels read every slot that is the same for all temporal samples from constant memory (rfk_cfp, see compile_flame_cuda)
+static void upload_constant_params(flame_device& d, const float* fp) {
+    if (!d.cfp || !d.cfp_floats) return;
+    cuda_check(cudaMemcpyAsync(d.cfp, fp, std::min<std::size_t>(d.cfp_floats, flame::PARAM_BUFFER) * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
+}
+
 static rfk_iter_params_host base_params(flame& f) {
     flame_device& d = *f.device();
     rfk_iter_params_host p{};
@@ -449,6 +496,7 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
 
     auto buf = copy_flame_data_to_buffer();
     cuda_check(cudaMemcpyAsync(d.fp, buf.data(), PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
+    upload_constant_params(d, buf.data());
     cuda_check(cudaMemcpyAsync(d.palette, palette.data(), 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
     cuda_check(cudaMemsetAsync(d.counters, 0, 64 * sizeof(unsigned long long), g_sim.stream), "clear counters");
     // the host arrays above are stack / member storage: finish the copies before returning control
@@ -524,6 +572,7 @@ void flame::reference_warmup(std::size_t num_passes, float tss_width, const std:
     needs_update_ = false;
     auto buf = copy_flame_data_to_buffer();
     cuda_check(cudaMemcpyAsync(d.fp, buf.data(), PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
+    upload_constant_params(d, buf.data());
     cuda_check(cudaMemcpyAsync(d.palette, palette.data(), 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
     cuda_check(cudaMemsetAsync(d.counters, 0, 64 * sizeof(unsigned long long), g_sim.stream), "clear counters");
     kernels::animate(d.fp, d.fp_inflated, buffer_map_.size, (int)g_sim.temporal_samples, tss_width, d.anim, d.anim_count, g_sim.stream);
@@ -721,12 +770,14 @@ void flame_single_step(flame& f, int n, const float* xyz, const int* xid, std::u
     std::array<float, flame::PARAM_BUFFER> own;
     if (!fp) { own = f.copy_flame_data_to_buffer(); fp = own.data(); }
     d_fp.upload(fp);
+    upload_constant_params(*f.device(), fp);
     float4* outp = reinterpret_cast<float4*>(d_out.p);
     uint4* rngp = reinterpret_cast<uint4*>(d_rng.p);
     void* args[] = {&n, &d_xyz.p, &d_xid.p, &rngp, &d_fp.p, &first_run, &outp};
     launch(f.device()->single_step, (unsigned)((n + 127) / 128), 128, args);
     cuda_check(cudaStreamSynchronize(g_sim.stream), "rfk_single_step");
     d_out.download(out); d_rng.download(rng);
+    if (fp != own.data()) { own = f.copy_flame_data_to_buffer(); upload_constant_params(*f.device(), own.data()); }  // the flame's own values again
 }
 
 void flame_select_xform(flame& f, int n, const float* ratio, const float* fp, int* out) {
@@ -737,10 +788,12 @@ void flame_select_xform(flame& f, int n, const float* ratio, const float* fp, in
     std::array<float, flame::PARAM_BUFFER> own;
     if (!fp) { own = f.copy_flame_data_to_buffer(); fp = own.data(); }
     d_fp.upload(fp);
+    upload_constant_params(*f.device(), fp);
     void* args[] = {&n, &d_ratio.p, &d_fp.p, &d_out.p};
     launch(f.device()->select_xform, (unsigned)((n + 127) / 128), 128, args);
     cuda_check(cudaStreamSynchronize(g_sim.stream), "rfk_select_xform");
     d_out.download(out);
+    if (fp != own.data()) { own = f.copy_flame_data_to_buffer(); upload_constant_params(*f.device(), own.data()); }
 }
 
 void flame_bucket_index(flame& f, int n, const float* xyzw, const float ss_affine[6], int W, int H, int* idx_out, int* pal_out) {

@@ -23,7 +23,7 @@ uint4* sim_rng_states_mutable();
 std::size_t sim_shuffle_count();
 
 // NVRTC: CUDA source -> sm_100a cubin (no GPU needed). Throws with the compile log on failure.
-std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out);
+std::vector<char> compile_cubin(const std::string& source, const kernel_options& opt, std::string* log_out, int auto_min_blocks = 0);
 
 // test hooks: run the generated device functions on host-supplied vectors
 void flame_single_step(flame& f, int n, const float* xyz, const int* xid, std::uint32_t* rng, const float* fp, int first_run, float* out);

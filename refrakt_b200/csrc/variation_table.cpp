@@ -1,6 +1,7 @@
 #include "variation_table.hpp"
 
 #include <algorithm>
+#include <set>
 #include <stack>
 #include <stdexcept>
 
@@ -10,6 +11,7 @@
 namespace rfk {
 
 namespace {
+inline bool ident_char(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_'; }
 
 std::string slot_str(int slot) { return "fp[" + std::to_string(slot) + "]"; }  // variation_table.cpp:21
 
@@ -176,12 +178,34 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
         for (std::size_t i = 0; i < buf_map.xforms.size(); i++) slots += (i ? ", " : "") + std::to_string(buf_map.xforms[i].weight);
         if (buf_map.xforms.empty()) slots += "0";
         slots += "};\n";
-        return slots + xid_func + "\n" + disp_func + "\n";
+        // Parameter slots that are the same for every temporal sample — all but the four rotated affine coefficients of each
+        // xform (animate.tpl.glsl:42-49) — are read from constant memory: `fp[N]` becomes `rfk_cfp[N]`, which the compiler
+        // folds into the arithmetic instruction as a constant-bank operand instead of a shared-memory load. The host uploads
+        // the array at warmup (it holds the same binary32 values as fp_inflated).
+        std::set<int> per_sample;
+        auto mark = [&](const xform_slots& m) { for (int a = 0; a < 4; a++) per_sample.insert(m.affine[a]); };
+        for (auto& m : buf_map.xforms) mark(m);
+        if (buf_map.final_xform) mark(*buf_map.final_xform);
+        std::string body = xid_func + "\n" + disp_func + "\n", out;
+        out.reserve(body.size() + 1024);
+        for (std::size_t i = 0; i < body.size();) {
+            if (body.compare(i, 3, "fp[") == 0 && (i == 0 || !ident_char(body[i - 1]))) {
+                std::size_t j = i + 3, k = j;
+                while (k < body.size() && body[k] >= '0' && body[k] <= '9') k++;
+                if (k > j && k < body.size() && body[k] == ']' && !per_sample.count(std::stoi(body.substr(j, k - j)))) {
+                    out += "rfk_cfp[";
+                    i = j;
+                    continue;
+                }
+            }
+            out += body[i++];
+        }
+        // C linkage: the host finds it with cuModuleGetGlobal("rfk_cfp") although the text sits inside namespace rfk_glsl
+        return slots + "extern \"C\" { __constant__ float rfk_cfp[" + std::to_string(std::max(1, buf_map.size)) + "]; }\n" + out;
     }
     return xid_func + disp_func;
 }
 
-inline bool ident_char(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_'; }
 inline bool digit(char c) { return c >= '0' && c <= '9'; }
 
 }  // namespace

@@ -117,7 +117,7 @@ def test_generated_glsl_is_the_reference_text(flame, oracle):
 def test_cuda_dialect_rewrites(flame):
     c = flame.cuda_source()
     assert "2.0f * PI" in c and ".yx()" in c and "fp[163] == 0)" in c
-    assert re.search(r"float _rf0 = randf\(\), _rf1 = randf\(\), _rf2 = randf\(\), _rf3 = randf\(\), _rf4 = randf\(\); vec2 result = fp\[7\] \*\(_rf0 \+ _rf1 \+ _rf2 \+ _rf3 - 2.0f\) \* sincos\(_rf4 \* 2.0f \* PI\)\.yx\(\);", c)
+    assert re.search(r"float _rf0 = randf\(\), _rf1 = randf\(\), _rf2 = randf\(\), _rf3 = randf\(\), _rf4 = randf\(\); vec2 result = rfk_cfp\[7\] \*\(_rf0 \+ _rf1 \+ _rf2 \+ _rf3 - 2.0f\) \* sincos\(_rf4 \* 2.0f \* PI\)\.yx\(\);", c)
     assert "((first_run)? randf(): v.z)" in c  # a conditional draw stays conditional
     assert not re.search(r"(?<![\w.])\d+\.\d+(?![\dfeE])", c.split("namespace rfk_glsl {\n#define randf()")[1].split("#undef randf")[0])
     assert "__constant__ int rfk_weight_slot[10] = {0, 13, 30, 43, 59, 76, 92, 110, 125, 141};" in c
