@@ -69,22 +69,37 @@ __device__ __forceinline__ float2 rfk_sample_point(unsigned int i, int bits, flo
 // coords = ivec2(floor(pos)) lies in [0, W) x [0, H) exactly when 0 <= pos.x < W and 0 <= pos.y < H (W, H integers),
 // so the test runs on the un-floored position (NaN fails every comparison: non-finite positions never bin, where the
 // reference leaves ivec2(floor(NaN)) undefined), and inside the bounds truncation equals floor.
+// The truncation itself is an addition of 2^23 rounded toward zero: for 0 <= p < 2^23 the sum's mantissa field is
+// floor(p) exactly, so its bit pattern is 0x4B000000 + floor(p) — an FADD.RZ on the FMA pipe instead of an F2I on the
+// quarter-rate conversion unit, which is the busiest pipe of the kernel. The two biases fold into one constant of the
+// index arithmetic (mod 2^32; W, H < 2^23 is checked by the host).
+__device__ __forceinline__ bool rfk_bin_test(float x, float y, float w, const float* ss, float Wf, float Hf, float& px, float& py) {
+    px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
+    py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
+    return px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f;
+}
+__device__ __forceinline__ unsigned int rfk_trunc_biased(float p) { return __float_as_uint(__fadd_rz(p, 8388608.0f)); }  // 0x4B000000 + floor(p)
+__device__ __forceinline__ int rfk_bin_of(float px, float py, int W, int H) {
+    // (H - 1 - cy) * W + cx with cy = ty - B, cx = tx - B, B = 0x4B000000
+    const unsigned int B = 0x4B000000u;
+    const unsigned int base = (unsigned int)(H - 1) * (unsigned int)W + B * (unsigned int)W - B;  // uniform
+    return (int)(base - rfk_trunc_biased(py) * (unsigned int)W + rfk_trunc_biased(px));
+}
 __device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const float* ss, int W, int H, float Wf, float Hf) {
-    const float px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
-    const float py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
-    if (!(px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f)) return -1;
-    return (H - __float2int_rz(py) - 1) * W + __float2int_rz(px);
+    float px, py;
+    if (!rfk_bin_test(x, y, w, ss, Wf, Hf, px, py)) return -1;
+    return rfk_bin_of(px, py, W, H);
 }
 
 #if RFK_L2_HINTS
 // The same test and index as rfk_bin_index, also returning the bit of the bin's 16 x 16 tile in the hot map.
 __device__ __forceinline__ int rfk_bin_index_hot(float x, float y, float w, const float* ss, int W, int H, float Wf, float Hf,
                                                  const unsigned int* hot_map, int tiles_x, bool& hot) {
-    const float px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
-    const float py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
+    float px, py;
     hot = true;
-    if (!(px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f)) return -1;
-    const int row = H - __float2int_rz(py) - 1, col = __float2int_rz(px);
+    if (!rfk_bin_test(x, y, w, ss, Wf, Hf, px, py)) return -1;
+    const unsigned int B = 0x4B000000u;
+    const int row = H - 1 - (int)(rfk_trunc_biased(py) - B), col = (int)(rfk_trunc_biased(px) - B);
     if (hot_map) {
         const unsigned int tile = (unsigned int)(row >> 4) * (unsigned int)tiles_x + (unsigned int)(col >> 4);
         hot = (__ldg(hot_map + (tile >> 5)) >> (tile & 31u)) & 1u;
@@ -132,7 +147,9 @@ __device__ __forceinline__ float4 rfk_reduce_peers(unsigned int mask, unsigned i
 template <bool DRAW>
 __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     __shared__ float4 pal[256];
-    __shared__ float ex[2][3][RFK_BLOCK];  // re-deal exchange: [double buffer][x, y, colour][slot]
+    // re-deal exchange, double buffered: (x, y, colour, -) in one 128-bit slot — one STS.128 and one LDS.128 per iteration;
+    // conflict-free for any odd multiplier (the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups)
+    __shared__ float4 ex[2][RFK_BLOCK];
 #if RFK_COUNT_XFORMS
     __shared__ unsigned int xcount[RFK_NUM_XFORMS + 1];
 #endif
@@ -180,11 +197,10 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     auto deal = [&](int) {
         deal_key = deal_key * 1664525u + 1013904223u;  // CTA-uniform
         unsigned int j = rfk_deal_slot(tid, deal_key);
-        float* out = &ex[parity][0][j];
-        out[0] = x; out[RFK_BLOCK] = y; out[2 * RFK_BLOCK] = c;
+        ex[parity][j] = make_float4(x, y, c, 0.0f);
         __syncthreads();
-        const float* in = &ex[parity][0][tid];
-        x = in[0]; y = in[RFK_BLOCK]; c = in[2 * RFK_BLOCK];
+        const float4 in = ex[parity][tid];
+        x = in.x; y = in.y; c = in.z;
         parity ^= 1;
     };
 
@@ -230,12 +246,15 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #if RFK_L2_HINTS
             bool hot;
             const int idx = rfk_bin_index_hot(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf, p.hot_map, p.hot_tiles_x, hot);
+            const bool in_bounds = idx >= 0;
 #else
-            const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf);
+            float px, py;
+            const bool in_bounds = rfk_bin_test(fx, fy, fw, p.ss_affine, p.bin_wf, p.bin_hf, px, py);
+            const int idx = rfk_bin_of(px, py, p.bin_w, p.bin_h);  // meaningful only where in_bounds
 #endif
 #if RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC
-            const unsigned int hit = __ballot_sync(0xffffffffu, idx >= 0);
-            if (idx >= 0) {
+            const unsigned int hit = __ballot_sync(0xffffffffu, in_bounds);
+            if (in_bounds) {
                 float4 col = pal[rfk_palette_index(fc)];
                 float4 v = make_float4(col.x, col.y, col.z, fw);
                 unsigned int peers = __match_any_sync(hit, idx);
@@ -244,8 +263,18 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
                 binned++;
             }
 #else
-            if (idx >= 0) {
+            if (in_bounds) {
+  #if !RFK_DETERMINISTIC && !RFK_L2_HINTS
+                // The palette row is read as 64 + 32 bits into the first three registers of the reduction's operand quad;
+                // the density lane is already there. (One LDS.128 would overwrite that lane and cost three MOVs to regroup;
+                // `volatile` keeps ptxas from fusing the two loads back into one.)
+                const unsigned int prow = (unsigned int)__cvta_generic_to_shared(&pal[rfk_palette_index(fc)]);
+                float4 col;
+                asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(col.x), "=f"(col.y) : "r"(prow));
+                asm volatile("ld.volatile.shared.f32 %0, [%1+8];" : "=f"(col.z) : "r"(prow));
+  #else
                 float4 col = pal[rfk_palette_index(fc)];
+  #endif
   #if RFK_DETERMINISTIC
                 unsigned long long* b = p.fixed_bins + (size_t)idx * 4;
                 atomicAdd(b + 0, (unsigned long long)__float2ll_rn(col.x * RFK_FIXED_SCALE));

@@ -69,6 +69,13 @@ __device__ __forceinline__ vec2 operator/(vec2 a, float s) { float inv = 1.0f / 
 __device__ __forceinline__ vec2 operator/(float s, vec2 a) { return vec2(s / a.x, s / a.y); }
 #endif
 #undef RFK_BINOP
+// `e / rfk_cfp[n]` in the generated text (a divisor that is one warp-uniform parameter slot) is emitted as
+// `e RFK_DIVC(n, r)`: the quotient in mode 0, a product with the reciprocal the host stored in rfk_cfp[r] otherwise.
+#if RFK_MATH_MODE == 0
+#define RFK_DIVC(n, r) / rfk_cfp[n]
+#else
+#define RFK_DIVC(n, r) * rfk_cfp[r]
+#endif
 __device__ __forceinline__ vec2 operator-(vec2 a) { return vec2(-a.x, -a.y); }
 
 // math.glsl:1-4

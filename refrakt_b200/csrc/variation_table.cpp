@@ -12,6 +12,7 @@ namespace rfk {
 
 namespace {
 inline bool ident_char(char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_'; }
+inline bool digit_char(char c) { return c >= '0' && c <= '9'; }
 
 std::string slot_str(int slot) { return "fp[" + std::to_string(slot) + "]"; }  // variation_table.cpp:21
 
@@ -200,8 +201,33 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
             }
             out += body[i++];
         }
+        // A division whose divisor is one of those slots, `e / rfk_cfp[N]`, multiplies by the slot's reciprocal instead:
+        // the host stores 1 / fp[N] (IEEE) in the upper half of the array, rfk_cfp[size + N], so the MUFU.RCP the kernel
+        // would issue for a warp-uniform value on every iteration is gone. `/` and `*` associate alike, so the rewrite
+        // is local to the token pair. Math mode 0 (IEEE division) keeps the division (RFK_DIVC in device_prelude.cuh).
+        const int size = std::max(1, buf_map.size);
+        std::string folded;
+        folded.reserve(out.size() + 256);
+        for (std::size_t i = 0; i < out.size();) {
+            if (out[i] == '/' && i + 1 < out.size() && out[i + 1] != '/' && out[i + 1] != '*' && (i == 0 || out[i - 1] != '/')) {
+                std::size_t j = i + 1;
+                while (j < out.size() && (out[j] == ' ' || out[j] == '\t')) j++;
+                if (out.compare(j, 8, "rfk_cfp[") == 0) {
+                    std::size_t k = j + 8, e = k;
+                    while (e < out.size() && digit_char(out[e])) e++;
+                    // the slot must be the whole divisor: not `rfk_cfp[N].x`, not a call or index on it
+                    if (e > k && e < out.size() && out[e] == ']' && (e + 1 == out.size() || (out[e + 1] != '.' && out[e + 1] != '[' && out[e + 1] != '('))) {
+                        const int slot = std::stoi(out.substr(k, e - k));
+                        folded += " RFK_DIVC(" + std::to_string(slot) + ", " + std::to_string(size + slot) + ")";
+                        i = e + 1;
+                        continue;
+                    }
+                }
+            }
+            folded += out[i++];
+        }
         // C linkage: the host finds it with cuModuleGetGlobal("rfk_cfp") although the text sits inside namespace rfk_glsl
-        return slots + "extern \"C\" { __constant__ float rfk_cfp[" + std::to_string(std::max(1, buf_map.size)) + "]; }\n" + out;
+        return slots + "extern \"C\" { __constant__ float rfk_cfp[" + std::to_string(2 * size) + "]; }\n" + folded;
     }
     return xid_func + disp_func;
 }
