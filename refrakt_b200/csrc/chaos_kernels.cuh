@@ -74,8 +74,8 @@ __device__ __forceinline__ float2 rfk_sample_point(unsigned int i, int bits, flo
 // quarter-rate conversion unit, which is the busiest pipe of the kernel. The two biases fold into one constant of the
 // index arithmetic (mod 2^32; W, H < 2^23 is checked by the host).
 __device__ __forceinline__ bool rfk_bin_test(float x, float y, float w, const float* ss, float Wf, float Hf, float& px, float& py) {
-    px = fmaf(ss[0], x, fmaf(ss[2], y, ss[4]));
-    py = fmaf(ss[1], x, fmaf(ss[3], y, ss[5]));
+    const vec2 pos = rfk_affine(ss[0], ss[1], ss[2], ss[3], ss[4], ss[5], x, y);  // nested fma, as flame.glsl:79-80
+    px = pos.x; py = pos.y;
     return px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f;
 }
 __device__ __forceinline__ unsigned int rfk_trunc_biased(float p) { return __float_as_uint(__fadd_rz(p, 8388608.0f)); }  // 0x4B000000 + floor(p)

@@ -12,21 +12,47 @@ typedef uint4 rfk_rng;  // (a, b, c, d) = local_random_state.xyzw (random.glsl:1
 // Namespace scope, so that every fp[k] of the generated code is one LDS with an immediate offset.
 __shared__ float fp[RFK_TOTAL_PARAMS + 1];
 
+// Packed FP32 (sm_100: FFMA2 / FMUL2 / FADD2, `fma.rn.f32x2`): one instruction does the x and the y lane of a vec2
+// operation — the same FP32 rate as two scalar instructions but ONE issue slot, and the kernels are issue bound
+// (tools/ffma2_probe.cu: FFMA2 mixed with integer work runs 24 % faster than the same flops as FFMA). A scalar operand
+// is broadcast by the instruction itself (`R.F32`), so `s * v` costs no packing. Per-lane results are those of the
+// scalar IEEE operations; a product that feeds a sum is fused (vprod below), as the compiler fuses a * b + c.
+#define RFK_F2(v) make_float2((v).x, (v).y)
+struct vprod;
 struct vec2 {
     float x, y;
     vec2() = default;
     __device__ __forceinline__ vec2(float a, float b) : x(a), y(b) {}
     __device__ __forceinline__ explicit vec2(float a) : x(a), y(a) {}
+    __device__ __forceinline__ explicit vec2(float2 f) : x(f.x), y(f.y) {}
     __device__ __forceinline__ vec2 yx() const { return vec2(y, x); }
-    __device__ __forceinline__ vec2& operator+=(vec2 o) { x += o.x; y += o.y; return *this; }
+    __device__ __forceinline__ vec2& operator+=(vec2 o) { return *this = vec2(__fadd2_rn(RFK_F2(*this), RFK_F2(o))); }
     __device__ __forceinline__ vec2& operator-=(vec2 o) { x -= o.x; y -= o.y; return *this; }
-    __device__ __forceinline__ vec2& operator*=(vec2 o) { x *= o.x; y *= o.y; return *this; }
+    __device__ __forceinline__ vec2& operator*=(vec2 o) { return *this = vec2(__fmul2_rn(RFK_F2(*this), RFK_F2(o))); }
     __device__ __forceinline__ vec2& operator/=(vec2 o) { x /= o.x; y /= o.y; return *this; }
-    __device__ __forceinline__ vec2& operator+=(float s) { x += s; y += s; return *this; }
+    __device__ __forceinline__ vec2& operator+=(float s) { return *this = vec2(__fadd2_rn(RFK_F2(*this), make_float2(s, s))); }
     __device__ __forceinline__ vec2& operator-=(float s) { x -= s; y -= s; return *this; }
-    __device__ __forceinline__ vec2& operator*=(float s) { x *= s; y *= s; return *this; }
-    __device__ __forceinline__ vec2& operator/=(float s) { x /= s; y /= s; return *this; }
+    __device__ __forceinline__ vec2& operator*=(float s) { return *this = vec2(__fmul2_rn(RFK_F2(*this), make_float2(s, s))); }
+    __device__ __forceinline__ vec2& operator/=(float s);
+    __device__ __forceinline__ vec2& operator+=(const vprod& p);
+    __device__ __forceinline__ vec2& operator-=(const vprod& p);
 };
+
+// a * b not yet multiplied: converts to vec2 with one FMUL2, or is absorbed by a following sum as one FFMA2
+struct vprod {
+    vec2 a, b;
+    __device__ __forceinline__ vprod(vec2 a_, vec2 b_) : a(a_), b(b_) {}
+    __device__ __forceinline__ operator vec2() const { return vec2(__fmul2_rn(RFK_F2(a), RFK_F2(b))); }
+    __device__ __forceinline__ vec2 yx() const { return vec2(*this).yx(); }
+};
+__device__ __forceinline__ vec2 rfk_fma2(vec2 a, vec2 b, vec2 c) { return vec2(__ffma2_rn(RFK_F2(a), RFK_F2(b), RFK_F2(c))); }
+__device__ __forceinline__ vec2& vec2::operator+=(const vprod& p) { return *this = rfk_fma2(p.a, p.b, *this); }
+__device__ __forceinline__ vec2& vec2::operator-=(const vprod& p) { return *this = rfk_fma2(vec2(-p.a.x, -p.a.y), p.b, *this); }
+
+// x' = fma(a, x, fma(c, y, e)), y' = fma(b, x, fma(d, y, f)): the affine lines of the generated text, two FFMA2
+__device__ __forceinline__ vec2 rfk_affine(float a, float b, float c, float d, float e, float f, float x, float y) {
+    return rfk_fma2(vec2(a, b), vec2(x), rfk_fma2(vec2(c, d), vec2(y), vec2(e, f)));
+}
 
 struct ivec2 {
     int x, y;
@@ -53,22 +79,51 @@ struct vec4 {
     __device__ __forceinline__ vec4(vec2 a, float c, float d) : x(a.x), y(a.y), z(c), w(d) {}
 };
 
-#define RFK_BINOP(op)                                                                                       \
-    __device__ __forceinline__ vec2 operator op(vec2 a, vec2 b) { return vec2(a.x op b.x, a.y op b.y); }   \
-    __device__ __forceinline__ vec2 operator op(vec2 a, float s) { return vec2(a.x op s, a.y op s); }      \
-    __device__ __forceinline__ vec2 operator op(float s, vec2 a) { return vec2(s op a.x, s op a.y); }
-RFK_BINOP(+)
-RFK_BINOP(-)
-RFK_BINOP(*)
+__device__ __forceinline__ vec2 operator-(vec2 a) { return vec2(-a.x, -a.y); }
+__device__ __forceinline__ vprod operator-(vprod p) { return vprod(-p.a, p.b); }
+// sums
+__device__ __forceinline__ vec2 operator+(vec2 a, vec2 b) { return vec2(__fadd2_rn(RFK_F2(a), RFK_F2(b))); }
+__device__ __forceinline__ vec2 operator+(vec2 a, float s) { return vec2(__fadd2_rn(RFK_F2(a), make_float2(s, s))); }
+__device__ __forceinline__ vec2 operator+(float s, vec2 a) { return vec2(__fadd2_rn(make_float2(s, s), RFK_F2(a))); }
+__device__ __forceinline__ vec2 operator-(vec2 a, vec2 b) { return vec2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ vec2 operator-(vec2 a, float s) { return vec2(a.x - s, a.y - s); }
+__device__ __forceinline__ vec2 operator-(float s, vec2 a) { return vec2(s - a.x, s - a.y); }
+// products stay lazy until a sum or a conversion needs them
+__device__ __forceinline__ vprod operator*(vec2 a, vec2 b) { return vprod(a, b); }
+__device__ __forceinline__ vprod operator*(vec2 a, float s) { return vprod(a, vec2(s)); }
+__device__ __forceinline__ vprod operator*(float s, vec2 a) { return vprod(vec2(s), a); }
+__device__ __forceinline__ vprod operator*(vprod p, float s) { return vprod(vec2(p), vec2(s)); }
+__device__ __forceinline__ vprod operator*(float s, vprod p) { return vprod(vec2(s), vec2(p)); }
+__device__ __forceinline__ vprod operator*(vprod p, vec2 b) { return vprod(vec2(p), b); }
+__device__ __forceinline__ vprod operator*(vec2 a, vprod p) { return vprod(a, vec2(p)); }
+__device__ __forceinline__ vprod operator*(vprod p, vprod q) { return vprod(vec2(p), vec2(q)); }
+// product + addend: one FFMA2
+__device__ __forceinline__ vec2 operator+(vprod p, vec2 c) { return rfk_fma2(p.a, p.b, c); }
+__device__ __forceinline__ vec2 operator+(vec2 c, vprod p) { return rfk_fma2(p.a, p.b, c); }
+__device__ __forceinline__ vec2 operator+(vprod p, vprod q) { return rfk_fma2(p.a, p.b, vec2(q)); }
+__device__ __forceinline__ vec2 operator+(vprod p, float s) { return rfk_fma2(p.a, p.b, vec2(s)); }
+__device__ __forceinline__ vec2 operator+(float s, vprod p) { return rfk_fma2(p.a, p.b, vec2(s)); }
+__device__ __forceinline__ vec2 operator-(vprod p, vec2 c) { return rfk_fma2(p.a, p.b, -c); }
+__device__ __forceinline__ vec2 operator-(vec2 c, vprod p) { return rfk_fma2(-p.a, p.b, c); }
+__device__ __forceinline__ vec2 operator-(vprod p, vprod q) { return rfk_fma2(p.a, p.b, -vec2(q)); }
+__device__ __forceinline__ vec2 operator-(vprod p, float s) { return rfk_fma2(p.a, p.b, vec2(-s)); }
+__device__ __forceinline__ vec2 operator-(float s, vprod p) { return rfk_fma2(-p.a, p.b, vec2(s)); }
 #if RFK_MATH_MODE == 0
-RFK_BINOP(/)
-#else
-// two quotients by the same scalar share one reciprocal (each within 2 ulp of the IEEE quotient)
 __device__ __forceinline__ vec2 operator/(vec2 a, vec2 b) { return vec2(a.x / b.x, a.y / b.y); }
-__device__ __forceinline__ vec2 operator/(vec2 a, float s) { float inv = 1.0f / s; return vec2(a.x * inv, a.y * inv); }
+__device__ __forceinline__ vec2 operator/(vec2 a, float s) { return vec2(a.x / s, a.y / s); }
 __device__ __forceinline__ vec2 operator/(float s, vec2 a) { return vec2(s / a.x, s / a.y); }
+__device__ __forceinline__ vec2 operator/(vprod p, float s) { return vec2(p) / s; }
+#else
+// two quotients by the same scalar share one reciprocal (each within 2 ulp of the IEEE quotient); still a lazy product
+__device__ __forceinline__ vec2 operator/(vec2 a, vec2 b) { return vec2(a.x / b.x, a.y / b.y); }
+__device__ __forceinline__ vprod operator/(vec2 a, float s) { return vprod(a, vec2(1.0f / s)); }
+__device__ __forceinline__ vec2 operator/(float s, vec2 a) { return vec2(s / a.x, s / a.y); }
+__device__ __forceinline__ vprod operator/(vprod p, float s) { return vprod(vec2(p), vec2(1.0f / s)); }
 #endif
-#undef RFK_BINOP
+__device__ __forceinline__ vec2 operator/(vprod p, vec2 b) { return vec2(p) / b; }
+__device__ __forceinline__ vec2 operator/(vec2 a, vprod p) { return a / vec2(p); }
+__device__ __forceinline__ vec2 operator/(float s, vprod p) { return s / vec2(p); }
+__device__ __forceinline__ vec2& vec2::operator/=(float s) { return *this = vec2(*this / s); }
 // `e / rfk_cfp[n]` in the generated text (a divisor that is one warp-uniform parameter slot) is emitted as
 // `e RFK_DIVC(n, r)`: the quotient in mode 0, a product with the reciprocal the host stored in rfk_cfp[r] otherwise.
 #if RFK_MATH_MODE == 0
@@ -76,7 +131,6 @@ __device__ __forceinline__ vec2 operator/(float s, vec2 a) { return vec2(s / a.x
 #else
 #define RFK_DIVC(n, r) * rfk_cfp[r]
 #endif
-__device__ __forceinline__ vec2 operator-(vec2 a) { return vec2(-a.x, -a.y); }
 
 // math.glsl:1-4
 static constexpr float PI = 3.141592653589793f;

@@ -1,6 +1,7 @@
 #include "variation_table.hpp"
 
 #include <algorithm>
+#include <regex>
 #include <set>
 #include <stack>
 #include <stdexcept>
@@ -141,6 +142,15 @@ std::string xform_select_text(const buffer_map_t& map, bool cuda) {  // shaders/
 
 enum class dialect { glsl, cuda };
 
+// The affine lines the emitter writes (pre-affine of every xform, post-affine),
+//   vec2(fma(a, X, fma(c, Y, e)), fma(b, X, fma(d, Y, f)))
+// become rfk_affine(a, b, c, d, e, f, X, Y): the same nested fmas, two lanes per instruction (device_prelude.cuh).
+std::string pack_affines(const std::string& s) {
+    static const std::regex re(
+        R"(vec2\(fma\(([^,()]+), ([A-Za-z_][\w.]*), fma\(([^,()]+), ([A-Za-z_][\w.]*), ([^,()]+)\)\), fma\(([^,()]+), \2, fma\(([^,()]+), \4, ([^,()]+)\)\)\))");
+    return std::regex_replace(s, re, "rfk_affine($1, $6, $3, $7, $5, $8, $2, $4)");
+}
+
 std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
     const auto& buf_map = f.buffer_map();
     std::string disp_func = d == dialect::glsl
@@ -163,6 +173,7 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
             dispatch_invoke = suffix_float_literals(dispatch_invoke);
             dispatch_invoke = swizzles_to_calls(dispatch_invoke);
             dispatch_invoke = sequence_randf(dispatch_invoke, rf_counter);
+            dispatch_invoke = pack_affines(dispatch_invoke);
         }
 
         if (i + 1 == (int)f.xforms.size()) disp_func += "default: {\n" + dispatch_invoke + "\n}}\n";
