@@ -53,8 +53,11 @@ __device__ __forceinline__ unsigned int rfk_hash32(unsigned int h) {
 // A bijection of [0, RFK_BLOCK): j = (tid * a + b) mod RFK_BLOCK with a odd, a and b fresh every iteration.
 // Two particles of one warp land in the same warp again with probability ~1/8 (8 warps), as under a uniform
 // permutation; the multiplier changes every iteration, so no pair stays together.
-__device__ __forceinline__ unsigned int rfk_deal_slot(unsigned int tid, unsigned int key) {
-    return (tid * ((key >> 8) | 1u) + (key >> 20)) & (RFK_BLOCK - 1);
+// Only the low log2(RFK_BLOCK) bits of the multiplier matter: the low byte of the LCG key walks all 256 residues
+// (full period), `| 1` makes it odd; the offset b comes from the well-mixed high half (bits 16 and up).
+// Returned as the byte offset of the 16-byte exchange slot, j * 16, from tid * 16: the shift rides on the multiply.
+__device__ __forceinline__ unsigned int rfk_deal_offset(unsigned int tid16, unsigned int key) {
+    return (tid16 * (key | 1u) + (key >> 12)) & ((RFK_BLOCK - 1) << 4);
 }
 
 // src/hammersley.cpp:29-48 for point `i` (z = w = 0)
@@ -193,13 +196,13 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
         return xid;
 #endif
     };
+    const unsigned int tid16 = tid << 4;
     unsigned int deal_key = rfk_hash32(p.deal_seed ^ (blockIdx.x * 0x9E3779B9u));
     auto deal = [&](int) {
         deal_key = deal_key * 1664525u + 1013904223u;  // CTA-uniform
-        unsigned int j = rfk_deal_slot(tid, deal_key);
-        ex[parity][j] = make_float4(x, y, c, 0.0f);
+        *reinterpret_cast<float4*>(reinterpret_cast<char*>(ex[parity]) + rfk_deal_offset(tid16, deal_key)) = make_float4(x, y, c, c);
         __syncthreads();
-        const float4 in = ex[parity][tid];
+        const float4 in = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(ex[parity]) + tid16);
         x = in.x; y = in.y; c = in.z;
         parity ^= 1;
     };

@@ -126,10 +126,14 @@ __device__ __forceinline__ vec2 operator/(float s, vprod p) { return s / vec2(p)
 __device__ __forceinline__ vec2& vec2::operator/=(float s) { return *this = vec2(*this / s); }
 // `e / rfk_cfp[n]` in the generated text (a divisor that is one warp-uniform parameter slot) is emitted as
 // `e RFK_DIVC(n, r)`: the quotient in mode 0, a product with the reciprocal the host stored in rfk_cfp[r] otherwise.
+// RFK_MIXC(z, colour, speed, 1 - speed, colour * speed): the colour blend of every xform, mix(z, colour, speed), from
+// the two host-derived constants — one FFMA.
 #if RFK_MATH_MODE == 0
 #define RFK_DIVC(n, r) / rfk_cfp[n]
+#define RFK_MIXC(z, c, t, one_minus_t, c_times_t) mix(z, c, t)
 #else
 #define RFK_DIVC(n, r) * rfk_cfp[r]
+#define RFK_MIXC(z, c, t, one_minus_t, c_times_t) ::fmaf(z, one_minus_t, c_times_t)
 #endif
 
 // math.glsl:1-4

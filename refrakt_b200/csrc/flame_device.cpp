@@ -471,11 +471,18 @@ static void launch(CUfunction fn, unsigned grid, unsigned block, void** args) {
 // the kernels read every slot that is the same for all temporal samples from constant memory (rfk_cfp, see compile_flame_cuda)
 static void upload_constant_params(flame_device& d, const float* fp) {
     if (!d.cfp || !d.cfp_floats) return;
-    // lower half: the slots; upper half: their reciprocals, read by `e / slot` in the generated text (RFK_DIVC)
-    const std::size_t size = std::min<std::size_t>(d.cfp_floats / 2, flame::PARAM_BUFFER);
-    d.cfp_staging.resize(2 * size);
-    for (std::size_t i = 0; i < size; i++) { d.cfp_staging[i] = fp[i]; d.cfp_staging[size + i] = 1.0f / fp[i]; }
-    cuda_check(cudaMemcpyAsync(d.cfp, d.cfp_staging.data(), 2 * size * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
+    // four quarters: the slots; their reciprocals, read by `e / slot` in the generated text (RFK_DIVC); 1 - slot and
+    // slot[i - 1] * slot[i], the two constants of the colour blend (RFK_MIXC, indexed by the colour-speed slot)
+    const std::size_t size = std::min<std::size_t>(d.cfp_floats / 4, flame::PARAM_BUFFER);
+    d.cfp_staging.resize(4 * size);
+    for (std::size_t i = 0; i < size; i++) {
+        volatile float prod = i ? fp[i - 1] * fp[i] : 0.0f;  // rounded to binary32, like the device's FMUL
+        d.cfp_staging[i] = fp[i];
+        d.cfp_staging[size + i] = 1.0f / fp[i];
+        d.cfp_staging[2 * size + i] = 1.0f - fp[i];
+        d.cfp_staging[3 * size + i] = prod;
+    }
+    cuda_check(cudaMemcpyAsync(d.cfp, d.cfp_staging.data(), 4 * size * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
 }
 
 static rfk_iter_params_host base_params(flame& f) {

@@ -165,8 +165,16 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
 
         auto [inlined, xform_src] = make_xform_text(xform, xmap, vt);
 
-        std::string dispatch_invoke = "return vec4(" + std::string(inlined ? xform_src : "result") + ", mix(((first_run)? randf(): v.z), " +
-                                      slot_str(xmap.color) + ", " + slot_str(xmap.color_speed) + "), " + slot_str(xmap.opacity) + ");\n";
+        // colour blend mix(z, colour, speed) = z * (1 - speed) + colour * speed. The CUDA dialect spells it RFK_MIXC with the
+        // slots of the two derived constants 1 - speed and colour * speed (uploaded by the host behind the slots and their
+        // reciprocals: rfk_cfp[2 * size + speed], rfk_cfp[3 * size + speed]; needs colour and speed in adjacent slots):
+        // one FFMA instead of FADD + FMUL + FFMA on warp-uniform values in every iteration.
+        const int size = std::max(1, buf_map.size);
+        std::string blend = "mix(((first_run)? randf(): v.z), " + slot_str(xmap.color) + ", " + slot_str(xmap.color_speed) + ")";
+        if (d == dialect::cuda && xmap.color_speed == xmap.color + 1)
+            blend = "RFK_MIXC(((first_run)? randf(): v.z), " + slot_str(xmap.color) + ", " + slot_str(xmap.color_speed) + ", rfk_cfp[" +
+                    std::to_string(2 * size + xmap.color_speed) + "], rfk_cfp[" + std::to_string(3 * size + xmap.color_speed) + "])";
+        std::string dispatch_invoke = "return vec4(" + std::string(inlined ? xform_src : "result") + ", " + blend + ", " + slot_str(xmap.opacity) + ");\n";
         if (!inlined) dispatch_invoke = xform_src + dispatch_invoke;
 
         if (d == dialect::cuda) {
@@ -238,7 +246,7 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
             folded += out[i++];
         }
         // C linkage: the host finds it with cuModuleGetGlobal("rfk_cfp") although the text sits inside namespace rfk_glsl
-        return slots + "extern \"C\" { __constant__ float rfk_cfp[" + std::to_string(2 * size) + "]; }\n" + folded;
+        return slots + "extern \"C\" { __constant__ float rfk_cfp[" + std::to_string(4 * size) + "]; }\n" + folded;
     }
     return xid_func + disp_func;
 }
