@@ -69,40 +69,35 @@ __device__ __forceinline__ float2 rfk_sample_point(unsigned int i, int bits, flo
 }
 
 // flame.glsl:78-84: screen affine, floor, bounds and opacity test, row flip. Returns the bin index or -1.
-// coords = ivec2(floor(pos)) lies in [0, W) x [0, H) exactly when 0 <= pos.x < W and 0 <= pos.y < H (W, H integers),
-// so the test runs on the un-floored position (NaN fails every comparison: non-finite positions never bin, where the
-// reference leaves ivec2(floor(NaN)) undefined), and inside the bounds truncation equals floor.
-// The truncation itself is an addition of 2^23 rounded toward zero: for 0 <= p < 2^23 the sum's mantissa field is
-// floor(p) exactly, so its bit pattern is 0x4B000000 + floor(p) — an FADD.RZ on the FMA pipe instead of an F2I on the
-// quarter-rate conversion unit, which is the busiest pipe of the kernel. The two biases fold into one constant of the
-// index arithmetic (mod 2^32; W, H < 2^23 is checked by the host).
-__device__ __forceinline__ bool rfk_bin_test(float x, float y, float w, const float* ss, float Wf, float Hf, float& px, float& py) {
+// The truncation coords = ivec2(floor(pos)) is an addition of 2^23 rounded toward zero: for 0 <= p < 2^23 the sum's
+// mantissa field is floor(p) exactly, so its bit pattern is B + floor(p) with B = 0x4B000000 — an FADD.RZ on the FMA
+// pipe instead of an F2I on the quarter-rate conversion unit. The same integer also carries the bounds test:
+// t = bits - B, as unsigned, is below W exactly when 0 <= floor(p) < W (W < 2^23, checked by the host): a negative p
+// gives a sum below 2^23 (bits < B, t wraps to a huge value; -0.0 gives t = 0, and floor(-0.0) is in bounds), p >= 2^23
+// moves the exponent (t >= 2^23), a sum that is negative, infinite or NaN has bits >= 0x7F800000 or the sign bit set
+// (t >= 0x34800000). Non-finite positions therefore never bin, where the reference leaves ivec2(floor(NaN)) undefined.
+__device__ __forceinline__ unsigned int rfk_trunc_biased(float p) { return __float_as_uint(__fadd_rz(p, 8388608.0f)) - 0x4B000000u; }
+__device__ __forceinline__ bool rfk_bin_test(float x, float y, float w, const float* ss, int W, int H, unsigned int& cx, unsigned int& cy) {
     const vec2 pos = rfk_affine(ss[0], ss[1], ss[2], ss[3], ss[4], ss[5], x, y);  // nested fma, as flame.glsl:79-80
-    px = pos.x; py = pos.y;
-    return px >= 0.0f && py >= 0.0f && px < Wf && py < Hf && w > 0.0f;
+    cx = rfk_trunc_biased(pos.x);
+    cy = rfk_trunc_biased(pos.y);
+    return cx < (unsigned int)W && cy < (unsigned int)H && w > 0.0f;
 }
-__device__ __forceinline__ unsigned int rfk_trunc_biased(float p) { return __float_as_uint(__fadd_rz(p, 8388608.0f)); }  // 0x4B000000 + floor(p)
-__device__ __forceinline__ int rfk_bin_of(float px, float py, int W, int H) {
-    // (H - 1 - cy) * W + cx with cy = ty - B, cx = tx - B, B = 0x4B000000
-    const unsigned int B = 0x4B000000u;
-    const unsigned int base = (unsigned int)(H - 1) * (unsigned int)W + B * (unsigned int)W - B;  // uniform
-    return (int)(base - rfk_trunc_biased(py) * (unsigned int)W + rfk_trunc_biased(px));
-}
-__device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const float* ss, int W, int H, float Wf, float Hf) {
-    float px, py;
-    if (!rfk_bin_test(x, y, w, ss, Wf, Hf, px, py)) return -1;
-    return rfk_bin_of(px, py, W, H);
+__device__ __forceinline__ int rfk_bin_of(unsigned int cx, unsigned int cy, int W, int H) { return (int)(((unsigned int)(H - 1) - cy) * (unsigned int)W + cx); }
+__device__ __forceinline__ int rfk_bin_index(float x, float y, float w, const float* ss, int W, int H) {
+    unsigned int cx, cy;
+    if (!rfk_bin_test(x, y, w, ss, W, H, cx, cy)) return -1;
+    return rfk_bin_of(cx, cy, W, H);
 }
 
 #if RFK_L2_HINTS
 // The same test and index as rfk_bin_index, also returning the bit of the bin's 16 x 16 tile in the hot map.
-__device__ __forceinline__ int rfk_bin_index_hot(float x, float y, float w, const float* ss, int W, int H, float Wf, float Hf,
+__device__ __forceinline__ int rfk_bin_index_hot(float x, float y, float w, const float* ss, int W, int H,
                                                  const unsigned int* hot_map, int tiles_x, bool& hot) {
-    float px, py;
+    unsigned int cx, cy;
     hot = true;
-    if (!rfk_bin_test(x, y, w, ss, Wf, Hf, px, py)) return -1;
-    const unsigned int B = 0x4B000000u;
-    const int row = H - 1 - (int)(rfk_trunc_biased(py) - B), col = (int)(rfk_trunc_biased(px) - B);
+    if (!rfk_bin_test(x, y, w, ss, W, H, cx, cy)) return -1;
+    const int row = H - 1 - (int)cy, col = (int)cx;
     if (hot_map) {
         const unsigned int tile = (unsigned int)(row >> 4) * (unsigned int)tiles_x + (unsigned int)(col >> 4);
         hot = (__ldg(hot_map + (tile >> 5)) >> (tile & 31u)) & 1u;
@@ -224,8 +219,23 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
         x = st.x; y = st.y; c = st.z;
     }
 
-    for (int it = 0; it < p.num_iter; ++it) {
-        const int xid = pick_xform();
+    // Iterations run in blocks that end where the pool of picks does: the refill test and the pool index leave the inner loop.
+    for (int it = 0; it < p.num_iter;) {
+#if RFK_PER_LANE_XFORM
+        const int block_end = it + 1;
+#else
+        if ((pick_count & 31) == 0) pick_pool = get_xform_id(rfk_randf(rs));
+        int pick_lane = pick_count & 31;
+        const int block_len = ::min(32 - pick_lane, p.num_iter - it);
+        const int block_end = it + block_len;
+        pick_count += block_len;
+#endif
+      for (; it < block_end; ++it) {
+#if RFK_PER_LANE_XFORM
+        const int xid = get_xform_id(rfk_randf(rs));
+#else
+        const int xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane++);
+#endif
 #if RFK_COUNT_XFORMS
         if (DRAW) {  // picks of drawn iterations only (the read-out of main.cpp:595-611)
   #if RFK_PER_LANE_XFORM
@@ -248,12 +258,12 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #endif
 #if RFK_L2_HINTS
             bool hot;
-            const int idx = rfk_bin_index_hot(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf, p.hot_map, p.hot_tiles_x, hot);
+            const int idx = rfk_bin_index_hot(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.hot_map, p.hot_tiles_x, hot);
             const bool in_bounds = idx >= 0;
 #else
-            float px, py;
-            const bool in_bounds = rfk_bin_test(fx, fy, fw, p.ss_affine, p.bin_wf, p.bin_hf, px, py);
-            const int idx = rfk_bin_of(px, py, p.bin_w, p.bin_h);  // meaningful only where in_bounds
+            unsigned int cx, cy;
+            const bool in_bounds = rfk_bin_test(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, cx, cy);
+            const int idx = rfk_bin_of(cx, cy, p.bin_w, p.bin_h);  // meaningful only where in_bounds
 #endif
 #if RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC
             const unsigned int hit = __ballot_sync(0xffffffffu, in_bounds);
@@ -303,6 +313,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
         if ((it + 1) % RFK_DEAL_PERIOD == 0) deal(it);
   #endif
 #endif
+      }
     }
 
     p.particles[slot] = make_float4(x, y, c, 0.0f);
@@ -376,7 +387,7 @@ extern "C" __global__ void __launch_bounds__(256) rfk_reference_pass(const __gri
             fx = q.x; fy = q.y; fc = q.z; fw = q.w * r.w;
         }
 #endif
-        const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, p.bin_wf, p.bin_hf);
+        const int idx = rfk_bin_index(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h);
         if (idx >= 0) {
             float4 col = pal[rfk_palette_index(fc)];
             rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);  // the reference's racy +=, made atomic
@@ -416,6 +427,6 @@ extern "C" __global__ void rfk_bucket_index(int n, const float* __restrict__ xyz
                                             int* idx_out, int* pal_out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    idx_out[i] = rfk_bin_index(xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 3], bp.ss_affine, bp.bin_w, bp.bin_h, (float)bp.bin_w, (float)bp.bin_h);
+    idx_out[i] = rfk_bin_index(xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 3], bp.ss_affine, bp.bin_w, bp.bin_h);
     pal_out[i] = (int)rfk_palette_index(xyzw[4 * i + 2]);
 }
