@@ -39,7 +39,7 @@ class XformInfo(C.Structure):
 
 class KernelOptions(C.Structure):
     _fields_ = [("math_mode", C.c_int32), ("fmad", C.c_int32), ("per_lane_xform", C.c_int32), ("warp_aggregate", C.c_int32),
-                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32), ("l2_hints", C.c_int32)]
+                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32), ("l2_hints", C.c_int32), ("staged_bins", C.c_int32)]
 
 
 class HotMapInfo(C.Structure):

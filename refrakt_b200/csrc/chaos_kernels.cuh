@@ -18,7 +18,7 @@
 // Expects these macros from the host (flame_device.cpp): RFK_BLOCK, RFK_LOG2_BLOCK,
 // RFK_TOTAL_PARAMS, RFK_NUM_XFORMS, RFK_HAS_FINAL, RFK_LAUNCH_BOUNDS and the
 // option macros RFK_PER_LANE_XFORM, RFK_WARP_AGGREGATE, RFK_DETERMINISTIC,
-// RFK_COUNT_XFORMS (each 0 or 1).
+// RFK_COUNT_XFORMS, RFK_L2_HINTS, RFK_STAGED_BINS (each 0 or 1).
 
 using namespace rfk_glsl;
 
@@ -41,9 +41,20 @@ struct rfk_iter_params {
     float hammersley_inv_max;
     const unsigned int* hot_map;        // RFK_L2_HINTS: one bit per 16 x 16-bin tile, set = keep in L2; null = no hints
     int hot_tiles_x;                    // tiles per histogram row
+    // RFK_STAGED_BINS: samples are appended to per-region queues in HBM and accumulated region by region afterwards
+    uint2* stage_records;               // [regions][stage_capacity chunks][RFK_STAGE_CHUNK] (local bin << 8 | palette row, opacity bits)
+    unsigned int* stage_cursors;        // [regions] chunks handed out so far (may run past the capacity)
+    unsigned int* stage_fill;           // [regions][stage_capacity] records written into each chunk
+    unsigned int stage_capacity;        // chunks per region
+    int stage_region_shift;             // a region is 2^shift consecutive bins
+    int stage_regions;                  // <= RFK_STAGE_MAX_REGIONS
 };
 
 #define RFK_FIXED_SCALE 16777216.0f  // 2^24
+#define RFK_STAGE_CHUNK 512u         // records per chunk (4 KB); at least RFK_BLOCK, so one iteration of a CTA never spans three chunks
+#define RFK_STAGE_MAX_REGIONS 256
+#define RFK_STAGE_NONE 0xffffffffu    // no chunk opened yet
+#define RFK_STAGE_DEAD 0xfffffffeu    // the region's queue is exhausted: direct reductions from here on
 
 __device__ __forceinline__ unsigned int rfk_hash32(unsigned int h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -151,6 +162,10 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #if RFK_COUNT_XFORMS
     __shared__ unsigned int xcount[RFK_NUM_XFORMS + 1];
 #endif
+#if RFK_STAGED_BINS
+    // per region: records handed out from the CTA's open chunk (RFK_STAGE_CHUNK = full) and the chunk's number in the region's queue
+    __shared__ unsigned int st_fill[DRAW ? RFK_STAGE_MAX_REGIONS : 1], st_chunk[DRAW ? RFK_STAGE_MAX_REGIONS : 1];
+#endif
 
     const unsigned int tid = threadIdx.x;
     const unsigned int lane = tid & 31u;
@@ -163,13 +178,15 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #if RFK_COUNT_XFORMS
     if (tid <= RFK_NUM_XFORMS) xcount[tid] = 0;
 #endif
+#if RFK_STAGED_BINS
+    if (DRAW) for (int i = tid; i < p.stage_regions; i += RFK_BLOCK) { st_fill[i] = RFK_STAGE_CHUNK; st_chunk[i] = RFK_STAGE_NONE; }
+#endif
 
     rfk_rng rs = p.rng[slot];
     float x, y, c;
     __syncthreads();
 
     unsigned int binned = 0;
-    int parity = 0;
 #if RFK_L2_HINTS
     unsigned long long evict_first_policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first_policy));
@@ -192,15 +209,23 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #endif
     };
     const unsigned int tid16 = tid << 4;
+#if RFK_DEAL_PERIOD != 1
+    int since_deal = 0;
+#endif
     unsigned int deal_key = rfk_hash32(p.deal_seed ^ (blockIdx.x * 0x9E3779B9u));
-    auto deal = [&](int) {
+    // the two exchange buffers by shared-window address; `ex_cur = ex_both - ex_cur` flips between them (one uniform op)
+    unsigned int ex_cur = (unsigned int)__cvta_generic_to_shared(&ex[0][0]);
+    const unsigned int ex_both = ex_cur + (unsigned int)__cvta_generic_to_shared(&ex[1][0]);
+    auto deal_store = [&]() {
         deal_key = deal_key * 1664525u + 1013904223u;  // CTA-uniform
-        *reinterpret_cast<float4*>(reinterpret_cast<char*>(ex[parity]) + rfk_deal_offset(tid16, deal_key)) = make_float4(x, y, c, c);
-        __syncthreads();
-        const float4 in = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(ex[parity]) + tid16);
-        x = in.x; y = in.y; c = in.z;
-        parity ^= 1;
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" ::"r"(ex_cur + rfk_deal_offset(tid16, deal_key)), "f"(x), "f"(y), "f"(c) : "memory");
     };
+    auto deal_load = [&]() {  // after the barrier that follows deal_store
+        float unused;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(c), "=f"(unused) : "r"(ex_cur + tid16) : "memory");
+        ex_cur = ex_both - ex_cur;
+    };
+    auto deal = [&]() { deal_store(); __syncthreads(); deal_load(); };
 
     if (!DRAW && p.first_run) {
         // flame.glsl:58-65: every temporal sample starts from the same Hammersley set, jittered
@@ -213,7 +238,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
         float m = r0 * .1f * PI * 2.0f;
         vec4 r = dispatch<true>(vec3(s.x + m * sc.x, s.y + m * sc.y, 0.0f), xid, rs);
         x = r.x; y = r.y; c = r.z;
-        deal(-1);
+        deal();
     } else {
         float4 st = p.particles[slot];
         x = st.x; y = st.y; c = st.z;
@@ -229,12 +254,15 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
         const int block_len = ::min(32 - pick_lane, p.num_iter - it);
         const int block_end = it + block_len;
         pick_count += block_len;
+        // the inner loop counts on the pool index alone
+        const int pick_lane_end = pick_lane + block_len;
 #endif
-      for (; it < block_end; ++it) {
 #if RFK_PER_LANE_XFORM
+      for (; it < block_end; ++it) {
         const int xid = get_xform_id(rfk_randf(rs));
 #else
-        const int xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane++);
+      for (; pick_lane != pick_lane_end; ++pick_lane) {
+        const int xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane);
 #endif
 #if RFK_COUNT_XFORMS
         if (DRAW) {  // picks of drawn iterations only (the read-out of main.cpp:595-611)
@@ -265,7 +293,53 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
             const bool in_bounds = rfk_bin_test(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, cx, cy);
             const int idx = rfk_bin_of(cx, cy, p.bin_w, p.bin_h);  // meaningful only where in_bounds
 #endif
-#if RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC
+#if RFK_STAGED_BINS
+            // A histogram many times larger than L2 turns every reduction into a DRAM sector read-modify-write at a random
+            // address (76 B of traffic per sample on the 2.12 GB histogram of config 3). Here the sample is appended instead,
+            // as an 8-byte record, to the queue of its region (2^shift consecutive bins, sized to sit in L2), and
+            // stage_accumulate_kernel then walks the queues region by region, so the reductions of one region meet in L2
+            // (static_kernels.cu). A queue is a list of 4 KB chunks; a CTA owns one open chunk per region and hands out
+            // its slots with a shared-memory counter, so the global cursor of a region is bumped once per 512 samples
+            // (one bump per sample ran at the same-address atomic rate of L2: 22 G/s). A sample that finds its chunk full
+            // waits for the barrier, after which one thread per region has retired the chunk and opened the next.
+            // A region whose queue is exhausted falls back to the direct reduction.
+            const unsigned int live = __ballot_sync(0xffffffffu, in_bounds);
+            unsigned int st_pos = 0, st_region = 0, st_rec = 0;
+            if (in_bounds) {
+                st_region = (unsigned int)idx >> p.stage_region_shift;
+                st_rec = (((unsigned int)idx & ((1u << p.stage_region_shift) - 1u)) << 8) | rfk_palette_index(fc);
+                const unsigned int peers = __match_any_sync(live, st_region);
+                const int leader = __ffs(peers) - 1;
+                if ((int)lane == leader) st_pos = atomicAdd(&st_fill[st_region], (unsigned int)__popc(peers));
+                st_pos = __shfl_sync(peers, st_pos, leader) + __popc(peers & ((1u << lane) - 1u));
+                if (st_pos < RFK_STAGE_CHUNK)
+                    __stcs(p.stage_records + (((size_t)st_region * p.stage_capacity + st_chunk[st_region]) * RFK_STAGE_CHUNK + st_pos), make_uint2(st_rec, __float_as_uint(fw)));
+                binned++;
+            }
+            __syncthreads();
+            for (unsigned int r = tid; r < (unsigned int)p.stage_regions; r += RFK_BLOCK) {
+                if (st_fill[r] > RFK_STAGE_CHUNK) {  // somebody is waiting for a slot
+                    const unsigned int old = st_chunk[r];
+                    if (old < RFK_STAGE_DEAD) p.stage_fill[(size_t)r * p.stage_capacity + old] = RFK_STAGE_CHUNK;
+                    const unsigned int k = old == RFK_STAGE_DEAD ? RFK_STAGE_DEAD : atomicAdd(p.stage_cursors + r, 1u);
+                    if (k < p.stage_capacity) { st_chunk[r] = k; st_fill[r] -= RFK_STAGE_CHUNK; }
+                    else { st_chunk[r] = RFK_STAGE_DEAD; st_fill[r] = RFK_STAGE_CHUNK; }  // queue exhausted: "full, no chunk" for good
+                }
+            }
+  #if !RFK_PER_LANE_XFORM && RFK_DEAL_PERIOD == 1
+            deal_store();  // the re-deal's barrier doubles as the one before the late writers
+  #endif
+            __syncthreads();
+            if (in_bounds && st_pos >= RFK_STAGE_CHUNK) {
+                const unsigned int chunk = st_chunk[st_region];
+                if (chunk < RFK_STAGE_DEAD) {
+                    __stcs(p.stage_records + (((size_t)st_region * p.stage_capacity + chunk) * RFK_STAGE_CHUNK + (st_pos - RFK_STAGE_CHUNK)), make_uint2(st_rec, __float_as_uint(fw)));
+                } else {
+                    const float4 col = pal[st_rec & 255u];
+                    rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);
+                }
+            }
+#elif RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC
             const unsigned int hit = __ballot_sync(0xffffffffu, in_bounds);
             if (in_bounds) {
                 float4 col = pal[rfk_palette_index(fc)];
@@ -308,17 +382,31 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
         }
 #if !RFK_PER_LANE_XFORM
   #if RFK_DEAL_PERIOD == 1
-        deal(it);
+    #if RFK_STAGED_BINS
+        if (DRAW) deal_load(); else deal();  // stored before the staging barrier above
+    #else
+        deal();
+    #endif
   #else
-        if ((it + 1) % RFK_DEAL_PERIOD == 0) deal(it);
+        if (++since_deal == RFK_DEAL_PERIOD) { since_deal = 0; deal(); }
   #endif
 #endif
       }
+#if !RFK_PER_LANE_XFORM
+      it = block_end;
+#endif
     }
 
     p.particles[slot] = make_float4(x, y, c, 0.0f);
     p.rng[slot] = rs;  // flame.glsl:89
 
+#if RFK_STAGED_BINS
+    if (DRAW) {  // the open chunks are handed over with what they hold
+        __syncthreads();
+        for (unsigned int r = tid; r < (unsigned int)p.stage_regions; r += RFK_BLOCK)
+            if (st_chunk[r] < RFK_STAGE_DEAD) p.stage_fill[(size_t)r * p.stage_capacity + st_chunk[r]] = ::min(st_fill[r], RFK_STAGE_CHUNK);
+    }
+#endif
     if (DRAW) {
         // flame.glsl:85 does one same-address atomic per sample; one per warp here
         for (int o = 16; o > 0; o >>= 1) binned += __shfl_xor_sync(0xffffffffu, binned, o);

@@ -67,6 +67,8 @@ struct kernel_options {
     int block_width = 256;        // threads per CTA = particles per re-deal pool (128, 256 or 512; the reference's workgroup is 256)
     int deal_period = 1;          // re-deal particles across warps every n-th iteration
     int l2_hints = 0;             // histograms much larger than L2: evict-first reductions outside the hot map
+    int staged_bins = 0;          // histograms much larger than L2: samples go to per-region queues (regions of 2^staged_bins bins,
+                                  // 21 = 32 MB) and are accumulated region by region after the draw kernel; 0 = off
     bool operator==(const kernel_options&) const = default;
 };
 

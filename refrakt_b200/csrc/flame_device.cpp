@@ -188,6 +188,12 @@ struct rfk_iter_params_host {  // must match rfk_iter_params in chaos_kernels.cu
     float hammersley_inv_max;
     const unsigned int* hot_map;
     int hot_tiles_x;
+    uint2* stage_records;
+    unsigned int* stage_cursors;
+    unsigned int* stage_fill;
+    unsigned int stage_capacity;
+    int stage_region_shift;
+    int stage_regions;
 };
 
 struct rfk_pass_params_host {  // must match rfk_pass_params in chaos_kernels.cuh
@@ -233,9 +239,15 @@ struct flame_device {
     unsigned int* hot_bitmap = nullptr;
     std::size_t hot_capacity_tiles = 0;
     int hot_W = 0, hot_H = 0, hot_tiles_x = 0;  // dimensions the current map was built for; 0 = no map
+    // staging queues (kernel option staged_bins)
+    uint2* stage_records = nullptr;
+    unsigned int* stage_cursors = nullptr;
+    unsigned int* stage_fill = nullptr;
+    std::size_t stage_regions = 0, stage_capacity = 0;  // queues and chunks per queue the buffers were sized for
 
     ~flame_device() {
         cudaFree(hot_sums); cudaFree(hot_scratch); cudaFree(hot_bitmap);
+        cudaFree(stage_records); cudaFree(stage_cursors); cudaFree(stage_fill);
         if (module) driver().ModuleUnload(module);
         cudaFree(particles); cudaFree(swap); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
         cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
@@ -263,6 +275,7 @@ void flame::rebuild_cuda_source() {
     s += "#define RFK_DETERMINISTIC " + std::to_string(options_.deterministic ? 1 : 0) + "\n";
     s += "#define RFK_COUNT_XFORMS " + std::to_string(options_.count_xforms ? 1 : 0) + "\n";
     s += "#define RFK_L2_HINTS " + std::to_string(options_.l2_hints ? 1 : 0) + "\n";
+    s += "#define RFK_STAGED_BINS " + std::to_string(options_.staged_bins > 0 ? 1 : 0) + "\n";
     // min_blocks 0 = automatic (flame::cubin): 2048 resident threads per SM (32 registers) unless that spills, else 1536
     // (40 registers) — tools/probe_min_blocks.py; -1 = leave the register budget to the compiler
     if (options_.min_blocks > 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(options_.min_blocks) + ")\n";
@@ -684,8 +697,46 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         cuda_check(cudaMemsetAsync(d.fixed_bins, 0, W * H * 4 * sizeof(unsigned long long), g_sim.stream), "clear fixed-point bins");
         p.fixed_bins = d.fixed_bins;
     }
+    int stage_regions = 0;
+    if (options_.staged_bins > 0) {
+        // regions of 2^staged_bins bins, one queue of 4 KB chunks (512 records) per region. A queue holds sixteen times the
+        // even share of the call's samples plus one open chunk per CTA (beyond that: direct reductions), 16 GiB at most in total
+        // (environment variable RFK_STAGE_MAX_BYTES).
+        constexpr std::size_t chunk = 512, max_regions = 256;
+        const int shift = options_.staged_bins;
+        const std::size_t regions = (W * H + (std::size_t(1) << shift) - 1) >> shift;
+        if (regions > max_regions) throw std::runtime_error("staged_bins: " + std::to_string(regions) + " regions of 2^" + std::to_string(shift) +
+                                                            " bins; at most 256 (raise staged_bins)");
+        const std::size_t samples = g_sim.total_particles * (std::size_t)num_iter, ctas = g_sim.total_particles / options_.block_width;
+        std::size_t capacity = std::min(samples / chunk + ctas, 16 * samples / (chunk * regions) + ctas) + 1;
+        std::size_t max_bytes = std::size_t(16) << 30;
+        if (const char* e = std::getenv("RFK_STAGE_MAX_BYTES")) max_bytes = std::max<std::size_t>(1, std::strtoull(e, nullptr, 10));  // tests: exhausted queues
+        capacity = std::max<std::size_t>(1, std::min(capacity, max_bytes / (chunk * sizeof(uint2)) / regions));
+        if (d.stage_regions != regions || d.stage_capacity != capacity) {
+            cudaFree(d.stage_records); cudaFree(d.stage_cursors); cudaFree(d.stage_fill);
+            d.stage_records = nullptr; d.stage_cursors = d.stage_fill = nullptr; d.stage_regions = d.stage_capacity = 0;
+            cuda_check(cudaMalloc(&d.stage_records, regions * capacity * chunk * sizeof(uint2)), "cudaMalloc(staging queues)");
+            cuda_check(cudaMalloc(&d.stage_cursors, regions * sizeof(unsigned int)), "cudaMalloc(staging cursors)");
+            cuda_check(cudaMalloc(&d.stage_fill, regions * capacity * sizeof(unsigned int)), "cudaMalloc(staging chunk fill table)");
+            cuda_check(cudaMemsetAsync(d.stage_cursors, 0, regions * sizeof(unsigned int), g_sim.stream), "clear staging cursors");
+            d.stage_regions = regions; d.stage_capacity = capacity;
+        }
+        stage_regions = (int)regions;
+        p.stage_records = d.stage_records;
+        p.stage_cursors = d.stage_cursors;
+        p.stage_fill = d.stage_fill;
+        p.stage_capacity = (unsigned int)d.stage_capacity;
+        p.stage_region_shift = shift;
+        p.stage_regions = stage_regions;
+    }
     void* args[] = {&p};
     launch(d.draw, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
+    if (stage_regions) {
+        kernels::stage_accumulate(d.stage_records, d.stage_cursors, d.stage_fill, p.stage_capacity, p.stage_region_shift, stage_regions, d.palette, p.bins,
+                                  W * H, g_sim.stream);
+        cuda_check(cudaMemsetAsync(d.stage_cursors, 0, d.stage_regions * sizeof(unsigned int), g_sim.stream), "clear staging cursors");
+        count_launch(1);
+    }
     if (options_.deterministic) {
         kernels::fixed_to_float(d.fixed_bins, p.bins, W * H, g_sim.stream);
         count_launch(1);

@@ -465,6 +465,52 @@ void build_hot_map(const float4* bins, int W, int H, unsigned int budget_tiles, 
     hot_bitmap_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, s>>>(tile_sums, n_tiles, scratch, bitmap);
 }
 
+// Kernel option staged_bins, second half: rfk_draw left every sample of the call as an 8-byte record in the queue of its
+// region (2^region_shift consecutive bins). A queue is `cursors[region]` chunks of 512 records, chunk c holding fill[c]
+// of them. Grid = (CTAs per region, regions): the block scheduler hands out blockIdx.x fastest, so with four 512-thread
+// CTAs resident per SM the whole GPU works on at most two or three regions at any time and their bins (32 MB each by
+// default) stay in L2 while their samples stream in — every reduction is an L2 hit, DRAM sees each touched sector once
+// in and once out. The records are read with the streaming (evict-first) policy so that they do not push the bins out.
+constexpr unsigned int kStageChunk = 512;  // RFK_STAGE_CHUNK of chaos_kernels.cuh
+__global__ void __launch_bounds__(kStageChunk) stage_accumulate_kernel(const uint2* __restrict__ records, const unsigned int* __restrict__ cursors,
+                                                                       const unsigned int* __restrict__ fill, unsigned int capacity, int region_shift,
+                                                                       const float4* __restrict__ palette, float4* bins, size_t nbins) {
+    __shared__ float4 pal[256];
+    if (threadIdx.x < 256) pal[threadIdx.x] = palette[threadIdx.x];
+    __syncthreads();
+    const unsigned int region = blockIdx.y;
+    const size_t region_base = (size_t)region << region_shift;
+    const unsigned int chunks = min(cursors[region], capacity);
+    const unsigned int* region_fill = fill + (size_t)region * capacity;
+    const uint2* queue = records + (size_t)region * capacity * kStageChunk;
+    auto add = [&](uint2 rec) {
+        const size_t idx = region_base + (rec.x >> 8);
+        if (idx >= nbins) return;  // cannot happen for records rfk_draw wrote
+        const float4 col = pal[rec.x & 255u];
+        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bins + idx), "f"(col.x), "f"(col.y), "f"(col.z), "f"(__uint_as_float(rec.y)) : "memory");
+    };
+    // two chunks in flight per thread
+    unsigned int c = blockIdx.x;
+    for (; c + gridDim.x < chunks; c += 2 * gridDim.x) {
+        const unsigned int n0 = min(region_fill[c], kStageChunk), n1 = min(region_fill[c + gridDim.x], kStageChunk);
+        uint2 r0, r1;
+        if (threadIdx.x < n0) r0 = __ldcs(queue + (size_t)c * kStageChunk + threadIdx.x);
+        if (threadIdx.x < n1) r1 = __ldcs(queue + (size_t)(c + gridDim.x) * kStageChunk + threadIdx.x);
+        if (threadIdx.x < n0) add(r0);
+        if (threadIdx.x < n1) add(r1);
+    }
+    if (c < chunks && threadIdx.x < min(region_fill[c], kStageChunk)) add(__ldcs(queue + (size_t)c * kStageChunk + threadIdx.x));
+}
+
+void stage_accumulate(const uint2* records, const unsigned int* cursors, const unsigned int* fill, unsigned int capacity, int region_shift, int regions,
+                      const float4* palette, float4* bins, std::size_t nbins, cudaStream_t s) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dim3 grid((unsigned)sms * 4, (unsigned)regions);  // four 512-thread CTAs per SM: one region at a time on the whole GPU
+    stage_accumulate_kernel<<<grid, kStageChunk, 0, s>>>(records, cursors, fill, capacity, region_shift, palette, bins, nbins);
+}
+
 void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s) {
     if (!count) return;
     fixed_to_float_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(fixed, bins, count);

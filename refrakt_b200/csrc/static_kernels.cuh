@@ -47,6 +47,9 @@ void build_hot_map(const float4* bins, int W, int H, unsigned int budget_tiles, 
 
 // deterministic mode: bins += fixed * 2^-24, one thread per bin
 void fixed_to_float(const unsigned long long* fixed, float4* bins, std::size_t count, cudaStream_t s);
+// kernel option staged_bins: adds the queued samples of one draw call to the histogram, region by region
+void stage_accumulate(const uint2* records, const unsigned int* cursors, const unsigned int* fill, unsigned int capacity, int region_shift, int regions,
+                      const float4* palette, float4* bins, std::size_t nbins, cudaStream_t s);
 
 // 2x2 box average of a float4 image (config 3: 2x supersampled histogram -> image); W, H are the OUTPUT dims
 void downsample2x(const float4* in, float4* out, int W, int H, cudaStream_t s);
