@@ -52,9 +52,8 @@ struct rfk_iter_params {
 
 #define RFK_FIXED_SCALE 16777216.0f  // 2^24
 #define RFK_STAGE_CHUNK 512u         // records per chunk (4 KB); at least RFK_BLOCK, so one iteration of a CTA never spans three chunks
-#define RFK_STAGE_MAX_REGIONS 256
-#define RFK_STAGE_NONE 0xffffffffu    // no chunk opened yet
-#define RFK_STAGE_DEAD 0xfffffffeu    // the region's queue is exhausted: direct reductions from here on
+#define RFK_STAGE_MAX_REGIONS 64u    // a 6-bit key for the in-warp match
+#define RFK_STAGE_DEAD 0xffffffffu    // no chunk left in the region's queue: the samples of this chunk number are reduced directly
 
 __device__ __forceinline__ unsigned int rfk_hash32(unsigned int h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
@@ -153,6 +152,27 @@ __device__ __forceinline__ float4 rfk_reduce_peers(unsigned int mask, unsigned i
 }
 #endif
 
+#if RFK_STAGED_BINS
+// The lanes of `live` whose region equals this lane's: match.any restated for a 6-bit key as one vote and two
+// predicated logic operations per bit (MATCH.ANY held the MIO queue: mio_throttle 26 % -> 8 % of warp cycles, issue slots
+// 43 % -> 71 % busy). Every lane of the warp calls; a lane outside `live` gets a meaningless mask without its own bit.
+__device__ __forceinline__ unsigned int rfk_match_region(unsigned int live, unsigned int region) {
+    unsigned int peers = live;
+#pragma unroll
+    for (unsigned int bit = 1u; bit < RFK_STAGE_MAX_REGIONS; bit <<= 1) {
+        const bool set = region & bit;
+        const unsigned int v = __ballot_sync(0xffffffffu, set);
+        peers &= set ? v : ~v;
+    }
+    return peers;
+}
+__device__ __forceinline__ unsigned int rfk_lanemask_lt() {
+    unsigned int m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+#endif
+
 template <bool DRAW>
 __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     __shared__ float4 pal[256];
@@ -163,8 +183,8 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     __shared__ unsigned int xcount[RFK_NUM_XFORMS + 1];
 #endif
 #if RFK_STAGED_BINS
-    // per region: records handed out from the CTA's open chunk (RFK_STAGE_CHUNK = full) and the chunk's number in the region's queue
-    __shared__ unsigned int st_fill[DRAW ? RFK_STAGE_MAX_REGIONS : 1], st_chunk[DRAW ? RFK_STAGE_MAX_REGIONS : 1];
+    // per region: samples of this CTA so far, and the places in the region's queue of the CTA's four most recent chunks
+    __shared__ unsigned int st_fill[DRAW ? RFK_STAGE_MAX_REGIONS : 1], st_chunk[DRAW ? RFK_STAGE_MAX_REGIONS : 1][4];
 #endif
 
     const unsigned int tid = threadIdx.x;
@@ -179,7 +199,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     if (tid <= RFK_NUM_XFORMS) xcount[tid] = 0;
 #endif
 #if RFK_STAGED_BINS
-    if (DRAW) for (int i = tid; i < p.stage_regions; i += RFK_BLOCK) { st_fill[i] = RFK_STAGE_CHUNK; st_chunk[i] = RFK_STAGE_NONE; }
+    if (DRAW) for (int i = tid; i < p.stage_regions; i += RFK_BLOCK) st_fill[i] = 0;
 #endif
 
     rfk_rng rs = p.rng[slot];
@@ -298,42 +318,45 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
             // address (76 B of traffic per sample on the 2.12 GB histogram of config 3). Here the sample is appended instead,
             // as an 8-byte record, to the queue of its region (2^shift consecutive bins, sized to sit in L2), and
             // stage_accumulate_kernel then walks the queues region by region, so the reductions of one region meet in L2
-            // (static_kernels.cu). A queue is a list of 4 KB chunks; a CTA owns one open chunk per region and hands out
-            // its slots with a shared-memory counter, so the global cursor of a region is bumped once per 512 samples
-            // (one bump per sample ran at the same-address atomic rate of L2: 22 G/s). A sample that finds its chunk full
-            // waits for the barrier, after which one thread per region has retired the chunk and opened the next.
-            // A region whose queue is exhausted falls back to the direct reduction.
-            const unsigned int live = __ballot_sync(0xffffffffu, in_bounds);
-            unsigned int st_pos = 0, st_region = 0, st_rec = 0;
+            // (static_kernels.cu). A queue is a list of 4 KB chunks. A CTA numbers its samples per region with a
+            // shared-memory counter: sample n goes to slot n mod 512 of the CTA's (n / 512)-th chunk of that region, and the
+            // thread that draws slot 0 takes the chunk from the region's global cursor — one global atomic per 512 samples
+            // (one per sample ran at the same-address atomic rate of L2, 22 G/s). The records are written after the
+            // barrier of the re-deal, when the chunk numbers of this iteration are all published. A region whose queue is
+            // exhausted falls back to the direct reduction.
+            // (Tried and dropped: chunks of 32 records owned by a warp, numbered without atomics or barrier — the sectors of
+            // 75 000 open chunks fill too slowly, L2 writes them back half empty: 3.4 GB written and 1.5 GB read per call
+            // instead of 2.0 and 0.3.)
+            // All 32 lanes take part in the votes and the shuffle (a lane out of bounds computes on a junk region and is
+            // masked out of every group): no divergent-mask WARPSYNC around them.
+            const unsigned int st_region = ((unsigned int)idx >> p.stage_region_shift) & (RFK_STAGE_MAX_REGIONS - 1u);
+            const unsigned int peers = rfk_match_region(__ballot_sync(0xffffffffu, in_bounds), st_region);  // in-bounds lanes of the same region
+            const unsigned int rank = __popc(peers & rfk_lanemask_lt());
+            unsigned int st_pos = 0;
+            if (in_bounds && rank == 0u) st_pos = atomicAdd(&st_fill[st_region], (unsigned int)__popc(peers));
+            st_pos = __shfl_sync(0xffffffffu, st_pos, __ffs(peers) - 1) + rank;
+            unsigned int* const st_base = &st_chunk[st_region][(st_pos / RFK_STAGE_CHUNK) & 3u];
+            unsigned int st_rec = 0;
             if (in_bounds) {
-                st_region = (unsigned int)idx >> p.stage_region_shift;
                 st_rec = (((unsigned int)idx & ((1u << p.stage_region_shift) - 1u)) << 8) | rfk_palette_index(fc);
-                const unsigned int peers = __match_any_sync(live, st_region);
-                const int leader = __ffs(peers) - 1;
-                if ((int)lane == leader) st_pos = atomicAdd(&st_fill[st_region], (unsigned int)__popc(peers));
-                st_pos = __shfl_sync(peers, st_pos, leader) + __popc(peers & ((1u << lane) - 1u));
-                if (st_pos < RFK_STAGE_CHUNK)
-                    __stcs(p.stage_records + (((size_t)st_region * p.stage_capacity + st_chunk[st_region]) * RFK_STAGE_CHUNK + st_pos), make_uint2(st_rec, __float_as_uint(fw)));
+                if ((st_pos & (RFK_STAGE_CHUNK - 1u)) == 0u) {
+                    const unsigned int k = atomicAdd(p.stage_cursors + st_region, 1u);
+                    const bool got = k < p.stage_capacity;
+                    // published as the index of the chunk's first record (below 2^32: the host caps the queues at 32 GiB);
+                    // four slots: a reader of chunk n and the opener of chunk n + 4 are never in the same or adjacent iterations
+                    *st_base = got ? (st_region * p.stage_capacity + k) * RFK_STAGE_CHUNK : RFK_STAGE_DEAD;
+                    if (got) p.stage_fill[(size_t)st_region * p.stage_capacity + k] = RFK_STAGE_CHUNK;  // full, unless it is the CTA's last one
+                }
                 binned++;
             }
-            __syncthreads();
-            for (unsigned int r = tid; r < (unsigned int)p.stage_regions; r += RFK_BLOCK) {
-                if (st_fill[r] > RFK_STAGE_CHUNK) {  // somebody is waiting for a slot
-                    const unsigned int old = st_chunk[r];
-                    if (old < RFK_STAGE_DEAD) p.stage_fill[(size_t)r * p.stage_capacity + old] = RFK_STAGE_CHUNK;
-                    const unsigned int k = old == RFK_STAGE_DEAD ? RFK_STAGE_DEAD : atomicAdd(p.stage_cursors + r, 1u);
-                    if (k < p.stage_capacity) { st_chunk[r] = k; st_fill[r] -= RFK_STAGE_CHUNK; }
-                    else { st_chunk[r] = RFK_STAGE_DEAD; st_fill[r] = RFK_STAGE_CHUNK; }  // queue exhausted: "full, no chunk" for good
-                }
-            }
   #if !RFK_PER_LANE_XFORM && RFK_DEAL_PERIOD == 1
-            deal_store();  // the re-deal's barrier doubles as the one before the late writers
+            deal_store();  // the re-deal's barrier doubles as the one before the records are written
   #endif
             __syncthreads();
-            if (in_bounds && st_pos >= RFK_STAGE_CHUNK) {
-                const unsigned int chunk = st_chunk[st_region];
-                if (chunk < RFK_STAGE_DEAD) {
-                    __stcs(p.stage_records + (((size_t)st_region * p.stage_capacity + chunk) * RFK_STAGE_CHUNK + (st_pos - RFK_STAGE_CHUNK)), make_uint2(st_rec, __float_as_uint(fw)));
+            if (in_bounds) {
+                const unsigned int first = *st_base;
+                if (first != RFK_STAGE_DEAD) {
+                    __stcs(p.stage_records + (first | (st_pos & (RFK_STAGE_CHUNK - 1u))), make_uint2(st_rec, __float_as_uint(fw)));
                 } else {
                     const float4 col = pal[st_rec & 255u];
                     rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, fw);
@@ -401,10 +424,14 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     p.rng[slot] = rs;  // flame.glsl:89
 
 #if RFK_STAGED_BINS
-    if (DRAW) {  // the open chunks are handed over with what they hold
+    if (DRAW) {  // the last chunk of every region is handed over with what it holds
         __syncthreads();
-        for (unsigned int r = tid; r < (unsigned int)p.stage_regions; r += RFK_BLOCK)
-            if (st_chunk[r] < RFK_STAGE_DEAD) p.stage_fill[(size_t)r * p.stage_capacity + st_chunk[r]] = ::min(st_fill[r], RFK_STAGE_CHUNK);
+        for (unsigned int r = tid; r < (unsigned int)p.stage_regions; r += RFK_BLOCK) {
+            const unsigned int total = st_fill[r];
+            if (!total) continue;
+            const unsigned int last = (total - 1u) / RFK_STAGE_CHUNK, first = st_chunk[r][last & 3u];
+            if (first != RFK_STAGE_DEAD) p.stage_fill[first / RFK_STAGE_CHUNK] = total - last * RFK_STAGE_CHUNK;
+        }
     }
 #endif
     if (DRAW) {

@@ -702,15 +702,16 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         // regions of 2^staged_bins bins, one queue of 4 KB chunks (512 records) per region. A queue holds sixteen times the
         // even share of the call's samples plus one open chunk per CTA (beyond that: direct reductions), 16 GiB at most in total
         // (environment variable RFK_STAGE_MAX_BYTES).
-        constexpr std::size_t chunk = 512, max_regions = 256;
+        constexpr std::size_t chunk = 512, max_regions = 64;
         const int shift = options_.staged_bins;
         const std::size_t regions = (W * H + (std::size_t(1) << shift) - 1) >> shift;
         if (regions > max_regions) throw std::runtime_error("staged_bins: " + std::to_string(regions) + " regions of 2^" + std::to_string(shift) +
-                                                            " bins; at most 256 (raise staged_bins)");
+                                                            " bins; at most 64 (raise staged_bins)");
         const std::size_t samples = g_sim.total_particles * (std::size_t)num_iter, ctas = g_sim.total_particles / options_.block_width;
         std::size_t capacity = std::min(samples / chunk + ctas, 16 * samples / (chunk * regions) + ctas) + 1;
         std::size_t max_bytes = std::size_t(16) << 30;
         if (const char* e = std::getenv("RFK_STAGE_MAX_BYTES")) max_bytes = std::max<std::size_t>(1, std::strtoull(e, nullptr, 10));  // tests: exhausted queues
+        max_bytes = std::min(max_bytes, std::size_t(31) << 30);  // record indices are 32-bit in the kernel
         capacity = std::max<std::size_t>(1, std::min(capacity, max_bytes / (chunk * sizeof(uint2)) / regions));
         if (d.stage_regions != regions || d.stage_capacity != capacity) {
             cudaFree(d.stage_records); cudaFree(d.stage_cursors); cudaFree(d.stage_fill);

@@ -413,27 +413,29 @@ def test_staged_bins_give_the_same_histogram(gpu_ready, rfk, flame, monkeypatch)
     rounding; also with queues so small (one chunk per region) that most samples overflow into the direct reduction."""
     W, H, P, TS = 2048, 1152, 256 * 64, 16
     hists = []
-    for staged, max_bytes in ((0, None), (14, None), (16, None), (16, 36 * 4096), (17, None)):
+    #        staged_bins, queue bytes, block_width, deal_period
+    cases = [(0, None, 256, 1), (16, None, 256, 1), (16, 36 * 4096, 256, 1), (17, None, 256, 2), (18, None, 512, 1), (21, None, 128, 1)]
+    for staged, max_bytes, width, period in cases:
         if max_bytes:
             monkeypatch.setenv("RFK_STAGE_MAX_BYTES", str(max_bytes))
         else:
             monkeypatch.delenv("RFK_STAGE_MAX_BYTES", raising=False)
         flame.set_options(math_mode=1, fmad=1, per_lane_xform=0, warp_aggregate=0, deterministic=0, count_xforms=0, min_blocks=0,
-                          block_width=512 if staged == 17 else 256, deal_period=2 if staged == 14 else 1, l2_hints=0, staged_bins=staged)
+                          block_width=width, deal_period=period, l2_hints=0, staged_bins=staged)
         rfk.set_sim_parameters(P, TS, 64, seed=9)
         flame.warmup(16, TSS)
         buf = rfk.DeviceBuffer(W * H * 16)
         buf.zero_out()
         n = flame.draw_to_bins(buf.ptr, W * H, W, 32)
         n += flame.draw_to_bins(buf.ptr, W * H, W, 8)   # a shorter call reuses the queues of the longer one
-        hists.append((staged, buf.download(np.float32, (H, W, 4)), n))
+        hists.append((buf.download(np.float32, (H, W, 4)), n))
         buf.free()
     flame.set_options(staged_bins=0, block_width=256, deal_period=1)
-    for staged, h, n in hists:
+    for h, n in hists:  # every sample landed exactly once, whatever the kernel options
         assert n > 0.5 * P * 40 and h[..., 3].astype(np.float64).sum() == n
-    # the same kernel options apart from staging: (0, 16, 16 with exhausted queues) draw the same samples
-    (_, a, na) = hists[0]
-    for _, b, nb in (hists[2], hists[3]):
+    # the same kernel options apart from staging (also with exhausted queues): the same samples
+    (a, na) = hists[0]
+    for b, nb in (hists[1], hists[2]):
         assert na == nb and np.array_equal(a[..., 3], b[..., 3])
         assert np.allclose(a[..., :3], b[..., :3], rtol=1e-5, atol=1e-5)
 
