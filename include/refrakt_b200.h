@@ -152,11 +152,13 @@ typedef struct rfk_kernel_options {
     int32_t deal_period;    /* re-deal the CTA's particles across warps every n-th iteration; default 1 */
     int32_t l2_hints;       /* histograms several times larger than L2: reductions outside the hot map (rfk_flame_build_hot_map)
                                carry an L2 evict-first hint; default 0 */
-    int32_t staged_bins;    /* histograms several times larger than L2: 0 = off (default); n = 8..24: rfk_draw appends every sample
-                               to the queue of its region (2^n consecutive bins; 21 = 32 MB, a quarter of the L2) and a second
-                               kernel accumulates the queues region by region, so the reductions meet in L2 instead of being
-                               DRAM read-modify-writes at random addresses. Same samples, same histogram; excludes
-                               deterministic, warp_aggregate and l2_hints */
+    int32_t staged_bins;    /* histograms several times larger than L2: rfk_draw appends every sample as an 8-byte record to the
+                               queue of its region (2^n consecutive bins) and a second kernel accumulates the queues region by
+                               region, so the reductions meet in L2 instead of being DRAM read-modify-writes at random addresses.
+                               Same samples, same histogram. -1 = automatic (default): on for histograms of 1 GiB or more, in
+                               at most 64 regions of 2^22 bins (64 MB) or larger; 0 = off; n = 8..24 = always on with regions of
+                               2^n bins (at most 64 regions; excludes deterministic, warp_aggregate and l2_hints, which also
+                               switch the automatic mode off). Queue memory: 16 GiB at most (RFK_STAGE_MAX_BYTES) */
 } rfk_kernel_options;
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* out);
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* in);

@@ -349,8 +349,9 @@ int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
     k.deal_period = i->deal_period;
     k.l2_hints = i->l2_hints ? 1 : 0;
     k.staged_bins = i->staged_bins;
-    if (k.staged_bins != 0 && (k.staged_bins < 8 || k.staged_bins > 24)) return fail(RFK_E_INVALID, "staged_bins must be 0 or the log2 of the bins per region, 8 to 24");
-    if (k.staged_bins && (k.deterministic || k.warp_aggregate || k.l2_hints)) return fail(RFK_E_INVALID, "staged_bins excludes deterministic, warp_aggregate and l2_hints");
+    if (k.staged_bins != 0 && k.staged_bins != -1 && (k.staged_bins < 8 || k.staged_bins > 24))
+        return fail(RFK_E_INVALID, "staged_bins must be -1 (automatic), 0 (off) or the log2 of the bins per region, 8 to 24");
+    if (k.staged_bins > 0 && (k.deterministic || k.warp_aggregate || k.l2_hints)) return fail(RFK_E_INVALID, "staged_bins excludes deterministic, warp_aggregate and l2_hints");
     if (k.block_width != 128 && k.block_width != 256 && k.block_width != 512) return fail(RFK_E_INVALID, "block_width must be 128, 256 or 512");
     if (k.deal_period < 1) return fail(RFK_E_INVALID, "deal_period must be >= 1");
     if (k.min_blocks < -1 || k.min_blocks * k.block_width > 2048) return fail(RFK_E_INVALID, "min_blocks must be -1, 0 or at most 2048 / block_width");

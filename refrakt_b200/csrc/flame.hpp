@@ -67,8 +67,9 @@ struct kernel_options {
     int block_width = 256;        // threads per CTA = particles per re-deal pool (128, 256 or 512; the reference's workgroup is 256)
     int deal_period = 1;          // re-deal particles across warps every n-th iteration
     int l2_hints = 0;             // histograms much larger than L2: evict-first reductions outside the hot map
-    int staged_bins = 0;          // histograms much larger than L2: samples go to per-region queues (regions of 2^staged_bins bins,
-                                  // 21 = 32 MB) and are accumulated region by region after the draw kernel; 0 = off
+    int staged_bins = -1;         // histograms much larger than L2: samples go to per-region queues (regions of 2^staged_bins bins,
+                                  // 22 = 64 MB) and are accumulated region by region after the draw kernel; 0 = off;
+                                  // -1 = automatic: on for histograms of 1 GiB or more, in regions of 2^22 bins or larger
     bool operator==(const kernel_options&) const = default;
 };
 
@@ -159,6 +160,7 @@ struct flame {
     const std::string& glsl_source() const { return glsl_source_; }
     const std::string& cuda_source() const { return cuda_source_; }
     const kernel_options& options() const { return options_; }
+    std::vector<char> staged_cubin() const;  // the kernels with rfk_draw's staging path compiled in (staged_bins = -1)
     // Rebuilds the CUDA module with new options (the structure of the genome is fixed
     // after load, only values change without a rebuild: src/flame.hpp, main.cpp:335-369).
     bool set_options(const kernel_options& opt);

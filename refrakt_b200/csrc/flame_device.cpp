@@ -217,6 +217,11 @@ struct flame_device {
     CUmodule module = nullptr;
     CUfunction warm = nullptr, draw = nullptr, single_step = nullptr, select_xform = nullptr, bucket_index = nullptr, reference_pass = nullptr;
     float* cfp = nullptr;         // the module's __constant__ rfk_cfp[]: parameter slots that do not depend on the temporal sample
+    // staged_bins = -1 (automatic): the same kernels compiled with RFK_STAGED_BINS, built the first time a histogram of 1 GiB
+    // or more is drawn into; it has a constant bank of its own
+    CUmodule staged_module = nullptr;
+    CUfunction staged_draw = nullptr;
+    float* staged_cfp = nullptr;
     std::size_t cfp_floats = 0;
     std::vector<float> cfp_staging;  // host copy of the last upload (slots, then reciprocals)
     float4* particles = nullptr;
@@ -249,6 +254,7 @@ struct flame_device {
         cudaFree(hot_sums); cudaFree(hot_scratch); cudaFree(hot_bitmap);
         cudaFree(stage_records); cudaFree(stage_cursors); cudaFree(stage_fill);
         if (module) driver().ModuleUnload(module);
+        if (staged_module) driver().ModuleUnload(staged_module);
         cudaFree(particles); cudaFree(swap); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
         cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
     }
@@ -350,20 +356,30 @@ static std::size_t spilled_bytes(const std::string& log) {
 
 static constexpr std::size_t kSpillTolerance = 128;  // bytes, rfk_draw + rfk_warm together (stress genome: 48 bytes, +4 % at full occupancy)
 
-const std::vector<char>& flame::cubin() {
-    if (!cubin_.empty()) return cubin_;
-    if (options_.min_blocks != 0) {
-        cubin_ = compile_cubin(cuda_source_, options_, nullptr, 0);
-        return cubin_;
-    }
-    // automatic launch bounds: full occupancy (2048 threads per SM, 32 registers per thread) when the genome's kernels fit
-    // without spilling (more than kSpillTolerance bytes), else 1536 threads per SM (40 registers)
+// automatic launch bounds (min_blocks 0): full occupancy (2048 threads per SM, 32 registers per thread) when the genome's
+// kernels fit without spilling (more than kSpillTolerance bytes), else 1536 threads per SM (40 registers)
+static std::vector<char> compile_with_bounds(const std::string& source, const kernel_options& opt) {
+    if (opt.min_blocks != 0) return compile_cubin(source, opt, nullptr, 0);
     std::string log;
-    std::vector<char> tight = compile_cubin(cuda_source_, options_, &log, 2048 / options_.block_width);
+    std::vector<char> tight = compile_cubin(source, opt, &log, 2048 / opt.block_width);
     // a few spilled bytes are loop-invariant values parked before the loop and re-read inside one xform's body (an L1 hit):
     // cheaper than giving up a quarter of the resident warps
-    cubin_ = spilled_bytes(log) <= kSpillTolerance ? std::move(tight) : compile_cubin(cuda_source_, options_, nullptr, 1536 / options_.block_width);
+    return spilled_bytes(log) <= kSpillTolerance ? std::move(tight) : compile_cubin(source, opt, nullptr, 1536 / opt.block_width);
+}
+
+const std::vector<char>& flame::cubin() {
+    if (cubin_.empty()) cubin_ = compile_with_bounds(cuda_source_, options_);
     return cubin_;
+}
+
+// the same source with the staging path of rfk_draw compiled in (kernel option staged_bins = -1)
+std::vector<char> flame::staged_cubin() const {
+    const std::string off = "#define RFK_STAGED_BINS 0\n", on = "#define RFK_STAGED_BINS 1\n";
+    std::string source = cuda_source_;
+    const std::size_t at = source.find(off);
+    if (at == std::string::npos) throw std::runtime_error("staged_cubin: the kernels are already compiled with staging");
+    source.replace(at, off.size(), on);
+    return compile_with_bounds(source, options_);
 }
 
 void flame::reset_animation() { needs_update_ = true; }
@@ -436,6 +452,22 @@ static void ensure_module(flame& f) {
     d.cfp_floats = cfp_bytes / sizeof(float);
 }
 
+static void ensure_staged_module(flame& f) {
+    flame_device& d = *f.device();
+    if (d.staged_module) return;
+    const auto& api = driver();
+    const std::vector<char> image = f.staged_cubin();
+    cu_check(api.ModuleLoadData(&d.staged_module, image.data()), "cuModuleLoadData(staged)");
+    cu_check(api.ModuleGetFunction(&d.staged_draw, d.staged_module, "rfk_draw"), "rfk_draw(staged)");
+    CUdeviceptr cfp = 0;
+    std::size_t cfp_bytes = 0;
+    cu_check(api.ModuleGetGlobal(&cfp, &cfp_bytes, d.staged_module, "rfk_cfp"), "rfk_cfp(staged)");
+    d.staged_cfp = reinterpret_cast<float*>(cfp);
+    if (!d.cfp_staging.empty())  // the parameters of the last warmup
+        cuda_check(cudaMemcpyAsync(d.staged_cfp, d.cfp_staging.data(), std::min(cfp_bytes, d.cfp_staging.size() * sizeof(float)), cudaMemcpyHostToDevice, g_sim.stream),
+                   "upload constant parameters");
+}
+
 static void ensure_buffers(flame& f) {
     ensure_module(f);
     flame_device& d = *f.device();
@@ -496,6 +528,8 @@ static void upload_constant_params(flame_device& d, const float* fp) {
         d.cfp_staging[3 * size + i] = prod;
     }
     cuda_check(cudaMemcpyAsync(d.cfp, d.cfp_staging.data(), 4 * size * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
+    if (d.staged_cfp)
+        cuda_check(cudaMemcpyAsync(d.staged_cfp, d.cfp_staging.data(), 4 * size * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
 }
 
 static rfk_iter_params_host base_params(flame& f) {
@@ -697,13 +731,25 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         cuda_check(cudaMemsetAsync(d.fixed_bins, 0, W * H * 4 * sizeof(unsigned long long), g_sim.stream), "clear fixed-point bins");
         p.fixed_bins = d.fixed_bins;
     }
-    int stage_regions = 0;
-    if (options_.staged_bins > 0) {
+    int stage_regions = 0, stage_shift = options_.staged_bins > 0 ? options_.staged_bins : 0;
+    CUfunction draw_fn = d.draw;
+    if (options_.staged_bins < 0 && !options_.deterministic && !options_.warp_aggregate && !options_.l2_hints && W * H * sizeof(float4) >= (std::size_t(1) << 30)) {
+        // automatic: a histogram of 1 GiB or more (eight times the L2) is drawn through the queues, in at most 64 regions of
+        // at least 2^22 bins (64 MB, half the L2; measured best on the 2.12 GB histogram of config 3: profiles/)
+        int shift = 22;
+        while (((W * H + (std::size_t(1) << shift) - 1) >> shift) > 64) shift++;
+        if (shift <= 24) {  // a record holds 24 bits of bin index
+            ensure_staged_module(*this);
+            draw_fn = d.staged_draw;
+            stage_shift = shift;
+        }
+    }
+    if (stage_shift > 0) {
         // regions of 2^staged_bins bins, one queue of 4 KB chunks (512 records) per region. A queue holds sixteen times the
         // even share of the call's samples plus one open chunk per CTA (beyond that: direct reductions), 16 GiB at most in total
         // (environment variable RFK_STAGE_MAX_BYTES).
         constexpr std::size_t chunk = 512, max_regions = 64;
-        const int shift = options_.staged_bins;
+        const int shift = stage_shift;
         const std::size_t regions = (W * H + (std::size_t(1) << shift) - 1) >> shift;
         if (regions > max_regions) throw std::runtime_error("staged_bins: " + std::to_string(regions) + " regions of 2^" + std::to_string(shift) +
                                                             " bins; at most 64 (raise staged_bins)");
@@ -731,7 +777,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         p.stage_regions = stage_regions;
     }
     void* args[] = {&p};
-    launch(d.draw, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
+    launch(draw_fn, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
     if (stage_regions) {
         kernels::stage_accumulate(d.stage_records, d.stage_cursors, d.stage_fill, p.stage_capacity, p.stage_region_shift, stage_regions, d.palette, p.bins,
                                   W * H, g_sim.stream);

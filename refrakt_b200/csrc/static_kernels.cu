@@ -489,17 +489,23 @@ __global__ void __launch_bounds__(kStageChunk) stage_accumulate_kernel(const uin
         const float4 col = pal[rec.x & 255u];
         asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(bins + idx), "f"(col.x), "f"(col.y), "f"(col.z), "f"(__uint_as_float(rec.y)) : "memory");
     };
-    // two chunks in flight per thread
-    unsigned int c = blockIdx.x;
-    for (; c + gridDim.x < chunks; c += 2 * gridDim.x) {
-        const unsigned int n0 = min(region_fill[c], kStageChunk), n1 = min(region_fill[c + gridDim.x], kStageChunk);
-        uint2 r0, r1;
-        if (threadIdx.x < n0) r0 = __ldcs(queue + (size_t)c * kStageChunk + threadIdx.x);
-        if (threadIdx.x < n1) r1 = __ldcs(queue + (size_t)(c + gridDim.x) * kStageChunk + threadIdx.x);
-        if (threadIdx.x < n0) add(r0);
-        if (threadIdx.x < n1) add(r1);
+    // four chunks in flight per thread: their fill counts first, then the records, then the reductions
+    constexpr int kInFlight = 4;
+    for (unsigned int c0 = blockIdx.x; c0 < chunks; c0 += kInFlight * gridDim.x) {
+        unsigned int n[kInFlight];
+        uint2 rec[kInFlight];
+#pragma unroll
+        for (int j = 0; j < kInFlight; j++) {
+            const unsigned int c = c0 + j * gridDim.x;
+            n[j] = c < chunks ? min(__ldg(region_fill + c), kStageChunk) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < kInFlight; j++)
+            if (threadIdx.x < n[j]) rec[j] = __ldcs(queue + (size_t)(c0 + j * gridDim.x) * kStageChunk + threadIdx.x);
+#pragma unroll
+        for (int j = 0; j < kInFlight; j++)
+            if (threadIdx.x < n[j]) add(rec[j]);
     }
-    if (c < chunks && threadIdx.x < min(region_fill[c], kStageChunk)) add(__ldcs(queue + (size_t)c * kStageChunk + threadIdx.x));
 }
 
 void stage_accumulate(const uint2* records, const unsigned int* cursors, const unsigned int* fill, unsigned int capacity, int region_shift, int regions,

@@ -430,7 +430,7 @@ def test_staged_bins_give_the_same_histogram(gpu_ready, rfk, flame, monkeypatch)
         n += flame.draw_to_bins(buf.ptr, W * H, W, 8)   # a shorter call reuses the queues of the longer one
         hists.append((buf.download(np.float32, (H, W, 4)), n))
         buf.free()
-    flame.set_options(staged_bins=0, block_width=256, deal_period=1)
+    flame.set_options(staged_bins=-1, block_width=256, deal_period=1)
     for h, n in hists:  # every sample landed exactly once, whatever the kernel options
         assert n > 0.5 * P * 40 and h[..., 3].astype(np.float64).sum() == n
     # the same kernel options apart from staging (also with exhausted queues): the same samples
@@ -448,8 +448,39 @@ def test_staged_bins_reject_too_many_regions(gpu_ready, rfk, flame):
     buf.zero_out()
     with pytest.raises(Exception):
         flame.draw_to_bins(buf.ptr, 2048 * 1152, 2048, 8)
-    flame.set_options(staged_bins=0)
+    flame.set_options(staged_bins=-1)
     buf.free()
+
+
+def test_staging_is_automatic_for_a_histogram_of_one_gibibyte(gpu_ready, rfk, flame):
+    """staged_bins = -1 (the default): a histogram of 1 GiB goes through the queues (one more launch per call: the
+    accumulation kernel; the staged kernels are built on first use and see the parameters of the last warmup), a smaller
+    one does not; the samples are the same as with staging off"""
+    W = H = 8192
+    P, TS = 256 * 64, 16
+    out = []
+    for staged in (-1, 0):
+        flame.set_options(staged_bins=staged)
+        rfk.set_sim_parameters(P, TS, 64, seed=11)
+        flame.warmup(16, TSS)
+        buf = rfk.DeviceBuffer(W * H * 16)
+        buf.zero_out()
+        before = rfk.kernel_launch_count()
+        n = flame.draw_to_bins(buf.ptr, W * H, W, 16)
+        launches = rfk.kernel_launch_count() - before
+        flame.warmup(8, TSS)  # new parameters reach the staged module as well
+        n += flame.draw_to_bins(buf.ptr, W * H, W, 16)
+        small = rfk.DeviceBuffer(1024 * 1024 * 16)
+        small.zero_out()
+        before = rfk.kernel_launch_count()
+        flame.draw_to_bins(small.ptr, 1024 * 1024, 1024, 4)
+        out.append((buf.download(np.float32, (H, W, 4))[..., 3].copy(), n, launches, rfk.kernel_launch_count() - before))
+        buf.free()
+        small.free()
+    flame.set_options(staged_bins=-1)
+    (a, na, la, sa), (b, nb, lb, sb) = out
+    assert (la, lb, sa, sb) == (2, 1, 1, 1)
+    assert na == nb and na > 0 and np.array_equal(a, b)
 
 
 def test_release_buffers_frees_and_the_library_recovers(gpu_ready, rfk, flame):

@@ -19,4 +19,11 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:rfk_
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/prof_draw_$tag.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:density_tonemap --launch-skip 3 --launch-count 1 -f -o $out/prof_density_$tag \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/prof_density_$tag.log 2>&1
+if [ -n "$WITH_CONFIGS" ]; then
+  timeout 900 python tools/run_configs.py 1 2 3 5 > $out/configs_$tag.jsonl 2> $out/configs_$tag.err
+  timeout 300 python tools/run_configs.py 3 --staged 0 >> $out/configs_$tag.jsonl 2>> $out/configs_$tag.err
+  cut -c1-260 $out/configs_$tag.jsonl
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'rfk_draw|stage_accumulate' --launch-skip 2 --launch-count 2 -f -o $out/prof_config3_$tag \
+    python tools/run_configs.py 3 --draw-calls 2 > $out/prof_config3_$tag.log 2>&1
+fi
 ls -la $out | tail -12

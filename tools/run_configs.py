@@ -75,7 +75,7 @@ def main():
     ap.add_argument("--frames", type=int, default=16)
     ap.add_argument("--hot-budget-mb", type=float, default=0.0, help="config 3: hot-map budget (0 = the library default, half the L2)")
     ap.add_argument("--no-l2-hints", action="store_true", help="config 3 without the hot map / evict-first reductions")
-    ap.add_argument("--staged", type=int, default=0, help="config 3 with kernel option staged_bins = log2(bins per region), e.g. 21; 0 = off")
+    ap.add_argument("--staged", type=int, default=-1, help="config 3: kernel option staged_bins: -1 = automatic (the default: queues, regions of 2^22 bins), n = log2(bins per region), 0 = direct reductions with the L2 hot map")
     ap.add_argument("--draw-calls", type=int, default=256, help="config 3: draw calls per GPU")
     args = ap.parse_args()
     global HOT_BUDGET
@@ -111,14 +111,14 @@ def main():
             ms = res["ms_warmup"] + res["ms_draw"] + res["ms_reduce"] + res["ms_post"]
             emit(2, "shipped genome, 3840x2160, 2000 spp, DE + tonemap (4K frame ms = ms_total)", res, res["iterations"] * world, ms)
         elif cfg == 3:
-            hints = 0 if (args.no_l2_hints or args.staged) else 1
+            hints = 0 if (args.no_l2_hints or args.staged != 0) else 1
             flame.set_options(l2_hints=hints, staged_bins=args.staged)
             render_still(flame, 15360, 8640, draw_calls=1)
             res = render_still(flame, 15360, 8640, draw_calls=args.draw_calls, rank=rank, world=world, downsample=True, hot_map=bool(hints))
             res["l2_hints"] = hints
             res["staged_bins"] = args.staged
             res["hot_budget_mb"] = args.hot_budget_mb
-            flame.set_options(l2_hints=0, staged_bins=0)
+            flame.set_options(l2_hints=0, staged_bins=-1)
             flame.clear_hot_map()
             ms = res["ms_warmup"] + res["ms_draw"] + res["ms_reduce"] + res["ms_post"]
             emit(3, "shipped genome, 15360x8640 histogram (2x supersampled 7680x4320), %d draw calls per GPU, NCCL reduce, DE + tonemap + 2x2 box" % args.draw_calls, res, res["iterations"] * world, ms)
