@@ -42,10 +42,14 @@ TSS_WIDTH = 1.2 / 60.0
 METRIC = "chaos_game_iterations_per_second"
 UNIT = "iterations/s"
 WORKLOAD = "configs[1]: electricsheep.247.11256 still, 3840x2160, 2000 samples/pixel, P=2097152, TS=512, warmup 16 + draw 128 passes/call, density estimation + tonemap"
-# From the committed ncu captures of rfk_draw (profiles/r01*_rfk_draw*.md): DRAM bytes of one launch
-# (dram__bytes_read.sum + dram__bytes_write.sum) and executed warp instructions per warp-iteration.
-DRAW_DRAM_TRAFFIC_BYTES = 435.7e6
-DRAW_WARP_INST_PER_WARP_ITERATION = 190.8
+
+
+def draw_counters():
+    """profiles/r01_rfk_draw.json (tools/summarize_profiles.py over the `ncu --set full` capture of rfk_draw in this very
+    workload): DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum) and executed warp instructions per
+    warp-iteration. None when the file is missing: the derived fields are then left out rather than guessed."""
+    path = os.path.join(ROOT, "profiles", "r01_rfk_draw.json")
+    return json.load(open(path)) if os.path.exists(path) else None
 
 
 def roofline_probes():
@@ -272,6 +276,7 @@ def main():
 
     if rank == 0:
         peak, peak_src, peaks = measured_peaks()
+        counters = draw_counters()
         mean_draw_ms = sum(draw_ms) / len(draw_ms)
         mean_binned = sum(draw_binned) / len(draw_binned)
         # algorithmic bytes of one rfk_draw launch: 16 B per binned sample (one float4 reduction) + particle and
@@ -290,7 +295,7 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks.summary(),
             "roofline": {"kernel": "rfk_draw", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": DRAW_DRAM_TRAFFIC_BYTES, "peak_source": peak_src, "launch_ms": mean_draw_ms, "launches_timed": len(draw_ms),
+                         "traffic": counters["dram_bytes_per_launch"] if counters else None, "peak_source": peak_src, "launch_ms": mean_draw_ms, "launches_timed": len(draw_ms),
                          "algorithmic_bytes_per_launch": alg_bytes, "share_of_step": sum(draw_ms) / ms,
                          "binding_limit": "fp32/alu issue, not memory: see DESIGN.md and profiles/",
                          "iterations_per_s_kernel": P * DRAW_PASSES / (mean_draw_ms * 1e-3)},
@@ -304,12 +309,13 @@ def main():
                                         "achieved": post_bytes / (post_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": post_bytes / (post_ms * 1e-3) / 1e9 / peak,
                                         "share_of_step": post_ms * len(post_events) / ms}
         probes = roofline_probes()
-        if probes:
+        if probes and counters:
             kernel_iters_s = P * DRAW_PASSES / (mean_draw_ms * 1e-3)
-            winst = kernel_iters_s / 32.0 * DRAW_WARP_INST_PER_WARP_ITERATION
+            winst = kernel_iters_s / 32.0 * counters["warp_inst_per_unit"]
             line["roofline"]["issue"] = {"achieved_warp_inst_per_s": winst, "peak_measured_ffma_issue": probes["ffma_warp_inst_per_s"],
-                                         "frac": winst / probes["ffma_warp_inst_per_s"], "warp_inst_per_warp_iteration": DRAW_WARP_INST_PER_WARP_ITERATION,
-                                         "source": "ncu smsp__inst_executed.sum (profiles/) x CUDA-event kernel rate; peak = tools/roofline_probes.cu"}
+                                         "frac": winst / probes["ffma_warp_inst_per_s"], "warp_inst_per_warp_iteration": counters["warp_inst_per_unit"],
+                                         "source": "ncu smsp__inst_executed.sum (profiles/r01_rfk_draw.json) x CUDA-event kernel rate; peak = tools/roofline_probes.cu"}
+        if probes:
             red = probes["red_v4_f32"]["132.7MB_4K"]["v4_gred_per_s"]
             line["roofline"]["atomics"] = {"achieved_gred_per_s": mean_binned / (mean_draw_ms * 1e-3) / 1e9, "uniform_random_probe_gred_per_s": red,
                                            "note": "red.global.add.v4.f32 at random addresses over the same 132.7 MB footprint; a flame's hits are concentrated, so the kernel can exceed it"}

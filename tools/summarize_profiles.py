@@ -1,6 +1,6 @@
 """Turns the raw ncu outputs in gpurun_out/ into the committed summaries under profiles/.
   python tools/summarize_profiles.py launches gpurun_out/launches_r01.csv profiles/r01_launches.md
-  python tools/summarize_profiles.py report gpurun_out/prof_draw_r01.ncu-rep profiles/r01_rfk_draw.md [units_per_launch]
+  python tools/summarize_profiles.py report gpurun_out/prof_draw_r01.ncu-rep profiles/r01_rfk_draw.md [units_per_launch [kernel_regex]]
 """
 import collections
 import csv
@@ -56,8 +56,9 @@ def launches(src, dst):
         fh.write("| total | %d | %.3f | | |\n" % (sum(v[0] for v in per.values()), total))
 
 
-def report(src, dst, units=None):
-    raw = ncu_csv(src, "--page", "raw")
+def report(src, dst, units=None, kernel=None):
+    pick = ["-k", "regex:" + kernel] if kernel else []
+    raw = ncu_csv(src, "--page", "raw", *pick)
     hdr, unit, data = raw[0], raw[1], raw[2:]
     name = data[0][hdr.index("Kernel Name")]
     with open(dst, "w") as fh:
@@ -71,10 +72,21 @@ def report(src, dst, units=None):
                 fh.write("| %s | %s | %s |\n" % (k, data[0][i], unit[i]))
         if units and "smsp__inst_executed.sum" in vals:
             fh.write("\nWarp instructions per unit of work (%s units per launch): **%.1f**\n" % (units, float(vals["smsp__inst_executed.sum"].replace(",", "")) / float(units)))
+        # the counters bench.py quotes (roofline.traffic, roofline.issue), next to the summary
+        def num(k):
+            return float(vals[k].replace(",", "")) * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit[hdr.index(k)], 1.0)
+        if "dram__bytes_read.sum" in vals and "smsp__inst_executed.sum" in vals:
+            import json
+            json.dump({"source": src, "kernel": name, "gpu_time_ms": float(vals["gpu__time_duration.sum"]) if "gpu__time_duration.sum" in vals else None,
+                       "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
+                       "warp_instructions_per_launch": num("smsp__inst_executed.sum"), "units_per_launch": float(units) if units else None,
+                       "warp_inst_per_unit": num("smsp__inst_executed.sum") / float(units) if units else None,
+                       "issue_active_pct": float(vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan"))},
+                      open(dst.rsplit(".", 1)[0] + ".json", "w"), indent=1)
         if "dram__bytes_read.sum" in vals:
             fh.write("\nDRAM traffic per launch: read %s + write %s (%s).\n" % (vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"], unit[hdr.index("dram__bytes_read.sum")]))
         # opcode mix
-        rows = ncu_csv(src, "--page", "source", "--print-source", "sass")
+        rows = ncu_csv(src, "--page", "source", "--print-source", "sass", *pick)
         starts = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
         if starts:
             h = rows[starts[0]]
@@ -96,4 +108,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
     else:
-        report(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
+        report(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 and sys.argv[4] != "-" else None, sys.argv[5] if len(sys.argv) > 5 else None)
