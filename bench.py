@@ -173,9 +173,16 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
     r.lib().rfk_set_device(local_rank)
+    json_fd = 1
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL writes its version banner (and anything NCCL_DEBUG asks for) to file
+        # descriptor 1 when its first communicator comes up, so for the length of the run descriptor 1 is stderr and the
+        # line goes to a duplicate of the real stdout
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, which carries exactly one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     compiler = r.FlameCompiler(VARIATIONS)
@@ -325,7 +332,8 @@ def main():
                 line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the bench line must still print
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
