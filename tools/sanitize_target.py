@@ -42,6 +42,27 @@ print("hot map", info.tiles_x, info.tiles_y, info.hot_tiles, "binned with hints"
 flame.clear_hot_map()
 flame.set_options(**defaults)
 
+# region queues (kernel option staged_bins): plenty of room, exhausted queues (one chunk per region), a wider CTA, a longer
+# re-deal period; every case is checked against the direct path's binned count being positive and the density sum matching
+for kw, max_bytes in ((dict(staged_bins=8), None), (dict(staged_bins=8), 21 * 4096), (dict(staged_bins=9, block_width=512), None),
+                      (dict(staged_bins=10, deal_period=4), None), (dict(staged_bins=8, count_xforms=1), None)):
+    if max_bytes:
+        os.environ["RFK_STAGE_MAX_BYTES"] = str(max_bytes)
+    else:
+        os.environ.pop("RFK_STAGE_MAX_BYTES", None)
+    flame.set_options(**defaults)
+    flame.set_options(**kw)
+    flame.warmup(3, 1.2 / 60)
+    sb = r.DeviceBuffer(W * H * 16)
+    sb.zero_out()
+    n = flame.draw_to_bins(sb.ptr, W * H, W, 5) + flame.draw_to_bins(sb.ptr, W * H, W, 2)
+    dens = sb.download(np.float32, (H, W, 4))[..., 3].astype(np.float64).sum()
+    assert n > 0 and dens == n, (kw, n, dens)
+    print("staged", kw, "queue bytes", max_bytes, "binned", n)
+    sb.free()
+os.environ.pop("RFK_STAGE_MAX_BYTES", None)
+flame.set_options(**defaults)
+
 img, stats = flame.render_frame(W, H, max_draw_calls=1, drawing_passes=4, warmup_passes=3, supersample=2, filter_radius=0.75)
 print("supersampled frame", img.shape, stats.binned)
 
