@@ -144,7 +144,7 @@ static constexpr float EPS = (1e-10f);
 // RFK_MATH_MODE 0: libdevice functions (1-2 ulp), IEEE division and square root.
 // RFK_MATH_MODE 1: the same accuracy class against the 1e-5 parity contract at a fraction of the
 //   instructions: 2-ulp division / square root (compiler flags), sine and cosine on the SFU after a
-//   two-constant Cody-Waite reduction to [-pi, pi] (absolute error ~5e-7), denormals flushed, pow through lg2/ex2 while |y| <= 16 and x >= 0 (relative error < 3e-6, libdevice otherwise), a polynomial atan2
+//   two-constant Cody-Waite reduction to [-pi, pi] (absolute error ~5e-7), denormals flushed, pow through lg2/ex2 while |y| <= 16 and x is not negative (relative error < 3e-6, libdevice otherwise), a polynomial atan2
 //   (absolute error 1.3e-7), vec2 / scalar through one reciprocal.
 // RFK_MATH_MODE 2: --use_fast_math (SFU intrinsics with no range reduction; outside the parity contract).
 #if RFK_MATH_MODE == 1
@@ -182,8 +182,11 @@ __device__ __forceinline__ void rfk_sincos(float v, float* s, float* c) {
     *s = ::__sinf(r);
     *c = ::__cosf(r);
 }
+// `!(a < 0)` rather than `a >= 0`: a NaN base takes the two-SFU path as well (NaN in, NaN out). The reference never resets
+// a particle that went non-finite (the badval line of flame.glsl:70 is commented out), so on genomes that overflow — a
+// quarter of the stress genome's particles — every warp had lanes in libdevice's 65-instruction powf on every iteration.
 __device__ __forceinline__ float pow(float a, float b) {
-    if (a >= 0.0f && ::fabsf(b) <= 16.0f) return ::exp2f(b * ::__log2f(a));
+    if (!(a < 0.0f) && ::fabsf(b) <= 16.0f) return ::exp2f(b * ::__log2f(a));
     return RFK_POWF(a, b);
 }
 // atan2 from a degree-15 odd polynomial on [0, 1] (least-squares fit on Chebyshev nodes; absolute error 1.3e-7 in
