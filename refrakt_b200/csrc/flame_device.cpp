@@ -249,6 +249,8 @@ struct flame_device {
     unsigned int* stage_cursors = nullptr;
     unsigned int* stage_fill = nullptr;
     std::size_t stage_regions = 0, stage_capacity = 0;  // queues and chunks per queue the buffers were sized for
+    std::size_t stage_requested = 0;                    // chunks per queue asked for (more than stage_capacity when memory was short)
+    bool stage_unavailable = false;                     // automatic mode: no memory for the queues, draw directly
 
     ~flame_device() {
         cudaFree(hot_sums); cudaFree(hot_scratch); cudaFree(hot_bitmap);
@@ -733,7 +735,8 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
     }
     int stage_regions = 0, stage_shift = options_.staged_bins > 0 ? options_.staged_bins : 0;
     CUfunction draw_fn = d.draw;
-    if (options_.staged_bins < 0 && !options_.deterministic && !options_.warp_aggregate && !options_.l2_hints && W * H * sizeof(float4) >= (std::size_t(1) << 30)) {
+    if (options_.staged_bins < 0 && !d.stage_unavailable && !options_.deterministic && !options_.warp_aggregate && !options_.l2_hints &&
+        W * H * sizeof(float4) >= (std::size_t(1) << 30)) {
         // automatic: a histogram of 1 GiB or more (eight times the L2) is drawn through the queues, in at most 64 regions of
         // at least 2^22 bins (64 MB, half the L2; measured best on the 2.12 GB histogram of config 3: profiles/)
         int shift = 22;
@@ -759,15 +762,45 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         if (const char* e = std::getenv("RFK_STAGE_MAX_BYTES")) max_bytes = std::max<std::size_t>(1, std::strtoull(e, nullptr, 10));  // tests: exhausted queues
         max_bytes = std::min(max_bytes, std::size_t(31) << 30);  // record indices are 32-bit in the kernel
         capacity = std::max<std::size_t>(1, std::min(capacity, max_bytes / (chunk * sizeof(uint2)) / regions));
-        if (d.stage_regions != regions || d.stage_capacity != capacity) {
-            cudaFree(d.stage_records); cudaFree(d.stage_cursors); cudaFree(d.stage_fill);
-            d.stage_records = nullptr; d.stage_cursors = d.stage_fill = nullptr; d.stage_regions = d.stage_capacity = 0;
-            cuda_check(cudaMalloc(&d.stage_records, regions * capacity * chunk * sizeof(uint2)), "cudaMalloc(staging queues)");
-            cuda_check(cudaMalloc(&d.stage_cursors, regions * sizeof(unsigned int)), "cudaMalloc(staging cursors)");
-            cuda_check(cudaMalloc(&d.stage_fill, regions * capacity * sizeof(unsigned int)), "cudaMalloc(staging chunk fill table)");
-            cuda_check(cudaMemsetAsync(d.stage_cursors, 0, regions * sizeof(unsigned int), g_sim.stream), "clear staging cursors");
-            d.stage_regions = regions; d.stage_capacity = capacity;
+        if (d.stage_regions != regions || d.stage_requested != capacity) {
+            auto release = [&] {
+                cudaFree(d.stage_records); cudaFree(d.stage_cursors); cudaFree(d.stage_fill);
+                d.stage_records = nullptr; d.stage_cursors = d.stage_fill = nullptr; d.stage_regions = d.stage_capacity = d.stage_requested = 0;
+            };
+            const char* fail_above = std::getenv("RFK_STAGE_FAIL_ABOVE_BYTES");  // tests: pretend larger allocations fail
+            auto allocate = [&](std::size_t chunks) {
+                if (fail_above && regions * chunks * chunk * sizeof(uint2) > std::strtoull(fail_above, nullptr, 10)) return false;
+                return cudaMalloc(&d.stage_records, regions * chunks * chunk * sizeof(uint2)) == cudaSuccess &&
+                       cudaMalloc(&d.stage_cursors, regions * sizeof(unsigned int)) == cudaSuccess &&
+                       cudaMalloc(&d.stage_fill, regions * chunks * sizeof(unsigned int)) == cudaSuccess;
+            };
+            release();
+            // queues that do not fit the free memory are halved (what overflows is reduced directly); in the automatic mode a
+            // device without even 1 GiB to spare draws without staging
+            std::size_t chunks = capacity;
+            while (!allocate(chunks)) {
+                release();
+                cudaGetLastError();  // clear the allocation failure
+                chunks /= 2;
+                if (regions * chunks * chunk * sizeof(uint2) < (std::size_t(1) << 30) && regions * capacity * chunk * sizeof(uint2) >= (std::size_t(1) << 30)) { chunks = 0; break; }
+                if (chunks == 0) break;
+            }
+            if (chunks == 0) {
+                if (options_.staged_bins > 0) throw std::runtime_error("staged_bins: no device memory for the region queues");
+                d.stage_unavailable = true;
+            } else {
+                cuda_check(cudaMemsetAsync(d.stage_cursors, 0, regions * sizeof(unsigned int), g_sim.stream), "clear staging cursors");
+                d.stage_regions = regions; d.stage_capacity = chunks; d.stage_requested = capacity;
+            }
         }
+        if (d.stage_unavailable) {
+            draw_fn = d.draw;
+            stage_shift = 0;
+        }
+    }
+    if (stage_shift > 0) {
+        const std::size_t regions = d.stage_regions;
+        const int shift = stage_shift;
         stage_regions = (int)regions;
         p.stage_records = d.stage_records;
         p.stage_cursors = d.stage_cursors;

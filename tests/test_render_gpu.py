@@ -452,6 +452,43 @@ def test_staged_bins_reject_too_many_regions(gpu_ready, rfk, flame):
     buf.free()
 
 
+def test_staging_survives_a_device_short_of_memory(gpu_ready, rfk, flame, monkeypatch):
+    """the queues are halved until they fit (what overflows is reduced directly); with no room at all the automatic mode draws
+    without staging (one launch per call) and an explicit staged_bins fails loudly. Allocation failures are simulated."""
+    W = H = 8192
+    P, TS = 256 * 64, 16
+    out = []
+    for fail_above in (None, 8 << 20, 0):
+        if fail_above is None:
+            monkeypatch.delenv("RFK_STAGE_FAIL_ABOVE_BYTES", raising=False)
+        else:
+            monkeypatch.setenv("RFK_STAGE_FAIL_ABOVE_BYTES", str(fail_above))
+        flame.set_options(staged_bins=0)
+        flame.set_options(staged_bins=-1)  # a fresh device state: the earlier verdict on memory is forgotten
+        rfk.set_sim_parameters(P, TS, 64, seed=12)
+        flame.warmup(16, TSS)
+        buf = rfk.DeviceBuffer(W * H * 16)
+        buf.zero_out()
+        before = rfk.kernel_launch_count()
+        n = flame.draw_to_bins(buf.ptr, W * H, W, 16)
+        launches = rfk.kernel_launch_count() - before
+        n += flame.draw_to_bins(buf.ptr, W * H, W, 16)
+        out.append((buf.download(np.float32, (H, W, 4))[..., 3].copy(), n, launches))
+        buf.free()
+    assert [o[2] for o in out] == [2, 2, 1]
+    for d, n, _ in out[1:]:
+        assert n == out[0][1] and np.array_equal(d, out[0][0])
+    flame.set_options(staged_bins=22)
+    rfk.set_sim_parameters(P, TS, 64, seed=12)
+    flame.warmup(4, TSS)
+    buf = rfk.DeviceBuffer(W * H * 16)
+    with pytest.raises(rfk.RefraktError):
+        flame.draw_to_bins(buf.ptr, W * H, W, 4)
+    buf.free()
+    monkeypatch.delenv("RFK_STAGE_FAIL_ABOVE_BYTES")
+    flame.set_options(staged_bins=-1)
+
+
 def test_staging_is_automatic_for_a_histogram_of_one_gibibyte(gpu_ready, rfk, flame):
     """staged_bins = -1 (the default): a histogram of 1 GiB goes through the queues (one more launch per call: the
     accumulation kernel; the staged kernels are built on first use and see the parameters of the last warmup), a smaller
