@@ -52,7 +52,7 @@ struct rfk_iter_params {
 
 #define RFK_FIXED_SCALE 16777216.0f  // 2^24
 #define RFK_STAGE_CHUNK 512u         // records per chunk (4 KB); at least RFK_BLOCK, so one iteration of a CTA never spans three chunks
-#define RFK_STAGE_MAX_REGIONS 64u    // a 6-bit key for the in-warp match
+#define RFK_STAGE_MAX_REGIONS 64u
 #define RFK_STAGE_DEAD 0xffffffffu    // no chunk left in the region's queue: the samples of this chunk number are reduced directly
 
 __device__ __forceinline__ unsigned int rfk_hash32(unsigned int h) {
@@ -149,27 +149,6 @@ __device__ __forceinline__ float4 rfk_reduce_peers(unsigned int mask, unsigned i
         rel_pos >>= 1;
     }
     return v;
-}
-#endif
-
-#if RFK_STAGED_BINS
-// The lanes of `live` whose region equals this lane's: match.any restated for a 6-bit key as one vote and two
-// predicated logic operations per bit (MATCH.ANY held the MIO queue: mio_throttle 26 % -> 8 % of warp cycles, issue slots
-// 43 % -> 71 % busy). Every lane of the warp calls; a lane outside `live` gets a meaningless mask without its own bit.
-__device__ __forceinline__ unsigned int rfk_match_region(unsigned int live, unsigned int region) {
-    unsigned int peers = live;
-#pragma unroll
-    for (unsigned int bit = 1u; bit < RFK_STAGE_MAX_REGIONS; bit <<= 1) {
-        const bool set = region & bit;
-        const unsigned int v = __ballot_sync(0xffffffffu, set);
-        peers &= set ? v : ~v;
-    }
-    return peers;
-}
-__device__ __forceinline__ unsigned int rfk_lanemask_lt() {
-    unsigned int m;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
-    return m;
 }
 #endif
 
@@ -327,14 +306,13 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
             // (Tried and dropped: chunks of 32 records owned by a warp, numbered without atomics or barrier — the sectors of
             // 75 000 open chunks fill too slowly, L2 writes them back half empty: 3.4 GB written and 1.5 GB read per call
             // instead of 2.0 and 0.3.)
-            // All 32 lanes take part in the votes and the shuffle (a lane out of bounds computes on a junk region and is
-            // masked out of every group): no divergent-mask WARPSYNC around them.
-            const unsigned int st_region = ((unsigned int)idx >> p.stage_region_shift) & (RFK_STAGE_MAX_REGIONS - 1u);
-            const unsigned int peers = rfk_match_region(__ballot_sync(0xffffffffu, in_bounds), st_region);  // in-bounds lanes of the same region
-            const unsigned int rank = __popc(peers & rfk_lanemask_lt());
+            const unsigned int st_region = (unsigned int)idx >> p.stage_region_shift;  // junk where out of bounds, and unused there
+            // one shared-memory atomic per in-bounds lane. (Grouping the lanes of a region first, so that one lane adds for all:
+            // with MATCH.ANY the MIO queue was the limit, issue slots 43 % busy; with six votes on the 6-bit region number
+            // 83 % busy but 47 more instructions per iteration; the plain ATOMS — 2 cycles per lane on the LSU, which has the
+            // room — is 199 instead of 246 instructions per iteration and 1.73 instead of 2.19 ms per call.)
             unsigned int st_pos = 0;
-            if (in_bounds && rank == 0u) st_pos = atomicAdd(&st_fill[st_region], (unsigned int)__popc(peers));
-            st_pos = __shfl_sync(0xffffffffu, st_pos, __ffs(peers) - 1) + rank;
+            if (in_bounds) st_pos = atomicAdd(&st_fill[st_region], 1u);
             unsigned int* const st_base = &st_chunk[st_region][(st_pos / RFK_STAGE_CHUNK) & 3u];
             unsigned int st_rec = 0;
             if (in_bounds) {
