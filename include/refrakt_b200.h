@@ -155,7 +155,7 @@ typedef struct rfk_kernel_options {
     int32_t staged_bins;    /* histograms several times larger than L2: rfk_draw appends every sample as an 8-byte record to the
                                queue of its region (2^n consecutive bins) and a second kernel accumulates the queues region by
                                region, so the reductions meet in L2 instead of being DRAM read-modify-writes at random addresses.
-                               Same samples, same histogram. -1 = automatic (default): on for histograms of 1 GiB or more, in
+                               Same samples, same histogram. -1 = automatic (default): on for histograms of 512 MiB or more, in
                                at most 64 regions of 2^22 bins (64 MB) or larger; 0 = off; n = 8..24 = always on with regions of
                                2^n bins (at most 64 regions; excludes deterministic, warp_aggregate and l2_hints, which also
                                switch the automatic mode off). Queue memory: 16 GiB at most (RFK_STAGE_MAX_BYTES) */

@@ -69,7 +69,7 @@ struct kernel_options {
     int l2_hints = 0;             // histograms much larger than L2: evict-first reductions outside the hot map
     int staged_bins = -1;         // histograms much larger than L2: samples go to per-region queues (regions of 2^staged_bins bins,
                                   // 22 = 64 MB) and are accumulated region by region after the draw kernel; 0 = off;
-                                  // -1 = automatic: on for histograms of 1 GiB or more, in regions of 2^22 bins or larger
+                                  // -1 = automatic: on for histograms of 512 MiB or more, in regions of 2^22 bins or larger
     bool operator==(const kernel_options&) const = default;
 };
 

@@ -217,7 +217,7 @@ struct flame_device {
     CUmodule module = nullptr;
     CUfunction warm = nullptr, draw = nullptr, single_step = nullptr, select_xform = nullptr, bucket_index = nullptr, reference_pass = nullptr;
     float* cfp = nullptr;         // the module's __constant__ rfk_cfp[]: parameter slots that do not depend on the temporal sample
-    // staged_bins = -1 (automatic): the same kernels compiled with RFK_STAGED_BINS, built the first time a histogram of 1 GiB
+    // staged_bins = -1 (automatic): the same kernels compiled with RFK_STAGED_BINS, built the first time a histogram of 512 MiB
     // or more is drawn into; it has a constant bank of its own
     CUmodule staged_module = nullptr;
     CUfunction staged_draw = nullptr;
@@ -736,9 +736,10 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
     int stage_regions = 0, stage_shift = options_.staged_bins > 0 ? options_.staged_bins : 0;
     CUfunction draw_fn = d.draw;
     if (options_.staged_bins < 0 && !d.stage_unavailable && !options_.deterministic && !options_.warp_aggregate && !options_.l2_hints &&
-        W * H * sizeof(float4) >= (std::size_t(1) << 30)) {
-        // automatic: a histogram of 1 GiB or more (eight times the L2) is drawn through the queues, in at most 64 regions of
-        // at least 2^22 bins (64 MB, half the L2; measured best on the 2.12 GB histogram of config 3: profiles/)
+        W * H * sizeof(float4) >= (std::size_t(1) << 29)) {
+        // automatic: a histogram of 512 MiB or more (four times the L2) is drawn through the queues, in at most 64 regions of
+        // at least 2^22 bins (64 MB, half the L2; measured best on the 2.12 GB histogram of config 3). The crossover was measured
+        // (profiles/r01_staged_threshold_probe.json): 299 MB direct 1.89 ms per call / queued 3.16; 531 MB 3.64 / 3.21; 944 MB 5.37 / 3.23
         int shift = 22;
         while (((W * H + (std::size_t(1) << shift) - 1) >> shift) > 64) shift++;
         if (shift <= 24) {  // a record holds 24 bits of bin index

@@ -490,7 +490,7 @@ def test_staging_survives_a_device_short_of_memory(gpu_ready, rfk, flame, monkey
 
 
 def test_staging_is_automatic_for_a_histogram_of_one_gibibyte(gpu_ready, rfk, flame):
-    """staged_bins = -1 (the default): a histogram of 1 GiB goes through the queues (one more launch per call: the
+    """staged_bins = -1 (the default): a histogram of 512 MiB or more (here 1 GiB) goes through the queues (one more launch per call: the
     accumulation kernel; the staged kernels are built on first use and see the parameters of the last warmup), a smaller
     one does not; the samples are the same as with staging off"""
     W = H = 8192
