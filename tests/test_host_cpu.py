@@ -480,3 +480,32 @@ def test_variation_table_reader_survives_mutated_input(rfk, tmp_path):
         if f is not None:
             assert "vec4 dispatch" in f.glsl_source() and "rfk_draw" in f.cuda_source()
     assert ok > 10 and bad > 10
+
+
+@pytest.mark.parametrize("block", [128, 256, 512])
+def test_staging_ring_of_four_chunk_slots_never_aliases(block):
+    """The protocol of rfk_draw's region queues (csrc/chaos_kernels.cuh), modelled for one region of one CTA: per iteration up
+    to `block` samples draw consecutive numbers; the sample with number n mod 512 == 0 opens chunk n / 512 and publishes it in
+    slot (n / 512) mod 4 BEFORE the iteration's barrier; every sample reads the slot of its chunk AFTER that barrier, possibly
+    while the next iteration's openers are already writing (they only wait for the NEXT barrier). No reader may ever see a
+    slot overwritten by a later chunk, for any sequence of per-iteration counts."""
+    import random
+    rng = random.Random(block)
+    CH = 512
+    for trial in range(200):
+        counts = [rng.choice([0, 1, block // 3, block - 1, block]) if rng.random() < 0.5 else rng.randrange(block + 1) for _ in range(40)]
+        slots = [None] * 4
+        total = 0
+        prev_reads = []                                      # (slot, chunk) pairs the previous iteration's samples still read
+        for c in counts:
+            numbers = range(total, total + c)
+            opened = [n // CH for n in numbers if n % CH == 0]
+            for chunk in opened:                             # openers of this iteration run concurrently with the previous readers
+                for slot, want in prev_reads:
+                    assert slot != chunk % 4 or want == chunk, (block, counts, chunk)
+                slots[chunk % 4] = chunk
+            reads = sorted({(n // CH % 4, n // CH) for n in numbers})
+            for slot, want in reads:                         # after the barrier: every sample finds its own chunk
+                assert slots[slot] == want, (block, counts, want)
+            prev_reads = reads
+            total += c
