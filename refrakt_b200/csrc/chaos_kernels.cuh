@@ -423,8 +423,12 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #endif
 }
 
-extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_warm(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<false>(p); }
+#ifndef RFK_DRAW_ONLY
+#define RFK_DRAW_ONLY 0  // 1: the module holds rfk_draw alone (the staged kernels of the automatic mode, built on first use)
+#endif
 extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_draw(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<true>(p); }
+#if !RFK_DRAW_ONLY
+extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_warm(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<false>(p); }
 
 // The reference's own dispatch structure, restated for the GPU: shaders/flame.glsl:41-90 as ONE iteration per launch
 // on a (PPT / 256, TS) grid, particle and RNG state through global memory, one xform per 256-thread workgroup picked
@@ -523,3 +527,4 @@ extern "C" __global__ void rfk_bucket_index(int n, const float* __restrict__ xyz
     idx_out[i] = rfk_bin_index(xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 3], bp.ss_affine, bp.bin_w, bp.bin_h);
     pal_out[i] = (int)rfk_palette_index(xyzw[4 * i + 2]);
 }
+#endif  // !RFK_DRAW_ONLY

@@ -376,7 +376,7 @@ const std::vector<char>& flame::cubin() {
 
 // the same source with the staging path of rfk_draw compiled in (kernel option staged_bins = -1)
 std::vector<char> flame::staged_cubin() const {
-    const std::string off = "#define RFK_STAGED_BINS 0\n", on = "#define RFK_STAGED_BINS 1\n";
+    const std::string off = "#define RFK_STAGED_BINS 0\n", on = "#define RFK_STAGED_BINS 1\n#define RFK_DRAW_ONLY 1\n";  // rfk_draw alone: half the build time
     std::string source = cuda_source_;
     const std::size_t at = source.find(off);
     if (at == std::string::npos) throw std::runtime_error("staged_cubin: the kernels are already compiled with staging");
