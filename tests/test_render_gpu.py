@@ -489,6 +489,27 @@ def test_staging_survives_a_device_short_of_memory(gpu_ready, rfk, flame, monkey
     flame.set_options(staged_bins=-1)
 
 
+def test_render_frame_of_a_supersampled_8k_wide_histogram_goes_through_the_queues(gpu_ready, rfk, flame):
+    """the end-to-end entry point (rfk_render_frame, the call the CLI makes): a 4096 x 2048 image from a 2x supersampled
+    histogram (8192 x 4096 bins, 512 MiB) is drawn through the region queues by default — two launches per draw call — and
+    the float image equals the one rendered with staging off (same samples; colour sums differ by rounding order)"""
+    W, H = 4096, 2048
+    imgs, stats = [], []
+    for staged in (-1, 0):
+        flame.set_options(staged_bins=staged)
+        rfk.set_sim_parameters(256 * 256, 16, 64, seed=21)
+        img = np.empty((H, W, 4), dtype=np.float32)
+        before = rfk.kernel_launch_count()
+        _, st = flame.render_frame(W, H, max_draw_calls=3, drawing_passes=32, warmup_passes=8, image_out=img, supersample=2, filter_radius=0.5)
+        imgs.append(img)
+        stats.append((st.binned, st.draw_calls, rfk.kernel_launch_count() - before))
+    flame.set_options(staged_bins=-1)
+    assert stats[0][0] == stats[1][0] > 0 and stats[0][1] == stats[1][1] == 3
+    assert stats[0][2] - stats[1][2] == 3            # one accumulation kernel per draw call
+    assert np.isfinite(imgs[0]).all() and imgs[0][..., :3].max() > 0
+    assert np.allclose(imgs[0], imgs[1], rtol=1e-4, atol=1e-5)
+
+
 def test_staging_is_automatic_for_a_histogram_of_one_gibibyte(gpu_ready, rfk, flame):
     """staged_bins = -1 (the default): a histogram of 512 MiB or more (here 1 GiB) goes through the queues (one more launch per call: the
     accumulation kernel; the staged kernels are built on first use and see the parameters of the last warmup), a smaller
