@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RFK_ABI_VERSION 2
+#define RFK_ABI_VERSION 3
 
 enum {
     RFK_OK = 0,
@@ -136,6 +136,12 @@ const char* rfk_flame_glsl_source(const rfk_flame* f); /* flame_compiler::compil
 const char* rfk_flame_cuda_source(const rfk_flame* f); /* the translation unit handed to NVRTC */
 /* sm_100a cubin of the generated kernels; *size receives the byte count, buf may be NULL to query. Needs no GPU. */
 int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size);
+/* The further builds of the same kernels the library makes on first use: `staged` = rfk_draw with the region queues of
+ * kernel option staged_bins compiled in; `specialised` = the current parameter values compiled in (kernel option
+ * specialize). Translation unit and sm_100a cubin; need no GPU. */
+const char* rfk_flame_variant_source(rfk_flame* f, int staged, int specialised);
+int rfk_flame_get_variant_cubin(rfk_flame* f, int staged, int specialised, void* buf, size_t buf_len, size_t* size);
+int rfk_flame_uses_specialised(const rfk_flame* f); /* 1 when the last warmup chose the value-specialised kernels */
 
 /* Options of the generated kernels (no reference counterpart). Changing them rebuilds the module. */
 typedef struct rfk_kernel_options {
@@ -159,6 +165,13 @@ typedef struct rfk_kernel_options {
                                at most 64 regions of 2^22 bins (64 MB) or larger; 0 = off; n = 8..24 = always on with regions of
                                2^n bins (at most 64 regions; excludes deterministic, warp_aggregate and l2_hints, which also
                                switch the automatic mode off). Queue memory: 16 GiB at most (RFK_STAGE_MAX_BYTES) */
+    int32_t specialize;     /* value-specialised kernels: every parameter slot that is the same for all temporal samples (weights,
+                               variation amounts, parameters, colours; not the rotated affine coefficients) is compiled into
+                               rfk_warm / rfk_draw as a literal. The reference compiles one shader per genome STRUCTURE and edits
+                               values live (src/main.cpp:335-369); that generic build stays the one rfk_flame_load makes. 0 = generic
+                               kernels only; 1 = warmup rebuilds the specialised kernels (NVRTC, 1-2 s) whenever a value changed;
+                               2 = automatic (default): built the second time warmup runs with unchanged values. Same results to
+                               rounding: constants fold at compile time with IEEE arithmetic */
 } rfk_kernel_options;
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* out);
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* in);

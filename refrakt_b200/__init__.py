@@ -39,7 +39,7 @@ class XformInfo(C.Structure):
 
 class KernelOptions(C.Structure):
     _fields_ = [("math_mode", C.c_int32), ("fmad", C.c_int32), ("per_lane_xform", C.c_int32), ("warp_aggregate", C.c_int32),
-                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32), ("l2_hints", C.c_int32), ("staged_bins", C.c_int32)]
+                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32), ("l2_hints", C.c_int32), ("staged_bins", C.c_int32), ("specialize", C.c_int32)]
 
 
 class HotMapInfo(C.Structure):
@@ -111,6 +111,9 @@ SIGNATURES = {
     "rfk_flame_glsl_source": (_cp, [_vp]),
     "rfk_flame_cuda_source": (_cp, [_vp]),
     "rfk_flame_get_cubin": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "rfk_flame_variant_source": (_cp, [_vp, _i, _i]),
+    "rfk_flame_get_variant_cubin": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz)]),
+    "rfk_flame_uses_specialised": (_i, [_vp]),
     "rfk_flame_get_options": (_i, [_vp, C.POINTER(KernelOptions)]),
     "rfk_flame_set_options": (_i, [_vp, C.POINTER(KernelOptions)]),
     "rfk_flame_kernel_info": (_i, [_vp, _cp, _ipp, _ipp, _ipp]),
@@ -371,6 +374,21 @@ class Flame:
         buf = C.create_string_buffer(size.value)
         _check(lib().rfk_flame_get_cubin(self.handle, buf, size.value, C.byref(size)), "get_cubin")
         return buf.raw
+
+    def variant_source(self, staged=False, specialised=False) -> str:
+        r = lib().rfk_flame_variant_source(self.handle, int(staged), int(specialised))
+        if r is None:
+            raise RefraktError("variant_source: " + Flame.last_error())
+        return r.decode()
+
+    def variant_cubin(self, staged=False, specialised=False) -> bytes:
+        size = C.c_size_t()
+        _check(lib().rfk_flame_get_variant_cubin(self.handle, int(staged), int(specialised), None, 0, C.byref(size)), "get_variant_cubin")
+        buf = C.create_string_buffer(size.value)
+        _check(lib().rfk_flame_get_variant_cubin(self.handle, int(staged), int(specialised), buf, size.value, C.byref(size)), "get_variant_cubin")
+        return buf.raw
+
+    def uses_specialised(self) -> bool: return bool(_check(lib().rfk_flame_uses_specialised(self.handle), "uses_specialised"))
 
     def options(self) -> KernelOptions:
         o = KernelOptions()

@@ -333,10 +333,44 @@ int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size) {
     });
 }
 
+int rfk_flame_get_variant_cubin(rfk_flame* f, int staged, int specialised, void* buf, size_t buf_len, size_t* size) {
+    return guarded([&]() -> int {
+        if (!f || !size) throw std::invalid_argument("null argument");
+        flame* fl = F(f);
+        std::vector<float> table;
+        if (specialised) {
+            auto fp = fl->copy_flame_data_to_buffer();
+            table = fl->constant_table(fp.data());
+        }
+        const auto image = fl->variant_cubin(staged != 0, specialised ? &table : nullptr);
+        *size = image.size();
+        if (buf) {
+            if (buf_len < image.size()) throw std::invalid_argument("cubin buffer too small");
+            std::memcpy(buf, image.data(), image.size());
+        }
+        return RFK_OK;
+    });
+}
+const char* rfk_flame_variant_source(rfk_flame* f, int staged, int specialised) {
+    if (!f) return nullptr;
+    try {
+        flame* fl = F(f);
+        std::vector<float> table;
+        if (specialised) {
+            auto fp = fl->copy_flame_data_to_buffer();
+            table = fl->constant_table(fp.data());
+        }
+        t_scratch = fl->variant_source(staged != 0, specialised ? &table : nullptr);
+        return t_scratch.c_str();
+    } catch (const std::exception& e) { fail(RFK_E_INVALID, e.what()); return nullptr; }
+}
+
+int rfk_flame_uses_specialised(const rfk_flame* f) { return f ? (flame_uses_baked(*F(f)) ? 1 : 0) : fail(RFK_E_INVALID, "null flame"); }
+
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* o) {
     if (!f || !o) return fail(RFK_E_INVALID, "null argument");
     const auto& k = F(f)->options();
-    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks, k.block_width, k.deal_period, k.l2_hints, k.staged_bins};
+    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks, k.block_width, k.deal_period, k.l2_hints, k.staged_bins, k.specialize};
     return RFK_OK;
 }
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
@@ -349,6 +383,8 @@ int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
     k.deal_period = i->deal_period;
     k.l2_hints = i->l2_hints ? 1 : 0;
     k.staged_bins = i->staged_bins;
+    k.specialize = i->specialize;
+    if (k.specialize < 0 || k.specialize > 2) return fail(RFK_E_INVALID, "specialize must be 0 (off), 1 (always) or 2 (automatic)");
     if (k.staged_bins != 0 && k.staged_bins != -1 && (k.staged_bins < 8 || k.staged_bins > 24))
         return fail(RFK_E_INVALID, "staged_bins must be -1 (automatic), 0 (off) or the log2 of the bins per region, 8 to 24");
     if (k.staged_bins > 0 && (k.deterministic || k.warp_aggregate || k.l2_hints)) return fail(RFK_E_INVALID, "staged_bins excludes deterministic, warp_aggregate and l2_hints");

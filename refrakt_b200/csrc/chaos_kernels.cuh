@@ -22,6 +22,22 @@
 
 using namespace rfk_glsl;
 
+// This CTA's copy of the parameter block: fp[] (flame.glsl:44-48) and the rotated affine coefficients as one float4 per
+// xform (device_prelude.cuh). `src` is a row of fp_inflated, or fp itself. The caller synchronises.
+__device__ __forceinline__ void rfk_stage_params(const float* __restrict__ src) {
+    for (int i = threadIdx.x; i < RFK_TOTAL_PARAMS; i += blockDim.x) rfk_glsl::fp[i] = src[i];
+    for (int i = threadIdx.x; i <= RFK_NUM_XFORMS; i += blockDim.x) {
+        const int s = rfk_affine_slot[i];
+        if (s >= 0) rfk_aff[i] = make_float4(src[s], src[s + 1], src[s + 2], src[s + 3]);
+    }
+}
+
+// dispatch(v, xform) of the generated text (variation_table.cpp:222-263) with the picked xform's rotated coefficients
+template <bool first_run>
+__device__ __forceinline__ vec4 dispatch(vec3 v, int xform, rfk_rng& rs) {
+    return dispatch_a<first_run>(v, xform, rs, rfk_aff[xform + 1]);
+}
+
 struct rfk_iter_params {
     float4* particles;                  // [P] (x, y, colour, 0): pos_in/pos_out of buffers.glsl:1-9
     uint4* rng;                         // [P] JSF32 state per thread slot (random.glsl:1-4)
@@ -172,7 +188,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     const unsigned int ts = blockIdx.x / blocks_per_ts;                  // gl_WorkGroupID.y
     const size_t slot = (size_t)blockIdx.x * RFK_BLOCK + tid;            // ts * ppt + gl_GlobalInvocationID.x
 
-    for (int i = tid; i < RFK_TOTAL_PARAMS; i += RFK_BLOCK) rfk_glsl::fp[i] = p.fp_inflated[(size_t)ts * RFK_TOTAL_PARAMS + i];
+    rfk_stage_params(p.fp_inflated + (size_t)ts * RFK_TOTAL_PARAMS);
     if (DRAW) for (int i = tid; i < 256; i += RFK_BLOCK) pal[i] = p.palette[i];
 #if RFK_COUNT_XFORMS
     if (tid <= RFK_NUM_XFORMS) xcount[tid] = 0;
@@ -272,6 +288,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
   #endif
         }
 #endif
+        __builtin_assume(xid >= 0 && xid < (RFK_NUM_XFORMS > 0 ? RFK_NUM_XFORMS : 1));  // get_xform_id() returns nothing else: no clamp before the jump table
         vec4 r = dispatch<false>(vec3(x, y, c), xid, rs);
         x = r.x; y = r.y; c = r.z;  // flame.glsl:72
 
@@ -427,9 +444,13 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #define RFK_DRAW_ONLY 0  // 1: the module holds rfk_draw alone (the staged kernels of the automatic mode, built on first use)
 #endif
 extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_draw(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<true>(p); }
+#ifndef RFK_HOT_ONLY
+#define RFK_HOT_ONLY 0   // 1: rfk_warm, rfk_draw and rfk_single_step only (the value-specialised build of kernel option `specialize`)
+#endif
 #if !RFK_DRAW_ONLY
 extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_warm(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<false>(p); }
 
+#if !RFK_HOT_ONLY
 // The reference's own dispatch structure, restated for the GPU: shaders/flame.glsl:41-90 as ONE iteration per launch
 // on a (PPT / 256, TS) grid, particle and RNG state through global memory, one xform per 256-thread workgroup picked
 // by its first thread, shuffle-buffer gather / scatter (flame.glsl:31-37, :55-61). Not the product path: it is the
@@ -458,7 +479,7 @@ extern "C" __global__ void __launch_bounds__(256) rfk_reference_pass(const __gri
     const unsigned int gid = blockIdx.x * 256 + threadIdx.x;        // gl_GlobalInvocationID.x
     const size_t base = (size_t)blockIdx.y * p.ppt;                 // gl_WorkGroupID.y * gl_WorkGroupSize.x * gl_NumWorkGroups.x
     rfk_rng rs = p.rng[base + gid];                                 // load_random_state()
-    for (int k = threadIdx.x; k < RFK_TOTAL_PARAMS; k += 256) rfk_glsl::fp[k] = p.fp_inflated[(size_t)blockIdx.y * RFK_TOTAL_PARAMS + k];
+    rfk_stage_params(p.fp_inflated + (size_t)blockIdx.y * RFK_TOTAL_PARAMS);
     pal[threadIdx.x] = p.palette[threadIdx.x];
     __syncthreads();
     if (threadIdx.x == 0) xid = get_xform_id(rfk_randf(rs));      // flame.glsl:51-53
@@ -494,11 +515,13 @@ extern "C" __global__ void __launch_bounds__(256) rfk_reference_pass(const __gri
     p.rng[base + gid] = rs;                                         // save_random_state()
 }
 
+#endif  // !RFK_HOT_ONLY
+
 // Test hook: one dispatch(v, xid) per thread on caller-supplied particles, RNG states
 // and parameter block — the single-step level of the parity contract.
 extern "C" __global__ void rfk_single_step(int n, const float* __restrict__ xyz, const int* __restrict__ xid, uint4* rng,
                                            const float* __restrict__ fp, int first_run, float4* out) {
-    for (int k = threadIdx.x; k < RFK_TOTAL_PARAMS; k += blockDim.x) rfk_glsl::fp[k] = fp[k];
+    rfk_stage_params(fp);
     __syncthreads();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -509,9 +532,10 @@ extern "C" __global__ void rfk_single_step(int n, const float* __restrict__ xyz,
     rng[i] = rs;
 }
 
+#if !RFK_HOT_ONLY
 // Test hook: xform selection for caller-supplied ratios (xform_select.tpl.glsl).
 extern "C" __global__ void rfk_select_xform(int n, const float* __restrict__ ratio, const float* __restrict__ fp, int* out) {
-    for (int k = threadIdx.x; k < RFK_TOTAL_PARAMS; k += blockDim.x) rfk_glsl::fp[k] = fp[k];
+    rfk_stage_params(fp);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = get_xform_id(ratio[i]);  // the generated if-chain, as the hot kernels call it
@@ -527,4 +551,5 @@ extern "C" __global__ void rfk_bucket_index(int n, const float* __restrict__ xyz
     idx_out[i] = rfk_bin_index(xyzw[4 * i], xyzw[4 * i + 1], xyzw[4 * i + 3], bp.ss_affine, bp.bin_w, bp.bin_h);
     pal_out[i] = (int)rfk_palette_index(xyzw[4 * i + 2]);
 }
+#endif  // !RFK_HOT_ONLY
 #endif  // !RFK_DRAW_ONLY

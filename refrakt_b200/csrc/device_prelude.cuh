@@ -11,6 +11,12 @@ typedef uint4 rfk_rng;  // (a, b, c, d) = local_random_state.xyzw (random.glsl:1
 // flame.glsl:27 `shared float fp[1024]`: this CTA's temporal sample of the parameter buffer.
 // Namespace scope, so that every fp[k] of the generated code is one LDS with an immediate offset.
 __shared__ float fp[RFK_TOTAL_PARAMS + 1];
+// The only slots that differ between temporal samples are the four rotated affine coefficients (a, b, c, d) of every
+// xform (animate.tpl.glsl:42-49). They are kept a second time as one float4 per xform — [0] the final xform, [1 + i] xform i —
+// so the kernel fetches the picked xform's coefficients with ONE 128-bit read whose address comes straight from the pick,
+// issued before the switch; the generated text names them RFK_AFF(xform, component) (compile_flame_cuda).
+__shared__ float4 rfk_aff[RFK_NUM_XFORMS + 1];
+#define RFK_AFF(xform, component) rfk_A.component
 
 // Packed FP32 (sm_100: FFMA2 / FMUL2 / FADD2, `fma.rn.f32x2`): one instruction does the x and the y lane of a vec2
 // operation — the same FP32 rate as two scalar instructions but ONE issue slot, and the kernels are issue bound

@@ -70,6 +70,11 @@ struct kernel_options {
     int staged_bins = -1;         // histograms much larger than L2: samples go to per-region queues (regions of 2^staged_bins bins,
                                   // 22 = 64 MB) and are accumulated region by region after the draw kernel; 0 = off;
                                   // -1 = automatic: on for histograms of 512 MiB or more, in regions of 2^22 bins or larger
+    int specialize = 2;           // value-specialised kernels: every parameter slot that is the same for all temporal samples is compiled in
+                                  // as a literal (operand-form immediates instead of constant-bank loads, branches on parameters folded).
+                                  // 0 = off (one module per genome structure, as the reference's one shader per genome);
+                                  // 1 = rebuilt by warmup() whenever a value changed; 2 = automatic (default): built the second time
+                                  // warmup() runs with unchanged values (stills, animations, benchmarks), generic kernels meanwhile
     bool operator==(const kernel_options&) const = default;
 };
 
@@ -160,7 +165,11 @@ struct flame {
     const std::string& glsl_source() const { return glsl_source_; }
     const std::string& cuda_source() const { return cuda_source_; }
     const kernel_options& options() const { return options_; }
-    std::vector<char> staged_cubin() const;  // the kernels with rfk_draw's staging path compiled in (staged_bins = -1)
+    // the translation unit of a kernel variant: `staged` compiles rfk_draw's region queues in (rfk_draw alone); `baked`, when
+    // not null, holds the 4 * size constants of rfk_cfp[] and replaces every rfk_cfp[k] of the text with its value
+    std::string variant_source(bool staged, const std::vector<float>* baked) const;
+    std::vector<char> variant_cubin(bool staged, const std::vector<float>* baked) const;
+    std::vector<float> constant_table(const float* fp) const;  // the contents of rfk_cfp[] for the parameter buffer `fp`
     // Rebuilds the CUDA module with new options (the structure of the genome is fixed
     // after load, only values change without a rebuild: src/flame.hpp, main.cpp:335-369).
     bool set_options(const kernel_options& opt);

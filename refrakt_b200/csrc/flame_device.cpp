@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <nvrtc.h>
 
+#include <cctype>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -217,13 +219,22 @@ struct flame_device {
     CUmodule module = nullptr;
     CUfunction warm = nullptr, draw = nullptr, single_step = nullptr, select_xform = nullptr, bucket_index = nullptr, reference_pass = nullptr;
     float* cfp = nullptr;         // the module's __constant__ rfk_cfp[]: parameter slots that do not depend on the temporal sample
-    // staged_bins = -1 (automatic): the same kernels compiled with RFK_STAGED_BINS, built the first time a histogram of 512 MiB
-    // or more is drawn into; it has a constant bank of its own
-    CUmodule staged_module = nullptr;
-    CUfunction staged_draw = nullptr;
-    float* staged_cfp = nullptr;
     std::size_t cfp_floats = 0;
-    std::vector<float> cfp_staging;  // host copy of the last upload (slots, then reciprocals)
+    std::vector<float> cfp_staging;  // host copy of the last upload (slots, reciprocals, 1 - slot, slot products)
+    // Further builds of the same kernels, made on first use. [staged][baked]:
+    //  staged — rfk_draw compiled with RFK_STAGED_BINS (staged_bins = -1, automatic: the first time a histogram of 512 MiB or
+    //           more is drawn into); holds rfk_draw alone;
+    //  baked  — every rfk_cfp[k] of the text replaced by its current value (kernel option `specialize`); holds rfk_warm and
+    //           rfk_draw (and rfk_single_step for the parity tests) and has no constant bank to upload.
+    struct variant {
+        CUmodule module = nullptr;
+        CUfunction warm = nullptr, draw = nullptr, single_step = nullptr;
+        float* cfp = nullptr;          // null for baked variants
+        std::vector<float> values;     // baked variants: the constants compiled in
+    };
+    variant variants[2][2];            // [0][0] stays empty: that is `module` above
+    std::vector<float> previous_constants;  // rfk_cfp values of the warmup before the last one (specialize = 2)
+    bool use_baked = false;                 // decided by warmup(): the baked variants match the uploaded parameters
     float4* particles = nullptr;
     float4* swap = nullptr;  // reference pass mode: swap_buffer_
     float* fp = nullptr;
@@ -256,7 +267,9 @@ struct flame_device {
         cudaFree(hot_sums); cudaFree(hot_scratch); cudaFree(hot_bitmap);
         cudaFree(stage_records); cudaFree(stage_cursors); cudaFree(stage_fill);
         if (module) driver().ModuleUnload(module);
-        if (staged_module) driver().ModuleUnload(staged_module);
+        for (auto& row : variants)
+            for (auto& v : row)
+                if (v.module) driver().ModuleUnload(v.module);
         cudaFree(particles); cudaFree(swap); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
         cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
     }
@@ -325,6 +338,11 @@ bool flame::do_common_init(const flame_compiler& fc) {
 
 bool flame::set_options(const kernel_options& opt) {
     if (opt == options_) return true;
+    {   // `specialize` alone does not change the generic module
+        kernel_options same = opt;
+        same.specialize = options_.specialize;
+        if (same == options_) { options_.specialize = opt.specialize; needs_update_ = true; return true; }
+    }
     kernel_options old = options_;
     options_ = opt;
     rebuild_cuda_source();
@@ -374,14 +392,88 @@ const std::vector<char>& flame::cubin() {
     return cubin_;
 }
 
-// the same source with the staging path of rfk_draw compiled in (kernel option staged_bins = -1)
-std::vector<char> flame::staged_cubin() const {
-    const std::string off = "#define RFK_STAGED_BINS 0\n", on = "#define RFK_STAGED_BINS 1\n#define RFK_DRAW_ONLY 1\n";  // rfk_draw alone: half the build time
+// C literal of a binary32 value, exact (hexadecimal floating literal; non-finite values through the compiler's builtins)
+static std::string float_literal(float v) {
+    if (std::isnan(v)) return "__builtin_nanf(\"\")";
+    if (std::isinf(v)) return v > 0 ? "__builtin_huge_valf()" : "(-__builtin_huge_valf())";
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "(%af)", (double)v);
+    return buf;
+}
+
+// The translation unit of a kernel variant, derived from the generic one by text:
+//  staged: `#define RFK_STAGED_BINS 1` and rfk_draw alone (half the build time);
+//  baked:  every `rfk_cfp[k]` (k is always a literal in the generated text) becomes the value of that slot, so the compiler
+//          sees the genome's weights, variation amounts, parameters and their host-derived companions as immediates: the
+//          constant-bank loads (LDC / LDCU, a tenth of the instructions of the shipped genome's rfk_draw) disappear, the
+//          cumulative weights of get_xform_id() fold into compare immediates, and selects on parameters
+//          (`rfk_cfp[n] == 0 ? ... : ...`) fold away. The four rotated affine coefficients of every xform differ between
+//          temporal samples and stay in shared memory (fp[k]).
+std::string flame::variant_source(bool staged, const std::vector<float>* baked) const {
     std::string source = cuda_source_;
-    const std::size_t at = source.find(off);
-    if (at == std::string::npos) throw std::runtime_error("staged_cubin: the kernels are already compiled with staging");
-    source.replace(at, off.size(), on);
-    return compile_with_bounds(source, options_);
+    if (staged) {
+        const std::string off = "#define RFK_STAGED_BINS 0\n", on = "#define RFK_STAGED_BINS 1\n#define RFK_DRAW_ONLY 1\n";
+        const std::size_t at = source.find(off);
+        if (at == std::string::npos) throw std::runtime_error("variant_source: the kernels are already compiled with staging");
+        source.replace(at, off.size(), on);
+    }
+    if (baked) {
+        const std::string decl_head = "extern \"C\" { __constant__ float rfk_cfp[";
+        const std::size_t decl = source.find(decl_head);
+        if (decl == std::string::npos) throw std::runtime_error("variant_source: no rfk_cfp declaration in the generated text");
+        const std::size_t decl_end = source.find('\n', decl);
+        source.replace(decl, decl_end - decl, "#define RFK_BAKED 1  // rfk_cfp[] compiled in as literals\n#define RFK_HOT_ONLY 1");
+        // `e RFK_DIVC(n, r)` (device_prelude.cuh) names its slots inside a macro: expanded here, so the pass below sees them
+        for (std::size_t at = source.find("RFK_DIVC("); at != std::string::npos; at = source.find("RFK_DIVC(", at + 1)) {
+            std::size_t j = at + 9, comma = source.find(',', j), close = source.find(')', j);
+            if (comma == std::string::npos || close == std::string::npos || comma > close || !std::isdigit((unsigned char)source[j])) continue;  // the macro's own definition
+            std::size_t r0 = comma + 1;
+            while (r0 < close && source[r0] == ' ') r0++;
+            const std::string n = source.substr(j, comma - j), r = source.substr(r0, close - r0);
+            source.replace(at, close + 1 - at, options_.math_mode == 0 ? "/ rfk_cfp[" + n + "]" : "* rfk_cfp[" + r + "]");
+        }
+        // An xform that does not rotate (rotation_frequency 0: animate.tpl.glsl multiplies its angle by it) has the same four
+        // coefficients in every temporal sample: RFK_AFF(i, c) of such an xform is a literal as well, and the kernel's
+        // 128-bit read for it is dead code.
+        auto bake_affine = [&](const xform_slots& m, int index) {
+            if ((std::size_t)m.rotation_frequency >= baked->size() || (*baked)[m.rotation_frequency] != 0.0f) return;
+            for (int a = 0; a < 4; a++) {
+                const std::string token = "RFK_AFF(" + std::to_string(index) + ", " + std::string(1, "xyzw"[a]) + ")";
+                const std::string value = float_literal((*baked)[m.affine[a]]);
+                for (std::size_t at = source.find(token); at != std::string::npos; at = source.find(token, at + value.size())) source.replace(at, token.size(), value);
+            }
+        };
+        for (std::size_t i = 0; i < buffer_map_.xforms.size(); i++) bake_affine(buffer_map_.xforms[i], (int)i);
+        if (buffer_map_.final_xform) bake_affine(*buffer_map_.final_xform, -1);
+        std::string out;
+        out.reserve(source.size() + 16 * 1024);
+        const std::string key = "rfk_cfp[";
+        std::size_t pos = 0;
+        for (;;) {
+            const std::size_t at = source.find(key, pos);
+            if (at == std::string::npos) break;
+            const bool ident_before = at > 0 && (std::isalnum((unsigned char)source[at - 1]) || source[at - 1] == '_');
+            std::size_t j = at + key.size(), k = 0;
+            bool digits = false;
+            while (j < source.size() && std::isdigit((unsigned char)source[j])) { k = k * 10 + (source[j] - '0'); j++; digits = true; }
+            if (ident_before || !digits || j >= source.size() || source[j] != ']') {  // a comment or another identifier: leave it
+                out.append(source, pos, at + key.size() - pos);
+                pos = at + key.size();
+                continue;
+            }
+            if (k >= baked->size()) throw std::runtime_error("variant_source: rfk_cfp index outside the parameter table");
+            out.append(source, pos, at - pos);
+            out += float_literal((*baked)[k]);
+            pos = j + 1;
+        }
+        out.append(source, pos, std::string::npos);
+        source = std::move(out);
+    }
+    return source;
+}
+
+std::vector<char> flame::variant_cubin(bool staged, const std::vector<float>* baked) const {
+    return compile_with_bounds(variant_source(staged, baked), options_);
 }
 
 void flame::reset_animation() { needs_update_ = true; }
@@ -454,20 +546,32 @@ static void ensure_module(flame& f) {
     d.cfp_floats = cfp_bytes / sizeof(float);
 }
 
-static void ensure_staged_module(flame& f) {
+// builds (on first use) and returns a further variant of the kernels; a baked variant whose values are stale is rebuilt
+static flame_device::variant& ensure_variant(flame& f, bool staged, bool baked) {
     flame_device& d = *f.device();
-    if (d.staged_module) return;
+    flame_device::variant& v = d.variants[staged][baked];
+    if (v.module && (!baked || v.values == d.cfp_staging)) return v;
     const auto& api = driver();
-    const std::vector<char> image = f.staged_cubin();
-    cu_check(api.ModuleLoadData(&d.staged_module, image.data()), "cuModuleLoadData(staged)");
-    cu_check(api.ModuleGetFunction(&d.staged_draw, d.staged_module, "rfk_draw"), "rfk_draw(staged)");
-    CUdeviceptr cfp = 0;
-    std::size_t cfp_bytes = 0;
-    cu_check(api.ModuleGetGlobal(&cfp, &cfp_bytes, d.staged_module, "rfk_cfp"), "rfk_cfp(staged)");
-    d.staged_cfp = reinterpret_cast<float*>(cfp);
-    if (!d.cfp_staging.empty())  // the parameters of the last warmup
-        cuda_check(cudaMemcpyAsync(d.staged_cfp, d.cfp_staging.data(), std::min(cfp_bytes, d.cfp_staging.size() * sizeof(float)), cudaMemcpyHostToDevice, g_sim.stream),
-                   "upload constant parameters");
+    if (v.module) { api.ModuleUnload(v.module); v = flame_device::variant{}; }
+    const std::vector<char> image = f.variant_cubin(staged, baked ? &d.cfp_staging : nullptr);
+    cu_check(api.ModuleLoadData(&v.module, image.data()), "cuModuleLoadData(variant)");
+    cu_check(api.ModuleGetFunction(&v.draw, v.module, "rfk_draw"), "rfk_draw(variant)");
+    if (!staged) {
+        cu_check(api.ModuleGetFunction(&v.warm, v.module, "rfk_warm"), "rfk_warm(variant)");
+        cu_check(api.ModuleGetFunction(&v.single_step, v.module, "rfk_single_step"), "rfk_single_step(variant)");
+    }
+    if (baked) {
+        v.values = d.cfp_staging;
+    } else {
+        CUdeviceptr cfp = 0;
+        std::size_t cfp_bytes = 0;
+        cu_check(api.ModuleGetGlobal(&cfp, &cfp_bytes, v.module, "rfk_cfp"), "rfk_cfp(variant)");
+        v.cfp = reinterpret_cast<float*>(cfp);
+        if (!d.cfp_staging.empty())  // the parameters of the last warmup
+            cuda_check(cudaMemcpyAsync(v.cfp, d.cfp_staging.data(), std::min(cfp_bytes, d.cfp_staging.size() * sizeof(float)), cudaMemcpyHostToDevice, g_sim.stream),
+                       "upload constant parameters");
+    }
+    return v;
 }
 
 static void ensure_buffers(flame& f) {
@@ -515,23 +619,31 @@ static void launch(CUfunction fn, unsigned grid, unsigned block, void** args) {
     count_launch(1);
 }
 
-// the kernels read every slot that is the same for all temporal samples from constant memory (rfk_cfp, see compile_flame_cuda)
-static void upload_constant_params(flame_device& d, const float* fp) {
-    if (!d.cfp || !d.cfp_floats) return;
-    // four quarters: the slots; their reciprocals, read by `e / slot` in the generated text (RFK_DIVC); 1 - slot and
-    // slot[i - 1] * slot[i], the two constants of the colour blend (RFK_MIXC, indexed by the colour-speed slot)
-    const std::size_t size = std::min<std::size_t>(d.cfp_floats / 4, flame::PARAM_BUFFER);
-    d.cfp_staging.resize(4 * size);
+// The table behind `rfk_cfp[]` in the generated text (compile_flame_cuda), four quarters of max(1, buffer map size) floats:
+// the slots; their reciprocals, read by `e / slot` (RFK_DIVC); 1 - slot and slot[i - 1] * slot[i], the two constants of
+// the colour blend (RFK_MIXC, indexed by the colour-speed slot). Pure host arithmetic in binary32.
+std::vector<float> flame::constant_table(const float* fp) const {
+    const std::size_t size = std::min<std::size_t>(std::max(1, buffer_map_.size), PARAM_BUFFER);
+    std::vector<float> t(4 * size);
     for (std::size_t i = 0; i < size; i++) {
         volatile float prod = i ? fp[i - 1] * fp[i] : 0.0f;  // rounded to binary32, like the device's FMUL
-        d.cfp_staging[i] = fp[i];
-        d.cfp_staging[size + i] = 1.0f / fp[i];
-        d.cfp_staging[2 * size + i] = 1.0f - fp[i];
-        d.cfp_staging[3 * size + i] = prod;
+        t[i] = fp[i];
+        t[size + i] = 1.0f / fp[i];
+        t[2 * size + i] = 1.0f - fp[i];
+        t[3 * size + i] = prod;
     }
-    cuda_check(cudaMemcpyAsync(d.cfp, d.cfp_staging.data(), 4 * size * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
-    if (d.staged_cfp)
-        cuda_check(cudaMemcpyAsync(d.staged_cfp, d.cfp_staging.data(), 4 * size * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
+    return t;
+}
+
+// the generic kernels read every slot that is the same for all temporal samples from constant memory (rfk_cfp)
+static void upload_constant_params(flame& f, const float* fp) {
+    flame_device& d = *f.device();
+    if (!d.cfp || !d.cfp_floats) return;
+    d.cfp_staging = f.constant_table(fp);
+    const std::size_t bytes = std::min(d.cfp_floats, d.cfp_staging.size()) * sizeof(float);
+    cuda_check(cudaMemcpyAsync(d.cfp, d.cfp_staging.data(), bytes, cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
+    if (float* staged_cfp = d.variants[1][0].cfp)
+        cuda_check(cudaMemcpyAsync(staged_cfp, d.cfp_staging.data(), bytes, cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
 }
 
 static rfk_iter_params_host base_params(flame& f) {
@@ -561,7 +673,7 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
 
     auto buf = copy_flame_data_to_buffer();
     cuda_check(cudaMemcpyAsync(d.fp, buf.data(), PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
-    upload_constant_params(d, buf.data());
+    upload_constant_params(*this, buf.data());
     cuda_check(cudaMemcpyAsync(d.palette, palette.data(), 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
     cuda_check(cudaMemsetAsync(d.counters, 0, 64 * sizeof(unsigned long long), g_sim.stream), "clear counters");
     // the host arrays above are stack / member storage: finish the copies before returning control
@@ -570,11 +682,20 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
 
     // the re-deal keys restart with every warmup, so a run is reproducible from (seed, parameters) alone
     d.deal_counter = 0x5EED0001u ^ (unsigned int)(g_sim.seed * 0x9E3779B9ull);
+    // kernel option `specialize`: 1 = the value-specialised kernels always (rebuilt when a value changed since they were
+    // built); 2 = once these values have been seen by two warmups in a row (a still rendered repeatedly, an animation whose
+    // frames only rotate affines, a benchmark) or while the ones built earlier still match
+    const bool seen_before = d.previous_constants == d.cfp_staging;
+    const bool have_match = d.variants[0][1].module && d.variants[0][1].values == d.cfp_staging;
+    d.use_baked = !d.cfp_staging.empty() && (options_.specialize == 1 || (options_.specialize == 2 && (seen_before || have_match)));
+    d.previous_constants = d.cfp_staging;
+    CUfunction warm_fn = d.use_baked ? ensure_variant(*this, false, true).warm : d.warm;
+
     rfk_iter_params_host p = base_params(*this);
     p.first_run = 1;
     p.num_iter = (int)num_passes;
     void* args[] = {&p};
-    launch(d.warm, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
+    launch(warm_fn, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
     cuda_check(cudaStreamSynchronize(g_sim.stream), "warmup");
     d.binned_reported = 0;
     d.warmed = true;
@@ -637,7 +758,7 @@ void flame::reference_warmup(std::size_t num_passes, float tss_width, const std:
     needs_update_ = false;
     auto buf = copy_flame_data_to_buffer();
     cuda_check(cudaMemcpyAsync(d.fp, buf.data(), PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
-    upload_constant_params(d, buf.data());
+    upload_constant_params(*this, buf.data());
     cuda_check(cudaMemcpyAsync(d.palette, palette.data(), 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
     cuda_check(cudaMemsetAsync(d.counters, 0, 64 * sizeof(unsigned long long), g_sim.stream), "clear counters");
     kernels::animate(d.fp, d.fp_inflated, buffer_map_.size, (int)g_sim.temporal_samples, tss_width, d.anim, d.anim_count, g_sim.stream);
@@ -696,6 +817,8 @@ std::size_t flame::reference_draw_to_bins(float* bins, std::size_t bins_len, std
     return (std::size_t)delta;
 }
 
+bool flame_uses_baked(const flame& f) { return const_cast<flame&>(f).device() && const_cast<flame&>(f).device()->use_baked; }
+
 void flame_copy_particles(flame& f, float* out) {
     if (!f.device() || !f.device()->particles) throw std::runtime_error("no particle buffer (warmup first)");
     cuda_check(cudaMemcpyAsync(out, f.device()->particles, g_sim.total_particles * sizeof(float4), cudaMemcpyDeviceToHost, g_sim.stream), "copy particles");
@@ -734,7 +857,8 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         p.fixed_bins = d.fixed_bins;
     }
     int stage_regions = 0, stage_shift = options_.staged_bins > 0 ? options_.staged_bins : 0;
-    CUfunction draw_fn = d.draw;
+    const bool baked = d.use_baked && !d.cfp_staging.empty();
+    CUfunction draw_fn = baked ? ensure_variant(*this, false, true).draw : d.draw;
     if (options_.staged_bins < 0 && !d.stage_unavailable && !options_.deterministic && !options_.warp_aggregate && !options_.l2_hints &&
         W * H * sizeof(float4) >= (std::size_t(1) << 29)) {
         // automatic: a histogram of 512 MiB or more (four times the L2) is drawn through the queues, in at most 64 regions of
@@ -743,8 +867,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         int shift = 22;
         while (((W * H + (std::size_t(1) << shift) - 1) >> shift) > 64) shift++;
         if (shift <= 24) {  // a record holds 24 bits of bin index
-            ensure_staged_module(*this);
-            draw_fn = d.staged_draw;
+            draw_fn = ensure_variant(*this, true, baked).draw;
             stage_shift = shift;
         }
     }
@@ -795,7 +918,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
             }
         }
         if (d.stage_unavailable) {
-            draw_fn = d.draw;
+            draw_fn = baked ? ensure_variant(*this, false, true).draw : d.draw;
             stage_shift = 0;
         }
     }
@@ -918,14 +1041,18 @@ void flame_single_step(flame& f, int n, const float* xyz, const int* xid, std::u
     std::array<float, flame::PARAM_BUFFER> own;
     if (!fp) { own = f.copy_flame_data_to_buffer(); fp = own.data(); }
     d_fp.upload(fp);
-    upload_constant_params(*f.device(), fp);
+    upload_constant_params(f, fp);
     float4* outp = reinterpret_cast<float4*>(d_out.p);
     uint4* rngp = reinterpret_cast<uint4*>(d_rng.p);
     void* args[] = {&n, &d_xyz.p, &d_xid.p, &rngp, &d_fp.p, &first_run, &outp};
-    launch(f.device()->single_step, (unsigned)((n + 127) / 128), 128, args);
+    // kernel option specialize = 1 and the flame's own values: through the value-specialised build (built here if need be),
+    // so the parity tests reach the code rfk_draw runs
+    CUfunction fn = f.device()->single_step;
+    if (f.options().specialize == 1 && fp == own.data()) fn = ensure_variant(f, false, true).single_step;
+    launch(fn, (unsigned)((n + 127) / 128), 128, args);
     cuda_check(cudaStreamSynchronize(g_sim.stream), "rfk_single_step");
     d_out.download(out); d_rng.download(rng);
-    if (fp != own.data()) { own = f.copy_flame_data_to_buffer(); upload_constant_params(*f.device(), own.data()); }  // the flame's own values again
+    if (fp != own.data()) { own = f.copy_flame_data_to_buffer(); upload_constant_params(f, own.data()); }  // the flame's own values again
 }
 
 void flame_select_xform(flame& f, int n, const float* ratio, const float* fp, int* out) {
@@ -936,12 +1063,12 @@ void flame_select_xform(flame& f, int n, const float* ratio, const float* fp, in
     std::array<float, flame::PARAM_BUFFER> own;
     if (!fp) { own = f.copy_flame_data_to_buffer(); fp = own.data(); }
     d_fp.upload(fp);
-    upload_constant_params(*f.device(), fp);
+    upload_constant_params(f, fp);
     void* args[] = {&n, &d_ratio.p, &d_fp.p, &d_out.p};
     launch(f.device()->select_xform, (unsigned)((n + 127) / 128), 128, args);
     cuda_check(cudaStreamSynchronize(g_sim.stream), "rfk_select_xform");
     d_out.download(out);
-    if (fp != own.data()) { own = f.copy_flame_data_to_buffer(); upload_constant_params(*f.device(), own.data()); }
+    if (fp != own.data()) { own = f.copy_flame_data_to_buffer(); upload_constant_params(f, own.data()); }
 }
 
 void flame_bucket_index(flame& f, int n, const float* xyzw, const float ss_affine[6], int W, int H, int* idx_out, int* pal_out) {

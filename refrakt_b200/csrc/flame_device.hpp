@@ -32,6 +32,7 @@ void flame_bucket_index(flame& f, int n, const float* xyzw, const float ss_affin
 void flame_animate_host(flame& f, float tss_width, int temporal_samples, float* out);
 void flame_kernel_info(flame& f, const char* kernel, int* regs, int* smem_bytes, int* blocks_per_sm);
 void flame_read_counters(flame& f, unsigned long long* out, int n);
+bool flame_uses_baked(const flame& f);  // the last warmup chose the value-specialised kernels (kernel option specialize)
 void flame_copy_particles(flame& f, float* out);  // the flame's particle buffer (P x float4), to host
 
 }  // namespace rfk

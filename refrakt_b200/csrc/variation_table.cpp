@@ -155,7 +155,7 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
     const auto& buf_map = f.buffer_map();
     std::string disp_func = d == dialect::glsl
         ? std::string("vec4 dispatch(vec3 v, int xform){\n").append("switch(xform){\n")
-        : std::string("template <bool first_run>\n__device__ __forceinline__ vec4 dispatch(vec3 v, int xform, rfk_rng& rs){\n").append("switch(xform){\n");
+        : std::string("template <bool first_run>\n__device__ __forceinline__ vec4 dispatch_a(vec3 v, int xform, rfk_rng& rs, const float4 rfk_A){\n").append("switch(xform){\n");
     int rf_counter = 0;
 
     for (int i = -1; i < (int)f.xforms.size(); i++) {
@@ -194,27 +194,37 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
     disp_func = replace_all(disp_func, "\n", "\n\t");
     disp_func += "\n}";
     if (d == dialect::cuda) {
-        std::string slots = "__constant__ int rfk_weight_slot[" + std::to_string(std::max<std::size_t>(1, buf_map.xforms.size())) + "] = {";
-        for (std::size_t i = 0; i < buf_map.xforms.size(); i++) slots += (i ? ", " : "") + std::to_string(buf_map.xforms[i].weight);
-        if (buf_map.xforms.empty()) slots += "0";
-        slots += "};\n";
         // Parameter slots that are the same for every temporal sample — all but the four rotated affine coefficients of each
         // xform (animate.tpl.glsl:42-49) — are read from constant memory: `fp[N]` becomes `rfk_cfp[N]`, which the compiler
         // folds into the arithmetic instruction as a constant-bank operand instead of a shared-memory load. The host uploads
         // the array at warmup (it holds the same binary32 values as fp_inflated).
-        std::set<int> per_sample;
-        auto mark = [&](const xform_slots& m) { for (int a = 0; a < 4; a++) per_sample.insert(m.affine[a]); };
-        for (auto& m : buf_map.xforms) mark(m);
-        if (buf_map.final_xform) mark(*buf_map.final_xform);
+        // The four rotated coefficients (a, b, c, d: consecutive slots) become RFK_AFF(xform, x|y|z|w): a component of the
+        // float4 the kernel loads for the picked xform with ONE 128-bit shared-memory read before it enters the switch
+        // (rfk_aff[] in device_prelude.cuh, staged per CTA from its temporal sample's row by rfk_stage_params()).
+        // rfk_affine_slot[1 + i] is the slot of xform i's coefficient a; [0] that of the final xform (-1: none).
+        std::map<int, std::pair<int, int>> per_sample;  // slot -> (xform index, component)
+        auto mark = [&](const xform_slots& m, int index) { for (int a = 0; a < 4; a++) per_sample[m.affine[a]] = {index, a}; };
+        for (std::size_t i = 0; i < buf_map.xforms.size(); i++) mark(buf_map.xforms[i], (int)i);
+        if (buf_map.final_xform) mark(*buf_map.final_xform, -1);
+        std::string slots = "__constant__ int rfk_affine_slot[" + std::to_string(buf_map.xforms.size() + 1) + "] = {" +
+                            std::to_string(buf_map.final_xform ? buf_map.final_xform->affine[0] : -1);
+        for (auto& m : buf_map.xforms) slots += ", " + std::to_string(m.affine[0]);
+        slots += "};\n";
         std::string body = xid_func + "\n" + disp_func + "\n", out;
         out.reserve(body.size() + 1024);
         for (std::size_t i = 0; i < body.size();) {
             if (body.compare(i, 3, "fp[") == 0 && (i == 0 || !ident_char(body[i - 1]))) {
                 std::size_t j = i + 3, k = j;
                 while (k < body.size() && body[k] >= '0' && body[k] <= '9') k++;
-                if (k > j && k < body.size() && body[k] == ']' && !per_sample.count(std::stoi(body.substr(j, k - j)))) {
-                    out += "rfk_cfp[";
-                    i = j;
+                if (k > j && k < body.size() && body[k] == ']') {
+                    const auto owner = per_sample.find(std::stoi(body.substr(j, k - j)));
+                    if (owner == per_sample.end()) {
+                        out += "rfk_cfp[";
+                        i = j;
+                    } else {
+                        out += "RFK_AFF(" + std::to_string(owner->second.first) + ", " + std::string(1, "xyzw"[owner->second.second]) + ")";
+                        i = k + 1;
+                    }
                     continue;
                 }
             }

@@ -19,7 +19,7 @@ def test_abi_exports_every_declared_symbol(rfk):
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export " + name
     assert declared == set(rfk.SIGNATURES), declared ^ set(rfk.SIGNATURES)
-    assert lib.rfk_abi_version() == 2
+    assert lib.rfk_abi_version() == 3
     out = subprocess.run(["nm", "-D", "--defined-only", rfk.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     exported = set(re.findall(r"\bT (rfk_[a-z0-9_]+)", out))
     assert declared <= exported
@@ -120,7 +120,7 @@ def test_cuda_dialect_rewrites(flame):
     assert re.search(r"float _rf0 = randf\(\), _rf1 = randf\(\), _rf2 = randf\(\), _rf3 = randf\(\), _rf4 = randf\(\); vec2 result = rfk_cfp\[7\] \*\(_rf0 \+ _rf1 \+ _rf2 \+ _rf3 - 2.0f\) \* sincos\(_rf4 \* 2.0f \* PI\)\.yx\(\);", c)
     assert "((first_run)? randf(): v.z)" in c  # a conditional draw stays conditional
     assert not re.search(r"(?<![\w.])\d+\.\d+(?![\dfeE])", c.split("namespace rfk_glsl {\n#define randf()")[1].split("#undef randf")[0])
-    assert "__constant__ int rfk_weight_slot[10] = {0, 13, 30, 43, 59, 76, 92, 110, 125, 141};" in c
+    assert "__constant__ int rfk_affine_slot[11] = {154, 1, 14, 31, 44, 60, 77, 93, 111, 126, 142};" in c
 
 
 @pytest.mark.parametrize("W,H,hexes", [
