@@ -3,6 +3,8 @@
 #include "static_kernels.cuh"
 
 #include <cmath>
+#include <cstring>
+#include <stdexcept>
 
 namespace rfk::kernels {
 
@@ -181,8 +183,9 @@ __global__ void pack_rgba8_kernel(const float4* __restrict__ in, uchar4* __restr
                          (unsigned char)rintf(fminf(fmaxf(v.z, 0.f), 1.f) * 255.0f), (unsigned char)rintf(fminf(fmaxf(v.w, 0.f), 1.f) * 255.0f));
 }
 
-// density_vert.glsl:35-44
-__device__ __forceinline__ int estimator_radius_of(float density, const density_params& p) {
+// density_vert.glsl:35-44, as the reference writes it (estimator_curve <= 0 only: the thresholds below need a radius that
+// does not grow with the density)
+__device__ __forceinline__ int estimator_radius_pow(float density, const density_params& p) {
     int r = (int)((float)p.estimator_radius / powf(density, p.estimator_curve));
     r = min(p.estimator_radius, r);
     return max(p.estimator_min, r);
@@ -211,38 +214,51 @@ __device__ __forceinline__ float4 tonemap_pixel(float4 color, const density_para
 
 constexpr int DE_TILE_W = 32, DE_ROWS_PER_WARP = 4, DE_WARPS = 8, DE_TILE_H = DE_ROWS_PER_WARP * DE_WARPS;
 constexpr int DE_THREADS = DE_WARPS * 32;
-constexpr int DE_CAP = 512;            // candidate-list entries per batch (48 B each)
-constexpr int DE_MAX_COUNTERS = 2048;  // (32 + 2 * 100) rows x 8 column chunks
+constexpr int DE_CAP = 256;        // candidate-list entries per batch (32 B each)
+constexpr int DE_SMALL_R = 3;      // radius classes: 1..3 ("small": the warp's band of source rows is +-3) and above
 
-// Gather form of the reference's point-sprite splat. Source bin (bx, by) with radius r lands on
-// out[cy + m][bx - 1 + i], cy = H-1-by, i, m in [-r, r], weight (1 - n(i)^2 - n(m)^2) * (2/pi) / r^2 when
-// that is >= 0, n(k) = 2k/(2r+1) + 1/(2r+1)^2; r == 0 copies the bin to out[cy][bx-1].
+// Packed FP32 (sm_100 FFMA2: two lanes per issue slot; the kernel is issue bound): acc.xy += c.xy * w, acc.zw += c.zw * w
+__device__ __forceinline__ void fma4(float4& acc, const float4& c, float w) {
+    const float2 w2 = make_float2(w, w);
+    const float2 lo = __ffma2_rn(make_float2(c.x, c.y), w2, make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(make_float2(c.z, c.w), w2, make_float2(acc.z, acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// Gather form of the reference's point-sprite splat. Source bin (bx, cy) with radius r lands on
+// out[cy + m][bx - 1 + i], i, m in [-r, r], weight (1 - n(i)^2 - n(m)^2) * (2/pi) / r^2 when that is >= 0,
+// n(k) = 2k/(2r+1) + 1/(2r+1)^2; r == 0 copies the bin to out[cy][bx-1]. |n(k)| > 1 for every k
+// outside [-r, r], so max(weight, 0) alone restricts a candidate to its (2r+1)^2 footprint.
 //
 // A CTA produces a 32 x 32 output tile; a warp owns 4 rows x 32 columns and keeps their float4 sums in
 // registers (no atomics, fixed summation order => deterministic).
-//  A0. The CTA reads the densities of its (32 + 2R)^2 source window once and stores one radius byte per bin in
-//      shared memory: 0 unless the density is below the threshold of radius 1 (one 4-byte load and a compare for
-//      the dense bulk of the image), the exact radius (the reference's int(R / pow(d, curve))) is >= 1 and the
-//      footprint reaches the tile.
-//  A1-A3. Candidates are counted per (row, 32-column chunk), prefix-summed, and written to a shared-memory list in
-//      row-major order with their colour and the per-radius constants (batches of DE_CAP).
-//  B.  Every warp walks the list entries whose source row can reach its 4 rows (a contiguous range, the list being
-//      row-major) and accumulates; lanes are output columns.
+//  A0. The CTA reads the densities of its (32 + 2R)^2 source window once and stores one radius byte per bin in shared
+//      memory, 0 = not a candidate: the radius is the number of thresholds T[1] > T[2] > ... the density stays under
+//      (host table, density_thresholds(): exactly the densities where the reference's int(R / pow(d, curve)) steps), so
+//      the dense bulk of an image costs one 4-byte load and one compare per scanned bin; a candidate has radius >= 1
+//      and a footprint that reaches the tile.
+//  A1-A2. Candidates are counted per (class, row, 32-column chunk) — class "small" = radius <= 3, "large" above — and
+//      prefix-summed: the list is class-major, row-major inside a class.
+//  A3. The list is written to shared memory in batches of DE_CAP entries: colour premultiplied by (2/pi)/r^2, and
+//      (bx - 1, cy, 2/S, 1/S^2), S = 2r + 1.
+//  B.  Every warp walks, per class, the contiguous list range whose source rows can reach its 4 rows — +-3 rows for the
+//      small class, +-R for the large one — and accumulates; lanes are output columns.
+// Multi-GPU row slabs (rfk_comm_*): `bins` then holds the source rows [src_y0, src_y1) only and the launch produces the
+// output rows [y0, y1); rows outside [src_y0, src_y1) count as empty (they are outside the image, or not needed).
 template <bool DENSITY, bool TONEMAP>
-__global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
+__global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
                                                                      uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
-    __shared__ int s_off[DE_MAX_COUNTERS + 1];
     __shared__ int s_part[DE_THREADS];
-    __shared__ float4 s_col[DE_CAP];
-    __shared__ int4 s_geo[DE_CAP];    // source column, source row (cy), radius
-    __shared__ float4 s_k[DE_CAP];    // 2/S, 1/S^2, (2/pi)/r^2
-    extern __shared__ unsigned char s_rad[];  // [nrows][pitch] radius of every window bin, 0 = not a candidate
+    __shared__ float4 s_list[2 * DE_CAP];  // entry e: [2e] = (bx - 1, cy, 2/S, 1/S^2), [2e + 1] = colour * (2/pi)/r^2
+    extern __shared__ unsigned char s_dyn[];  // [nrows][pitch] radius bytes, then 2 * ncnt + 1 list offsets (unsigned short)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * DE_TILE_W, ty0 = blockIdx.y * DE_TILE_H;
+    const int tx0 = blockIdx.x * DE_TILE_W, ty0 = p.y0 + blockIdx.y * DE_TILE_H;
     const int ox = tx0 + lane;
     const int oy0 = ty0 + warp * DE_ROWS_PER_WARP;
-    const int W = p.W, H = p.H;
+    const int W = p.W;
+    // bin (bx, cy) of the histogram: row flip of flame.glsl:84, relative to the rows `bins` holds
+    auto bin_at = [&](int bx, int cy) -> const float4* { return bins + (size_t)(p.src_y1 - 1 - cy) * W + bx; };
 
     float4 acc[DE_ROWS_PER_WARP];
 #pragma unroll
@@ -250,50 +266,64 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
 
     if (DENSITY) {
         const int R = max(p.estimator_radius, p.estimator_min);
-        const float t_any = p.thresholds[1];  // no bin denser than this has a radius >= 1 (conservative)
-        // radius-0 sources: out[cy][ox] takes bin (ox + 1, cy)
-        if (p.estimator_min == 0) {
+        // radius-0 sources: out[cy][ox] takes bin (ox + 1, cy). Loaded first (the loads are in flight during A0); a bin that
+        // turns out to have a radius >= 1 is dropped again below.
 #pragma unroll
-            for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
-                int cy = oy0 + k, bx = ox + 1;
-                if (cy < H && bx < W) {
-                    float4 c = __ldg(bins + (size_t)(H - 1 - cy) * W + bx);
-                    if (c.w != 0.0f && (c.w > t_any || estimator_radius_of(c.w, p) == 0)) acc[k] = c;
-                }
-            }
+        for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
+            const int cy = oy0 + k, bx = ox + 1;
+            if (cy >= p.src_y0 && cy < p.src_y1 && cy < p.y1 && bx < W) acc[k] = __ldg(bin_at(bx, cy));
         }
         if (R >= 1) {
             const int win_x0 = tx0 + 1 - R, win_w = DE_TILE_W + 2 * R, nch = (win_w + 31) >> 5, pitch = nch << 5;
             const int win_y0 = ty0 - R, nrows = DE_TILE_H + 2 * R;
             const int ncnt = nrows * nch;
+            unsigned char* const s_rad = s_dyn;
+            unsigned short* const s_off = reinterpret_cast<unsigned short*>(s_dyn + ((nrows * pitch + 15) & ~15));
 
             // A0: radius byte of every window bin
+            const float t_any = p.thresholds[1];
             for (int row = warp; row < nrows; row += DE_WARPS) {
                 const int cy = win_y0 + row;
+                const bool row_ok = cy >= p.src_y0 && cy < p.src_y1;
                 for (int c = 0; c < nch; c++) {
                     const int col = (c << 5) + lane, bx = win_x0 + col;
+                    float d = 0.0f;
+                    if (row_ok && col < win_w && bx >= 0 && bx < W) d = __ldg(&bin_at(bx, cy)->w);
                     int r = 0;
-                    if (cy >= 0 && cy < H && col < win_w && bx >= 0 && bx < W) {
-                        const float d = __ldg(&bins[(size_t)(H - 1 - cy) * W + bx].w);
-                        if (d != 0.0f && d <= t_any) {
-                            r = estimator_radius_of(d, p);
-                            if (r < 1 || bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1) r = 0;
+                    const bool cand = d != 0.0f && (p.use_pow || d <= t_any);
+                    if (__any_sync(0xffffffffu, cand)) {
+                        if (p.use_pow) {
+                            if (cand) r = estimator_radius_pow(d, p);
+                        } else {
+                            r = cand ? 1 : 0;
+                            for (int k = 2; k <= R; k++) {  // warp-uniform trip count: until no lane's density is under T[k]
+                                const bool under = cand && d <= p.thresholds[k];
+                                if (!__any_sync(0xffffffffu, under)) break;
+                                r += under ? 1 : 0;
+                            }
                         }
+                        if (r >= 1 && (bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1)) r = 0;
                     }
                     s_rad[row * pitch + col] = (unsigned char)r;
                 }
             }
             __syncthreads();
-            // A1: counts per (row, chunk)
+            // a bin of the tile's own rows and columns with a radius >= 1 is not a radius-0 source (its footprint always reaches the tile)
+#pragma unroll
+            for (int k = 0; k < DE_ROWS_PER_WARP; k++)
+                if (s_rad[(R + warp * DE_ROWS_PER_WARP + k) * pitch + R + lane] != 0) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            // A1: counts per (class, row, chunk)
             for (int i = warp; i < ncnt; i += DE_WARPS) {
-                unsigned int vote = __ballot_sync(0xffffffffu, s_rad[(i << 5) + lane] != 0);
-                if (lane == 0) s_off[i] = __popc(vote);
+                const int r = s_rad[(i << 5) + lane];
+                const unsigned int small = __ballot_sync(0xffffffffu, r != 0 && r <= DE_SMALL_R), large = __ballot_sync(0xffffffffu, r > DE_SMALL_R);
+                if (lane == 0) { s_off[i] = (unsigned short)__popc(small); s_off[ncnt + i] = (unsigned short)__popc(large); }
             }
             __syncthreads();
-            // A2: exclusive prefix sum over the counters
+            // A2: exclusive prefix sum over the 2 * ncnt counters (a window holds fewer than 65536 bins)
+            const int n2 = 2 * ncnt;
             {
-                const int per = (ncnt + DE_THREADS - 1) / DE_THREADS;
-                const int lo = min(tid * per, ncnt), hi = min(lo + per, ncnt);
+                const int per = (n2 + DE_THREADS - 1) / DE_THREADS;
+                const int lo = min(tid * per, n2), hi = min(lo + per, n2);
                 int sum = 0;
                 for (int i = lo; i < hi; i++) sum += s_off[i];
                 s_part[tid] = sum;
@@ -309,75 +339,86 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
                         s_part[base + lane] = carry + incl - v;
                         carry += __shfl_sync(0xffffffffu, incl, 31);
                     }
-                    if (lane == 0) s_off[ncnt] = carry;
+                    if (lane == 0) s_off[n2] = (unsigned short)carry;
                 }
                 __syncthreads();
                 int run = s_part[tid];
                 for (int i = lo; i < hi; i++) {
                     int v = s_off[i];
-                    s_off[i] = run;
+                    s_off[i] = (unsigned short)run;
                     run += v;
                 }
                 __syncthreads();
             }
-            const int total = s_off[ncnt];
+            const int total = s_off[n2];
+            if (total > 0) {  // CTA-uniform
+                // list ranges of this warp, per class: the source rows that can reach its output rows, as window rows
+                int w_lo[2], w_hi[2];
+#pragma unroll
+                for (int cls = 0; cls < 2; cls++) {
+                    const int reach = cls == 0 ? min(R, DE_SMALL_R) : R;
+                    const int rlo = max(0, R + warp * DE_ROWS_PER_WARP - reach), rhi = min(nrows - 1, R + warp * DE_ROWS_PER_WARP + DE_ROWS_PER_WARP - 1 + reach);
+                    w_lo[cls] = s_off[cls * ncnt + rlo * nch];
+                    w_hi[cls] = s_off[cls * ncnt + (rhi + 1) * nch];
+                }
+                const float oxf = (float)ox, oy0f = (float)oy0;
 
-            // source rows that can reach this warp's output rows, as window rows
-            const int rlo = warp * DE_ROWS_PER_WARP, rhi = min(nrows - 1, warp * DE_ROWS_PER_WARP + DE_ROWS_PER_WARP - 1 + 2 * R);
-            const int w_lo = s_off[rlo * nch], w_hi = s_off[(rhi + 1) * nch];
-
-            for (int base = 0; base < total; base += DE_CAP) {
-                // A3: write this batch of the list
-                for (int row = warp; row < nrows; row += DE_WARPS)
-                    for (int c = 0; c < nch; c++) {
-                        const int i = row * nch + c;
+                for (int base = 0; base < total; base += DE_CAP) {
+                    // A3: write this batch of the list
+                    for (int i = warp; i < n2; i += DE_WARPS) {
                         const int first = s_off[i], last = s_off[i + 1];
                         if (last == first || last <= base || first >= base + DE_CAP) continue;  // warp-uniform
-                        const int r = s_rad[(i << 5) + lane];
-                        const unsigned int vote = __ballot_sync(0xffffffffu, r != 0);
-                        if (r != 0) {
+                        const bool large = i >= ncnt;
+                        const int cell = large ? i - ncnt : i;
+                        const int r = s_rad[(cell << 5) + lane];
+                        const bool mine = large ? r > DE_SMALL_R : (r != 0 && r <= DE_SMALL_R);
+                        const unsigned int vote = __ballot_sync(0xffffffffu, mine);
+                        if (mine) {
                             const int e = first + __popc(vote & ((1u << lane) - 1u)) - base;
                             if (e >= 0 && e < DE_CAP) {
+                                const int row = cell / nch, c = cell - row * nch;
                                 const int cy = win_y0 + row, bx = win_x0 + (c << 5) + lane;
-                                s_col[e] = __ldg(&bins[(size_t)(H - 1 - cy) * W + bx]);
-                                s_geo[e] = make_int4(bx, cy, r, 0);
-                                const float S = (float)(2 * r + 1);
-                                s_k[e] = make_float4(2.0f / S, 1.0f / (S * S), 0.63661977236f / (float)(r * r), 0.0f);  // density_vert.glsl:62
+                                float4 col = __ldg(bin_at(bx, cy));
+                                const float S = (float)(2 * r + 1), norm = 0.63661977236f / (float)(r * r);  // density_vert.glsl:62
+                                col.x *= norm; col.y *= norm; col.z *= norm; col.w *= norm;
+                                s_list[2 * e] = make_float4((float)(bx - 1), (float)cy, 2.0f / S, 1.0f / (S * S));
+                                s_list[2 * e + 1] = col;
                             }
                         }
                     }
-                __syncthreads();
-                // B: accumulate
-                const int e_lo = max(w_lo, base) - base, e_hi = min(w_hi, base + DE_CAP) - base;
-                for (int e = e_lo; e < e_hi; e++) {
-                    const int4 g = s_geo[e];
-                    const int sr = g.z, m0 = oy0 - g.y;
-                    if (m0 > sr || m0 + DE_ROWS_PER_WARP - 1 < -sr) continue;  // warp-uniform
-                    const float4 col = s_col[e];
-                    const float4 k = s_k[e];
-                    const int i = ox - g.x + 1;
-                    // weight = (1 - n(i)^2 - n(m)^2) * norm, kept when >= 0 (density_frag.glsl:17 discards distance > 1).
-                    // Lane part c_i = n(i)^2 * norm (+inf outside the footprint columns), row part a_m = norm - n(m)^2 * norm.
-                    const float ni = fmaf((float)i, k.x, k.y);
-                    const float ci = (i >= -sr && i <= sr) ? ni * ni * k.z : INFINITY;
+                    __syncthreads();
+                    // B: accumulate. weight / norm = 1 - n(i)^2 - n(m)^2, kept when >= 0 (density_frag.glsl:17 discards distance > 1)
 #pragma unroll
-                    for (int q = 0; q < DE_ROWS_PER_WARP; q++) {
-                        const int m = m0 + q;
-                        const float nm = fmaf((float)m, k.x, k.y);
-                        const float am = (m >= -sr && m <= sr) ? fmaf(-nm * nm, k.z, k.z) : -INFINITY;
-                        const float wgt = fmaxf(am - ci, 0.0f);
-                        acc[q].x = fmaf(col.x, wgt, acc[q].x); acc[q].y = fmaf(col.y, wgt, acc[q].y);
-                        acc[q].z = fmaf(col.z, wgt, acc[q].z); acc[q].w = fmaf(col.w, wgt, acc[q].w);
+                    for (int cls = 0; cls < 2; cls++) {
+                        const int e_lo = max(w_lo[cls], base) - base, e_hi = min(w_hi[cls], base + DE_CAP) - base;
+                        // the entries by shared-window address: one register walks the list, both reads are [reg + immediate]
+                        const unsigned int list0 = (unsigned int)__cvta_generic_to_shared(s_list);
+                        for (unsigned int at = list0 + 32u * (unsigned int)max(e_lo, 0), end = list0 + 32u * (unsigned int)max(e_hi, 0); at < end; at += 32u) {
+                            float4 g;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "r"(at));
+                            const float nm0 = fmaf(oy0f - g.y, g.z, g.w);                    // n(m) of the warp's first row
+                            const float nm3 = fmaf((float)(DE_ROWS_PER_WARP - 1), g.z, nm0);  // ... and of its last one
+                            if (nm0 > 1.0f || nm3 < -1.0f) continue;  // no row of this warp inside the footprint (warp-uniform)
+                            float4 col;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(col.x), "=f"(col.y), "=f"(col.z), "=f"(col.w) : "r"(at));
+                            const float ni = fmaf(oxf - g.x, g.z, g.w);
+                            const float one_minus_ci = fmaf(-ni, ni, 1.0f);
+#pragma unroll
+                            for (int q = 0; q < DE_ROWS_PER_WARP; q++) {
+                                const float nm = fmaf((float)q, g.z, nm0);
+                                fma4(acc[q], col, fmaxf(fmaf(-nm, nm, one_minus_ci), 0.0f));
+                            }
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         }
     } else {
 #pragma unroll
         for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
             int cy = oy0 + k;
-            if (cy < H && ox < W) acc[k] = __ldg(bins + (size_t)cy * W + ox);  // tonemap only: input is already an image
+            if (cy < p.y1 && ox < W) acc[k] = __ldg(bins + (size_t)(cy - p.src_y0) * W + ox);  // tonemap only: input is already an image
         }
     }
 
@@ -385,9 +426,9 @@ __global__ void __launch_bounds__(DE_THREADS) density_tonemap_kernel(const float
 #pragma unroll
     for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
         int cy = oy0 + k;
-        if (cy >= H) continue;
+        if (cy >= p.y1) continue;
         float4 v = TONEMAP ? tonemap_pixel(acc[k], p) : acc[k];
-        size_t o = (size_t)cy * W + ox;
+        size_t o = (size_t)(cy - p.out_y0) * W + ox;
         if (out_f4) out_f4[o] = v;
         if (out_rgba8) out_rgba8[o] = make_uchar4((unsigned char)rintf(fminf(fmaxf(v.x, 0.f), 1.f) * 255.0f), (unsigned char)rintf(fminf(fmaxf(v.y, 0.f), 1.f) * 255.0f),
                                                   (unsigned char)rintf(fminf(fmaxf(v.z, 0.f), 1.f) * 255.0f), (unsigned char)rintf(fminf(fmaxf(v.w, 0.f), 1.f) * 255.0f));
@@ -425,33 +466,63 @@ void animate(const float* fp, float* fp_inflated, int total_params, int temporal
     animate_kernel<<<(temporal_samples + 31) / 32, 32, 0, s>>>(fp, fp_inflated, total_params, temporal_samples, temporal_sample_width, xforms_dev, num_xforms);
 }
 
-static void density_thresholds(float* host_out, int estimator_radius, int estimator_min, float estimator_curve) {
+// radius >= k  <=>  density <= thresholds[k], for k = 1 .. R = max(estimator_radius, estimator_min): the exact steps of the
+// reference's  max(estimator_min, min(estimator_radius, int(estimator_radius / pow(d, curve))))  (density_vert.glsl:35-44)
+// in binary32 with this host's powf, found by bisection on the bit pattern (positive floats order like their bits).
+// Needs a radius that does not grow with the density: estimator_curve > 0; returns false otherwise (the kernel then
+// evaluates the formula per bin).
+static bool density_thresholds(float* host_out, int estimator_radius, int estimator_min, float estimator_curve) {
     const int R = estimator_radius > estimator_min ? estimator_radius : estimator_min;
     host_out[0] = INFINITY;
-    for (int k = 1; k <= R; k++) {
-        // radius >= k  <=>  k <= estimator_min  or  estimator_radius / d^curve >= k
-        if (k <= estimator_min || !(estimator_curve > 0.0f)) { host_out[k] = INFINITY; continue; }
-        if (k > estimator_radius) { host_out[k] = 0.0f; continue; }
-        double t = std::pow((double)estimator_radius / (double)k, 1.0 / (double)estimator_curve);
-        host_out[k] = (float)(t * (1.0 + 1e-3));
+    for (int k = 1; k <= R && k < 102; k++) host_out[k] = INFINITY;
+    if (!(estimator_curve > 0.0f)) return false;
+    auto radius_of = [&](float d) {
+        int r = (int)((float)estimator_radius / powf(d, estimator_curve));
+        r = r < estimator_radius ? r : estimator_radius;
+        return r > estimator_min ? r : estimator_min;
+    };
+    for (int k = 1; k <= R && k < 102; k++) {
+        if (k <= estimator_min) { host_out[k] = INFINITY; continue; }
+        // largest finite positive float d with radius_of(d) >= k; radius_of is non-increasing in d
+        std::uint32_t lo = 1u, hi = 0x7f7fffffu;  // smallest subnormal .. FLT_MAX
+        auto as_float = [](std::uint32_t b) { float f; std::memcpy(&f, &b, 4); return f; };
+        if (radius_of(as_float(lo)) < k) { host_out[k] = 0.0f; continue; }
+        if (radius_of(as_float(hi)) >= k) { host_out[k] = INFINITY; continue; }
+        while (hi - lo > 1) {
+            const std::uint32_t mid = lo + (hi - lo) / 2;
+            if (radius_of(as_float(mid)) >= k) lo = mid; else hi = mid;
+        }
+        host_out[k] = as_float(lo);
     }
+    return true;
 }
 
 void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, density_params p, bool do_density, bool do_tonemap, cudaStream_t s) {
-    density_thresholds(p.thresholds, p.estimator_radius, p.estimator_min, p.estimator_curve);
-    dim3 grid((p.W + DE_TILE_W - 1) / DE_TILE_W, (p.H + DE_TILE_H - 1) / DE_TILE_H);
+    if (p.estimator_radius > 100) p.estimator_radius = 100;  // main.cpp:502
+    if (p.estimator_radius < 0) p.estimator_radius = 0;
+    if (p.estimator_min < 0) p.estimator_min = 0;
+    if (p.estimator_min > 100) throw std::invalid_argument("density estimation: estimator_min above 100 (the radius table and the source window hold 100)");
+    if (p.y1 == 0 && p.y0 == 0) { p.y1 = p.H; p.src_y0 = 0; p.src_y1 = p.H; p.out_y0 = 0; }  // the whole image
+    if (p.y0 < 0 || p.y1 > p.H || p.y0 >= p.y1 || p.src_y0 < 0 || p.src_y1 > p.H || p.src_y0 >= p.src_y1)
+        throw std::invalid_argument("density estimation: bad row range");
+    p.use_pow = density_thresholds(p.thresholds, p.estimator_radius, p.estimator_min, p.estimator_curve) ? 0 : 1;
+    dim3 grid((p.W + DE_TILE_W - 1) / DE_TILE_W, (p.y1 - p.y0 + DE_TILE_H - 1) / DE_TILE_H);
     dim3 block(DE_THREADS);
-    // radius bytes of the (32 + 2R)^2 source window: 3.4 KB at R = 11, 58 KB at the maximum R = 100
+    // dynamic shared memory: radius bytes of the (32 + 2R)^2 source window + 2 list offsets per (row, 32-column chunk):
+    // 3.9 KB at R = 11, 67 KB at the maximum R = 100
     const int R = p.estimator_radius > p.estimator_min ? p.estimator_radius : p.estimator_min;
-    const size_t rad_bytes = do_density ? (size_t)(DE_TILE_H + 2 * R) * (((DE_TILE_W + 2 * R + 31) >> 5) << 5) : 0;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(density_tonemap_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(density_tonemap_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        configured = true;
+    const size_t nrows = DE_TILE_H + 2 * R, nch = (DE_TILE_W + 2 * R + 31) >> 5;
+    const size_t dyn_bytes = do_density && R >= 1 ? ((nrows * (nch << 5) + 15) & ~size_t(15)) + (2 * nrows * nch + 2) * sizeof(unsigned short) : 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool configured[64] = {};
+    if (dev >= 0 && dev < 64 && !configured[dev]) {  // per device: the opt-in is a property of the function on that device
+        cudaFuncSetAttribute(density_tonemap_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        cudaFuncSetAttribute(density_tonemap_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        configured[dev] = true;
     }
-    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, rad_bytes, s>>>(bins, out_f4, out_rgba8, p);
-    else if (do_density) density_tonemap_kernel<true, false><<<grid, block, rad_bytes, s>>>(bins, out_f4, out_rgba8, p);
+    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
+    else if (do_density) density_tonemap_kernel<true, false><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
     else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
 }
 

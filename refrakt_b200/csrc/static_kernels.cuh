@@ -26,9 +26,13 @@ struct density_params {
     int estimator_radius, estimator_min;  // density_vert.glsl:3-4 (radius already clamped to <= 100, main.cpp:502)
     float estimator_curve;
     float gamma, brightness, vibrancy, scale_constant;  // tonemap.glsl:13-16 (scale_constant = 10^-4, main.cpp:528)
-    // a bin of density d can only have radius >= k when d <= thresholds[k] (conservative pre-filter;
-    // the kernel re-derives the exact radius of every candidate); filled by density_tonemap()
+    // radius >= k  <=>  density <= thresholds[k] (exact steps of the reference's formula); filled by density_tonemap()
     float thresholds[102];
+    int use_pow;           // estimator_curve <= 0: no thresholds, the kernel evaluates the formula per bin; filled by density_tonemap()
+    // Row slab of a multi-GPU frame (all zero = the whole image): the launch produces output rows [y0, y1); `bins` holds
+    // the histogram rows of the source rows [src_y0, src_y1) only (source row cy = histogram row H - 1 - cy, so bins[0] is
+    // the bin (0, src_y1 - 1)); output row cy is written to row cy - out_y0 of the output buffers.
+    int y0, y1, src_y0, src_y1, out_y0;
 };
 // Density estimation (density_vert.glsl:26-63 + density_frag.glsl:9-19 + main.cpp:490-515) and/or tonemap
 // (tonemap.glsl:18-39) in one pass. out_f4 / out_rgba8 may each be null.
