@@ -238,6 +238,12 @@ int rfk_density_estimate(const float* bins_dev, float* image_dev, size_t width, 
 int rfk_tonemap(const float* image_in_dev, float* image_out_dev, uint8_t* rgba8_dev, size_t width, size_t height, const rfk_post_params* p);
 /* both in one kernel; either output may be NULL */
 int rfk_density_tonemap(const float* bins_dev, float* image_out_dev, uint8_t* rgba8_dev, size_t width, size_t height, const rfk_post_params* p);
+/* The same for the output rows [y0, y1) only, from a histogram SLAB: bins_rows_dev holds the histogram rows of the source
+ * rows [src_y0, src_y1) (image row cy is histogram row height - 1 - cy, so the slab starts at histogram row
+ * height - src_y1), which must cover [y0 - R, y1 + R) inside the image, R = max(estimator_radius, estimator_min); output
+ * row cy is written to row cy - out_y0 of the output buffers. What every rank of rfk_render_frame_sharded runs on its rows. */
+int rfk_density_tonemap_rows(const float* bins_rows_dev, float* image_out_dev, uint8_t* rgba8_dev, size_t width, size_t height, const rfk_post_params* p,
+                             uint32_t y0, uint32_t y1, uint32_t src_y0, uint32_t src_y1, uint32_t out_y0);
 /* 2x2 box average of a float4 image: out is out_width x out_height, in is twice that in each dimension */
 int rfk_downsample2x(const float* image_in_dev, float* image_out_dev, size_t out_width, size_t out_height);
 /* flam3-style spatial filter + supersample reduction (absent in the reference, main.cpp:195-196: SURVEY §8f item 2):
@@ -277,6 +283,49 @@ typedef struct rfk_frame_stats {
 } rfk_frame_stats;
 int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_out, float* image_out /* optional float4 */,
                      rfk_frame_stats* stats);
+
+/* ---- several GPUs of one box, one process per GPU (the reference is single-GPU: no counterpart) ----
+ * Independent particle streams per GPU (rfk_set_sim_parameters with disjoint seeds) into a private histogram; ONE exchange
+ * step per frame: the histograms are summed. NCCL (loaded at run time; RFK_NCCL_LIBRARY overrides the soname) carries the
+ * bootstrap, the barriers and the fallback data path; where the GPUs can map each other's memory (NVLink / NVSwitch, CUDA
+ * IPC) the sum is a reduce-scatter over row slabs PULLED by the rank that owns the slab, and the finished rows are written
+ * straight into rank 0's image (RFK_COMM_P2P=0 forces the NCCL path).
+ *   rank 0: rfk_comm_unique_id(id); hand `id` to the other processes (file, pipe, MPI, torch.distributed ...);
+ *   every rank: rfk_set_device(local_rank); rfk_comm_init(id, rank, world);  ...  rfk_comm_destroy(). */
+#define RFK_COMM_ID_BYTES 128
+int rfk_comm_unique_id(uint8_t id_out[RFK_COMM_ID_BYTES]);
+int rfk_comm_init(const uint8_t id[RFK_COMM_ID_BYTES], int rank, int world); /* collective; at most 16 ranks */
+int rfk_comm_destroy(void);
+int rfk_comm_rank(void);
+int rfk_comm_world(void);  /* 1 when no communicator is up */
+int rfk_comm_p2p(void);    /* 1 once a sharded frame has mapped the peers' buffers, 0 = NCCL data path */
+int rfk_comm_barrier(void); /* all ranks; blocks the host */
+/* in-place sum of the per-rank histograms (bins_len float4 each) onto rank `root`, or onto every rank when root < 0 */
+int rfk_comm_reduce_histogram(float* bins_dev, size_t bins_len, int root);
+/* Row slabs (pure geometry, no GPU needed): rank r of `world` produces the output rows [y0, y1) of `height` — the first
+ * height % world ranks take one row more — and a density estimation of radius `halo` reads the source rows [src_y0, src_y1) */
+typedef struct rfk_row_slab { uint32_t y0, y1, src_y0, src_y1; } rfk_row_slab;
+int rfk_comm_row_slab(uint32_t height, uint32_t halo, int rank, int world, rfk_row_slab* out);
+/* One frame over all ranks (collective: every rank calls it with the same request). Strong scaling of rfk_render_frame:
+ * every rank warms up its own particles, the ranks together draw until `target_binned` samples are in the histograms
+ * (each rank the same number of passes, the last call shorter than drawing_passes so that no rank overshoots by a whole
+ * call), the histograms are reduce-scattered over row slabs with an estimator-radius halo, every rank runs density
+ * estimation + tonemap (+ the spatial filter when supersample > 1) on its rows, and the rows are gathered on rank 0.
+ * want_rgba8 / want_image say which outputs rank 0 wants; the output pointers are used on rank 0 only. */
+typedef struct rfk_sharded_request {
+    rfk_frame_request frame;
+    uint32_t want_rgba8, want_image;
+} rfk_sharded_request;
+typedef struct rfk_sharded_stats {
+    uint64_t iterations_global; /* chaos-game iterations of all ranks (warmup excluded) */
+    uint64_t binned_global;     /* samples in the summed histogram */
+    uint64_t passes;            /* drawn passes of this rank */
+    uint32_t draw_calls;        /* of this rank */
+    uint32_t p2p;               /* 1 = peer-memory data path, 0 = NCCL */
+    uint32_t y0, y1;            /* output rows this rank produced */
+    float ms_warmup, ms_draw, ms_reduce, ms_post, ms_readback; /* CUDA-event times of this rank's stages (ms_readback: barrier + device-to-host copy) */
+} rfk_sharded_stats;
+int rfk_render_frame_sharded(rfk_flame* f, const rfk_sharded_request* req, uint8_t* rgba8_out, float* image_out, rfk_sharded_stats* stats);
 
 /* ---- on-disk buffer cache in the reference's format (src/buffer_cache.hpp:12-60, src/buffer_cache.cpp:7-21):
  * <root>/cache/<type>/<group>/<name>.bin = size_t byte count + payload. refrakt caches its 1024 shuffle permutations

@@ -62,6 +62,20 @@ class FrameStats(C.Structure):
                 ("ms_warmup", C.c_float), ("ms_draw", C.c_float), ("ms_post", C.c_float), ("ms_readback", C.c_float)]
 
 
+class RowSlab(C.Structure):
+    _fields_ = [("y0", C.c_uint32), ("y1", C.c_uint32), ("src_y0", C.c_uint32), ("src_y1", C.c_uint32)]
+
+
+class ShardedRequest(C.Structure):
+    _fields_ = [("frame", FrameRequest), ("want_rgba8", C.c_uint32), ("want_image", C.c_uint32)]
+
+
+class ShardedStats(C.Structure):
+    _fields_ = [("iterations_global", C.c_uint64), ("binned_global", C.c_uint64), ("passes", C.c_uint64), ("draw_calls", C.c_uint32), ("p2p", C.c_uint32),
+                ("y0", C.c_uint32), ("y1", C.c_uint32),
+                ("ms_warmup", C.c_float), ("ms_draw", C.c_float), ("ms_reduce", C.c_float), ("ms_post", C.c_float), ("ms_readback", C.c_float)]
+
+
 _vp, _cp, _sz, _i, _f = C.c_void_p, C.c_char_p, C.c_size_t, C.c_int, C.c_float
 _fpp, _ipp, _upp = C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_uint32)
 
@@ -136,6 +150,7 @@ SIGNATURES = {
     "rfk_density_estimate": (_i, [_vp, _vp, _sz, _sz, C.POINTER(PostParams)]),
     "rfk_tonemap": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(PostParams)]),
     "rfk_density_tonemap": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(PostParams)]),
+    "rfk_density_tonemap_rows": (_i, [_vp, _vp, _vp, _sz, _sz, C.POINTER(PostParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "rfk_downsample2x": (_i, [_vp, _vp, _sz, _sz]),
     "rfk_spatial_downsample": (_i, [_vp, _vp, _sz, _sz, _i, _f]),
     "rfk_spatial_filter_taps": (_i, [_i, _f, _fpp]),
@@ -144,6 +159,16 @@ SIGNATURES = {
     "rfk_make_shuffle_buffers": (_i, [_vp, C.c_uint32, C.c_uint32, C.c_uint64]),
     "rfk_copy_rng_states": (_i, [_upp, _sz, _sz]),
     "rfk_render_frame": (_i, [_vp, C.POINTER(FrameRequest), _vp, _vp, C.POINTER(FrameStats)]),
+    "rfk_comm_unique_id": (_i, [_vp]),
+    "rfk_comm_init": (_i, [_vp, _i, _i]),
+    "rfk_comm_destroy": (_i, []),
+    "rfk_comm_rank": (_i, []),
+    "rfk_comm_world": (_i, []),
+    "rfk_comm_p2p": (_i, []),
+    "rfk_comm_barrier": (_i, []),
+    "rfk_comm_reduce_histogram": (_i, [_vp, _sz, _i]),
+    "rfk_comm_row_slab": (_i, [C.c_uint32, C.c_uint32, _i, _i, C.POINTER(RowSlab)]),
+    "rfk_render_frame_sharded": (_i, [_vp, C.POINTER(ShardedRequest), _vp, _vp, C.POINTER(ShardedStats)]),
     "rfk_cache_write_buffer": (_i, [_cp, _cp, _cp, _vp, _sz, _cp, _cp, _sz]),
     "rfk_cache_read_buffer": (C.c_int64, [_cp, _cp, _cp, _cp, _vp, _sz]),
     "rfk_cache_list": (_i, [_cp, _cp, _cp, _cp, _sz]),
@@ -481,6 +506,22 @@ class Flame:
                                       image_out.ctypes.data if image_out is not None else None, C.byref(stats)), "render_frame")
         return (rgba8_out if rgba8_out is not None else image_out), stats
 
+    def render_frame_sharded(self, width, height, target_binned=0, max_draw_calls=0, warmup_passes=16, drawing_passes=128, tss_width=1.2 / 60.0,
+                             scale_constant_exp=4.0, want_rgba8=True, want_image=False, supersample=1, filter_radius=1.0,
+                             rgba8_out: Optional[np.ndarray] = None, image_out: Optional[np.ndarray] = None):
+        """rfk_render_frame_sharded: collective over the ranks of comm_init; rank 0 gets the image(s), the others None"""
+        req = ShardedRequest(FrameRequest(width, height, warmup_passes, drawing_passes, tss_width, target_binned, max_draw_calls, scale_constant_exp, supersample, filter_radius),
+                             int(want_rgba8), int(want_image))
+        root = comm_rank() == 0
+        if root and want_rgba8 and rgba8_out is None:
+            rgba8_out = np.empty((height, width, 4), dtype=np.uint8)
+        if root and want_image and image_out is None:
+            image_out = np.empty((height, width, 4), dtype=np.float32)
+        stats = ShardedStats()
+        _check(lib().rfk_render_frame_sharded(self.handle, C.byref(req), rgba8_out.ctypes.data if (root and want_rgba8) else None,
+                                              image_out.ctypes.data if (root and want_image) else None, C.byref(stats)), "render_frame_sharded")
+        return (rgba8_out if root else None), (image_out if root else None), stats
+
     # --- test hooks
     def single_step(self, xyz, xid, rng, fp=None, first_run=False):
         xyz = _f32(xyz)
@@ -529,6 +570,36 @@ class Flame:
             pass
 
 
+# --- several GPUs, one process per GPU (include/refrakt_b200.h "rfk_comm_*")
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().rfk_comm_unique_id(buf), "comm_unique_id")
+    return buf.raw
+
+
+def comm_init(unique_id: bytes, rank: int, world: int):
+    assert len(unique_id) == 128
+    _check(lib().rfk_comm_init(C.create_string_buffer(unique_id, 128), rank, world), "comm_init")
+
+
+def comm_destroy(): _check(lib().rfk_comm_destroy(), "comm_destroy")
+def comm_rank() -> int: return int(lib().rfk_comm_rank())
+def comm_world() -> int: return int(lib().rfk_comm_world())
+def comm_p2p() -> bool: return bool(lib().rfk_comm_p2p())
+def comm_barrier(): _check(lib().rfk_comm_barrier(), "comm_barrier")
+
+
+def comm_reduce_histogram(bins_ptr: int, bins_len: int, root: int = 0):
+    """in-place sum of the per-rank float4 histograms onto `root` (every rank when root < 0); stream-ordered"""
+    _check(lib().rfk_comm_reduce_histogram(bins_ptr, bins_len, root), "comm_reduce_histogram")
+
+
+def comm_row_slab(height: int, halo: int, rank: int, world: int) -> RowSlab:
+    s = RowSlab()
+    _check(lib().rfk_comm_row_slab(height, halo, rank, world, C.byref(s)), "comm_row_slab")
+    return s
+
+
 def rotate_affine(a, deg):
     a, out = _f32(a), np.zeros(6, dtype=np.float32)
     lib().rfk_rotate_affine(_ptr(a), deg, _ptr(out))
@@ -557,6 +628,10 @@ def tonemap(in_ptr, out_ptr, rgba8_ptr, W, H, p: PostParams):
 
 def density_tonemap(bins_ptr, out_ptr, rgba8_ptr, W, H, p: PostParams):
     _check(lib().rfk_density_tonemap(bins_ptr, out_ptr, rgba8_ptr, W, H, C.byref(p)), "density_tonemap")
+
+
+def density_tonemap_rows(bins_rows_ptr, out_ptr, rgba8_ptr, W, H, p: PostParams, y0, y1, src_y0, src_y1, out_y0):
+    _check(lib().rfk_density_tonemap_rows(bins_rows_ptr, out_ptr, rgba8_ptr, W, H, C.byref(p), y0, y1, src_y0, src_y1, out_y0), "density_tonemap_rows")
 
 
 def downsample2x(in_ptr, out_ptr, W, H):

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -12,6 +13,7 @@
 #include "flame_device.hpp"
 #include "png_writer.hpp"
 #include "buffer_cache.hpp"
+#include "comm.hpp"
 #include "static_kernels.cuh"
 #include "textutil.hpp"
 #include "variation_table.hpp"
@@ -89,7 +91,15 @@ int rfk_abi_version(void) { return RFK_ABI_VERSION; }
 const char* rfk_last_error(void) { return t_error.c_str(); }
 
 int rfk_set_device(int ordinal) {
-    return guarded([&]() -> int { cuda_ok(cudaSetDevice(ordinal), "cudaSetDevice"); return RFK_OK; });
+    return guarded([&]() -> int {
+        int before = -1;
+        const bool had = cudaGetDevice(&before) == cudaSuccess;
+        cuda_ok(cudaSetDevice(ordinal), "cudaSetDevice");
+        // the buffers the library owns (simulation state, frame buffers) live on the device they were allocated on: a process
+        // that moves to another device starts over there (set_sim_parameters + warmup again)
+        if (had && before != ordinal) rfk_release_buffers();
+        return RFK_OK;
+    });
 }
 int rfk_set_stream(void* cuda_stream) { set_current_stream(reinterpret_cast<cudaStream_t>(cuda_stream)); return RFK_OK; }
 int rfk_synchronize(void) {
@@ -537,6 +547,22 @@ int rfk_tonemap(const float* in, float* out, uint8_t* rgba8, size_t W, size_t H,
 int rfk_density_tonemap(const float* bins, float* out, uint8_t* rgba8, size_t W, size_t H, const rfk_post_params* p) {
     return guarded([&]() -> int { return run_post(bins, out, rgba8, W, H, p, true, true); });
 }
+int rfk_density_tonemap_rows(const float* bins_rows, float* out, uint8_t* rgba8, size_t W, size_t H, const rfk_post_params* p,
+                             uint32_t y0, uint32_t y1, uint32_t src_y0, uint32_t src_y1, uint32_t out_y0) {
+    return guarded([&]() -> int {
+        if (!bins_rows || !p || W == 0 || H == 0 || W > 0x3fffffff || H > 0x3fffffff) throw std::invalid_argument("post: bad image arguments");
+        if (!out && !rgba8) throw std::invalid_argument("post: no output buffer");
+        auto d = to_density(*p, W, H);
+        const uint32_t R = (uint32_t)std::max(d.estimator_radius, d.estimator_min);
+        if (y0 >= y1 || y1 > H || src_y0 >= src_y1 || src_y1 > H || out_y0 > y0) throw std::invalid_argument("rfk_density_tonemap_rows: bad row range");
+        if (src_y0 > (y0 > R ? y0 - R : 0) || src_y1 < std::min<uint32_t>((uint32_t)H, y1 + R)) throw std::invalid_argument("rfk_density_tonemap_rows: the slab does not cover the estimator radius around the output rows");
+        d.y0 = (int)y0; d.y1 = (int)y1; d.src_y0 = (int)src_y0; d.src_y1 = (int)src_y1; d.out_y0 = (int)out_y0;
+        kernels::density_tonemap(reinterpret_cast<const float4*>(bins_rows), reinterpret_cast<float4*>(out), reinterpret_cast<uchar4*>(rgba8), d, true, true, current_stream());
+        count_launch(1);
+        cuda_ok(cudaGetLastError(), "density_tonemap launch");
+        return RFK_OK;
+    });
+}
 int rfk_downsample2x(const float* in, float* out, size_t W, size_t H) {
     return guarded([&]() -> int {
         if (!in || !out || !W || !H) throw std::invalid_argument("bad argument");
@@ -613,11 +639,30 @@ struct frame_buffers {
     }
 };
 frame_buffers g_frame;
+
+// device buffers of rfk_render_frame_sharded; every rank (re)allocates them in lockstep (the sizes follow from the request)
+struct sharded_buffers {
+    float4* bins = nullptr; float4* slab = nullptr; float4* image = nullptr; float4* small = nullptr; uchar4* rows8 = nullptr;
+    uchar4* full8 = nullptr; float4* full_image = nullptr;
+    size_t bins_n = 0, slab_n = 0, image_n = 0, small_n = 0, rows8_n = 0, full8_n = 0, full_image_n = 0;
+    unsigned long long* counters = nullptr;  // [0] binned samples of all ranks, [1] barrier token
+    uint64_t generation = 0;
+    cudaEvent_t ev[6] = {};
+    void release() {
+        comm::release_peers();
+        cudaFree(bins); cudaFree(slab); cudaFree(image); cudaFree(small); cudaFree(rows8); cudaFree(full8); cudaFree(full_image); cudaFree(counters);
+        bins = slab = image = small = full_image = nullptr; rows8 = full8 = nullptr; counters = nullptr;
+        bins_n = slab_n = image_n = small_n = rows8_n = full8_n = full_image_n = 0;
+        generation++;
+    }
+};
+sharded_buffers g_sharded;
 }  // namespace
 
 int rfk_release_buffers(void) {
     return guarded([&]() -> int {
         g_frame.release();
+        g_sharded.release();
         release_sim_buffers();
         return RFK_OK;
     });
@@ -664,13 +709,33 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
             cuda_ok(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev), "query L2 size");
             want_hot_map = n * sizeof(float4) > 2 * (size_t)l2;
         }
-        while ((req->max_draw_calls == 0 || calls < req->max_draw_calls) && (req->target_binned == 0 || binned < req->target_binned)) {
-            size_t got = fl->draw_to_bins(reinterpret_cast<float*>(b.bins), n, W, (int)req->drawing_passes);
-            binned += got;
-            iterations += (uint64_t)req->drawing_passes * sim_total_particles();
-            calls++;
-            if (want_hot_map && calls == 1 && got > 0) fl->build_hot_map(reinterpret_cast<const float*>(b.bins), n, W, 0);
-            if (req->target_binned && got == 0 && calls >= 4 && binned == 0) throw std::runtime_error("rfk_render_frame: nothing lands in the histogram");
+        // The reference reads the binned counter back after every draw_to_bins call (flame.cpp:329) and stops when
+        // `accumulated >= quality * W * H` (main.cpp:411). Same stopping rule, same whole calls of `drawing_passes` passes, but
+        // the read-back blocks only where the answer is needed: after the first call (it gives the samples a call lands), then
+        // once per batch of calls enqueued back to back, sized to stop just short of the target so that the count of calls is
+        // the one the call-by-call loop would make.
+        auto more = [&]() { return (req->max_draw_calls == 0 || calls < req->max_draw_calls) && (req->target_binned == 0 || binned < req->target_binned); };
+        uint64_t per_call = 0;
+        while (more()) {
+            uint32_t batch = 1;
+            if (per_call && req->target_binned) {
+                const uint64_t left = req->target_binned - binned;
+                const uint64_t safe = (uint64_t)((double)left / ((double)per_call * 1.01));  // calls that cannot reach the target yet
+                batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(safe, 1), 1u << 20);
+            } else if (per_call) {
+                batch = 1u << 20;
+            }
+            if (req->max_draw_calls) batch = std::min(batch, req->max_draw_calls - calls);
+            for (uint32_t k = 0; k < batch; k++) {
+                fl->draw_to_bins_async(reinterpret_cast<float*>(b.bins), n, W, (int)req->drawing_passes);
+                if (want_hot_map && calls + k == 0) fl->build_hot_map(reinterpret_cast<const float*>(b.bins), n, W, 0);
+            }
+            const uint64_t total = fl->binned_total();  // blocks, like counters_.get_one(0)
+            per_call = (total - binned) / batch;
+            binned = total;
+            calls += batch;
+            iterations += (uint64_t)batch * req->drawing_passes * sim_total_particles();
+            if (req->target_binned && binned == 0 && calls >= 4) throw std::runtime_error("rfk_render_frame: nothing lands in the histogram");
         }
         cuda_ok(cudaEventRecord(b.ev[2], s), "event");
 
@@ -701,6 +766,263 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
             cudaEventElapsedTime(&stats->ms_draw, b.ev[1], b.ev[2]);
             cudaEventElapsedTime(&stats->ms_post, b.ev[2], b.ev[3]);
             cudaEventElapsedTime(&stats->ms_readback, b.ev[3], b.ev[4]);
+        }
+        return RFK_OK;
+    });
+}
+
+// ---- several GPUs: one process per GPU (csrc/comm.cpp) ----
+
+int rfk_comm_unique_id(uint8_t id_out[RFK_COMM_ID_BYTES]) {
+    return guarded([&]() -> int {
+        if (!id_out) throw std::invalid_argument("rfk_comm_unique_id: null argument");
+        comm::unique_id(id_out);
+        return RFK_OK;
+    });
+}
+int rfk_comm_init(const uint8_t id[RFK_COMM_ID_BYTES], int rank, int world) {
+    return guarded([&]() -> int {
+        if (!id) throw std::invalid_argument("rfk_comm_init: null id");
+        g_sharded.release();
+        comm::init(id, rank, world);
+        return RFK_OK;
+    });
+}
+int rfk_comm_destroy(void) {
+    return guarded([&]() -> int {
+        if (current_stream()) cudaStreamSynchronize(current_stream()); else cudaDeviceSynchronize();
+        g_sharded.release();
+        comm::destroy();
+        return RFK_OK;
+    });
+}
+int rfk_comm_rank(void) { return comm::rank(); }
+int rfk_comm_world(void) { return comm::world(); }
+int rfk_comm_p2p(void) { return comm::p2p() ? 1 : 0; }
+int rfk_comm_barrier(void) {
+    return guarded([&]() -> int {
+        if (!comm::active()) throw std::runtime_error("rfk_comm_barrier: rfk_comm_init has not been called");
+        cudaStream_t s = current_stream();
+        if (!g_sharded.counters) {
+            cuda_ok(cudaMalloc(&g_sharded.counters, 8 * sizeof(unsigned long long)), "cudaMalloc(comm counters)");
+            cuda_ok(cudaMemsetAsync(g_sharded.counters, 0, 8 * sizeof(unsigned long long), s), "clear comm counters");
+        }
+        comm::barrier_sum(reinterpret_cast<std::uint64_t*>(g_sharded.counters + 1), 1, s);
+        cuda_ok(cudaStreamSynchronize(s), "rfk_comm_barrier");
+        return RFK_OK;
+    });
+}
+int rfk_comm_reduce_histogram(float* bins, size_t bins_len, int root) {
+    return guarded([&]() -> int {
+        if (!bins) throw std::invalid_argument("rfk_comm_reduce_histogram: null histogram");
+        comm::reduce_histogram(reinterpret_cast<float4*>(bins), bins_len, root, current_stream());
+        return RFK_OK;  // stream-ordered
+    });
+}
+int rfk_comm_row_slab(uint32_t height, uint32_t halo, int rank, int world, rfk_row_slab* out) {
+    return guarded([&]() -> int {
+        if (!out || height > 0x3fffffffu || halo > 0x3fffffffu) throw std::invalid_argument("rfk_comm_row_slab: bad argument");
+        const comm::row_slab s = comm::slab_of((int)height, (int)halo, rank, world);
+        *out = rfk_row_slab{(uint32_t)s.y0, (uint32_t)s.y1, (uint32_t)s.src_y0, (uint32_t)s.src_y1};
+        return RFK_OK;
+    });
+}
+
+int rfk_render_frame_sharded(rfk_flame* f, const rfk_sharded_request* sreq, uint8_t* rgba8_out, float* image_out, rfk_sharded_stats* stats) {
+    return guarded([&]() -> int {
+        if (!f || !sreq) throw std::invalid_argument("rfk_render_frame_sharded: null argument");
+        if (!comm::active()) throw std::runtime_error("rfk_render_frame_sharded: rfk_comm_init has not been called");
+        const rfk_frame_request* req = &sreq->frame;
+        const int rank = comm::rank(), world = comm::world();
+        const bool want8 = sreq->want_rgba8 != 0, wantf = sreq->want_image != 0;
+        if (!want8 && !wantf) throw std::invalid_argument("rfk_render_frame_sharded: neither want_rgba8 nor want_image");
+        if (rank == 0 && ((want8 && !rgba8_out) || (wantf && !image_out))) throw std::invalid_argument("rfk_render_frame_sharded: rank 0 needs the output buffers it asked for");
+        if (!req->width || !req->height) throw std::invalid_argument("rfk_render_frame_sharded: empty image");
+        if (!req->target_binned && !req->max_draw_calls) throw std::invalid_argument("rfk_render_frame_sharded: neither target_binned nor max_draw_calls given");
+        if (!req->drawing_passes) throw std::invalid_argument("rfk_render_frame_sharded: drawing_passes is 0");
+        flame* fl = F(f);
+        if (fl->options().deterministic) throw std::invalid_argument("rfk_render_frame_sharded: not with the deterministic kernel option (use rfk_flame_draw_to_bins + rfk_comm_reduce_histogram)");
+        const int ss = req->supersample > 1 ? (int)req->supersample : 1;
+        if (ss > 16) throw std::invalid_argument("rfk_render_frame_sharded: supersample > 16");
+        const int OW = (int)req->width, OH = (int)req->height, W = OW * ss, H = OH * ss;
+        const size_t n = (size_t)W * H;
+        cudaStream_t s = current_stream();
+
+        rfk_post_params pp;
+        rfk_flame_post_params(f, &pp);
+        pp.scale_constant = (float)(1.0 / std::pow(10.0, (double)req->scale_constant_exp));
+        auto d = to_density(pp, W, H);
+        const int halo = std::max(d.estimator_radius, d.estimator_min);
+
+        // geometry of every rank: output rows, the rows density estimation produces for them (more than the output rows when
+        // the spatial filter reads across the slab border), and the source rows of those
+        std::vector<comm::row_slab> out_slabs(world), de_slabs(world);
+        for (int r = 0; r < world; r++) {
+            out_slabs[r] = comm::slab_of(OH, 0, r, world);
+            comm::row_slab de = out_slabs[r];
+            if (ss > 1 && de.y1 > de.y0) kernels::spatial_filter_rows(ss, req->filter_radius, out_slabs[r].y0, out_slabs[r].y1, H, &de.y0, &de.y1);
+            de.src_y0 = std::max(0, de.y0 - halo);
+            de.src_y1 = std::min(H, de.y1 + halo);
+            if (de.y1 == de.y0) de.src_y0 = de.src_y1 = de.y0;
+            de_slabs[r] = de;
+        }
+        const comm::row_slab mine_out = out_slabs[rank], mine = de_slabs[rank];
+        const size_t out_rows = (size_t)(mine_out.y1 - mine_out.y0), de_rows = (size_t)(mine.y1 - mine.y0), src_rows = (size_t)(mine.src_y1 - mine.src_y0);
+        size_t max_out_rows = 0, max_de_rows = 0, max_src_rows = 0;
+        for (int r = 0; r < world; r++) {
+            max_out_rows = std::max(max_out_rows, (size_t)(out_slabs[r].y1 - out_slabs[r].y0));
+            max_de_rows = std::max(max_de_rows, (size_t)(de_slabs[r].y1 - de_slabs[r].y0));
+            max_src_rows = std::max(max_src_rows, (size_t)(de_slabs[r].src_y1 - de_slabs[r].src_y0));
+        }
+
+        sharded_buffers& b = g_sharded;
+        bool reallocated = false;
+        auto grow = [&](auto*& ptr, size_t& have, size_t want, const char* what) {
+            if (have >= want) return;
+            comm::release_peers();  // the peers' mappings of the old buffers die with them
+            cudaFree(ptr); ptr = nullptr; have = 0;
+            cuda_ok(cudaMalloc(&ptr, want * sizeof(*ptr)), what);
+            have = want;
+            reallocated = true;
+        };
+        // the same sizes on every rank (maxima over the ranks), so that all ranks re-allocate in the same call
+        grow(b.bins, b.bins_n, n, "cudaMalloc(bins)");
+        grow(b.slab, b.slab_n, std::max<size_t>(1, max_src_rows * W), "cudaMalloc(row slab)");
+        if (ss > 1) grow(b.image, b.image_n, std::max<size_t>(1, max_de_rows * W), "cudaMalloc(slab image)");
+        grow(b.small, b.small_n, std::max<size_t>(1, max_out_rows * OW), "cudaMalloc(slab rows)");
+        grow(b.rows8, b.rows8_n, std::max<size_t>(1, max_out_rows * OW), "cudaMalloc(slab rows rgba8)");
+        if (want8) grow(b.full8, b.full8_n, (size_t)OW * OH, "cudaMalloc(rgba8)");
+        if (wantf) grow(b.full_image, b.full_image_n, (size_t)OW * OH, "cudaMalloc(image)");
+        if (!b.counters) { cuda_ok(cudaMalloc(&b.counters, 8 * sizeof(unsigned long long)), "cudaMalloc(comm counters)"); reallocated = true; }
+        if (reallocated) b.generation++;
+        for (auto& e : b.ev) if (!e) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
+        const comm::peer_buffers& peers = comm::exchange(b.bins, b.full8, b.full_image, b.generation, s);
+        const bool p2p = comm::p2p();
+
+        cuda_ok(cudaEventRecord(b.ev[0], s), "event");
+        fl->warmup(req->warmup_passes, req->tss_width);
+        cuda_ok(cudaMemsetAsync(b.bins, 0, n * sizeof(float4), s), "clear bins");
+        cuda_ok(cudaMemsetAsync(b.counters, 0, 8 * sizeof(unsigned long long), s), "clear counters");
+        cuda_ok(cudaEventRecord(b.ev[1], s), "event");
+
+        // ---- draw: every rank the same number of passes ----
+        const unsigned long long* binned_dev = flame_binned_counter_dev(*fl);
+        uint64_t passes = 0, binned_global = 0;
+        uint32_t calls = 0;
+        auto global_binned = [&]() -> uint64_t {  // sum over the ranks of the binned counters; blocks
+            cuda_ok(cudaMemcpyAsync(b.counters, binned_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s), "copy binned counter");
+            comm::barrier_sum(reinterpret_cast<std::uint64_t*>(b.counters), 1, s);
+            unsigned long long v = 0;
+            cuda_ok(cudaMemcpyAsync(&v, b.counters, sizeof v, cudaMemcpyDeviceToHost, s), "read binned counter");
+            cuda_ok(cudaStreamSynchronize(s), "read binned counter");
+            return v;
+        };
+        auto draw_passes = [&](uint64_t count) {
+            while (count) {
+                if (req->max_draw_calls && calls >= req->max_draw_calls) return;
+                const int now = (int)std::min<uint64_t>(count, req->drawing_passes);
+                fl->draw_to_bins_async(reinterpret_cast<float*>(b.bins), n, W, now);
+                passes += now; count -= now; calls++;
+            }
+        };
+        double per_pass = 0.0;  // samples one pass of ALL ranks lands
+        if (!req->target_binned) {
+            draw_passes((uint64_t)req->max_draw_calls * req->drawing_passes);
+        } else {
+            // a first call on every rank measures what a pass lands; the rest is enqueued without a host round trip
+            const uint64_t even_share = (req->target_binned / ((uint64_t)world * sim_total_particles())) + 1;  // passes if every iteration binned
+            draw_passes(std::min<uint64_t>(req->drawing_passes, std::max<uint64_t>(1, even_share / 2)));
+            binned_global = global_binned();
+            if (binned_global < req->target_binned) {
+                // the rest in one go, with a 0.2 % margin; the draw calls stay in flight — the exchange below does not wait for
+                // their count, which is read together with the image (a shortfall, rare, costs one more round there)
+                per_pass = passes ? (double)binned_global / (double)passes : 0.0;
+                const double left = (double)(req->target_binned - binned_global);
+                draw_passes(per_pass > 0.0 ? std::max<uint64_t>(1, (uint64_t)std::ceil(left / per_pass * 1.002)) : req->drawing_passes);
+            }
+        }
+        cuda_ok(cudaEventRecord(b.ev[2], s), "event");
+
+        uint64_t final_binned = 0;
+        for (int attempt = 0;; attempt++) {
+            // ---- reduce-scatter over row slabs with halo; the all-reduce of the counters is also the barrier in front of it ----
+            cuda_ok(cudaMemcpyAsync(b.counters, binned_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s), "copy binned counter");
+            comm::barrier_sum(reinterpret_cast<std::uint64_t*>(b.counters), 1, s);
+            if (src_rows) {
+                if (p2p) {
+                    kernels::slab_reduce(peers.bins, world, (size_t)(H - mine.src_y1) * W, src_rows * W, b.slab, s);
+                    count_launch(1);
+                }
+            }
+            if (!p2p) comm::reduce_scatter_slabs_nccl(b.bins, b.slab, W, H, de_slabs, s);
+            cuda_ok(cudaGetLastError(), "row slab reduce");
+            if (attempt == 0) cuda_ok(cudaEventRecord(b.ev[3], s), "event");
+
+            // ---- density estimation + tonemap (+ spatial filter) on this rank's rows; finished rows go to rank 0 ----
+            if (de_rows) {
+                auto ds = d;
+                ds.y0 = mine.y0; ds.y1 = mine.y1; ds.src_y0 = mine.src_y0; ds.src_y1 = mine.src_y1;
+                if (ss == 1) {
+                    if (p2p) {  // straight into rank 0's images, rows addressed by their image row
+                        ds.out_y0 = 0;
+                        kernels::density_tonemap(b.slab, wantf ? peers.root_image : nullptr, want8 ? peers.root_rgba8 : nullptr, ds, true, true, s);
+                    } else {
+                        ds.out_y0 = mine.y0;
+                        kernels::density_tonemap(b.slab, wantf ? b.small : nullptr, want8 ? b.rows8 : nullptr, ds, true, true, s);
+                    }
+                    count_launch(1);
+                } else {
+                    ds.out_y0 = mine.y0;
+                    kernels::density_tonemap(b.slab, b.image, nullptr, ds, true, true, s);
+                    kernels::spatial_downsample_rows(b.image, b.small, OW, OH, ss, req->filter_radius, mine_out.y0, mine_out.y1, mine.y0, s);
+                    count_launch(2);
+                    if (want8) {
+                        kernels::pack_rgba8(b.small, p2p ? peers.root_rgba8 + (size_t)mine_out.y0 * OW : b.rows8, out_rows * OW, s);
+                        count_launch(1);
+                    }
+                    if (wantf && p2p)
+                        cuda_ok(cudaMemcpyAsync(peers.root_image + (size_t)mine_out.y0 * OW, b.small, out_rows * OW * sizeof(float4), cudaMemcpyDefault, s), "rows to rank 0");
+                }
+                cuda_ok(cudaGetLastError(), "density_tonemap launch");
+            }
+            if (!p2p) {
+                if (want8) comm::gather_slabs_nccl(rank == 0 ? nullptr : b.rows8, b.full8, (size_t)OW * sizeof(uchar4), out_slabs, s);
+                if (wantf) comm::gather_slabs_nccl(rank == 0 ? nullptr : b.small, b.full_image, (size_t)OW * sizeof(float4), out_slabs, s);
+                if (rank == 0 && out_rows) {  // rank 0's own rows
+                    if (want8) cuda_ok(cudaMemcpyAsync(b.full8 + (size_t)mine_out.y0 * OW, b.rows8, out_rows * OW * sizeof(uchar4), cudaMemcpyDeviceToDevice, s), "own rows");
+                    if (wantf) cuda_ok(cudaMemcpyAsync(b.full_image + (size_t)mine_out.y0 * OW, b.small, out_rows * OW * sizeof(float4), cudaMemcpyDeviceToDevice, s), "own rows");
+                }
+            }
+            if (attempt == 0) cuda_ok(cudaEventRecord(b.ev[4], s), "event");
+
+            // ---- barrier: all rows have landed on rank 0, and no rank clears its histogram before its peers have read it ----
+            comm::barrier_sum(reinterpret_cast<std::uint64_t*>(b.counters + 1), 1, s);
+            unsigned long long counted = 0;
+            cuda_ok(cudaMemcpyAsync(&counted, b.counters, sizeof counted, cudaMemcpyDeviceToHost, s), "read binned counter");
+            if (rank == 0) {
+                if (want8) cuda_ok(cudaMemcpyAsync(rgba8_out, b.full8, (size_t)OW * OH * sizeof(uchar4), cudaMemcpyDeviceToHost, s), "read back rgba8");
+                if (wantf) cuda_ok(cudaMemcpyAsync(image_out, b.full_image, (size_t)OW * OH * sizeof(float4), cudaMemcpyDeviceToHost, s), "read back image");
+            }
+            cuda_ok(cudaEventRecord(b.ev[5], s), "event");
+            cuda_ok(cudaStreamSynchronize(s), "rfk_render_frame_sharded");
+            final_binned = counted;
+            const bool capped = req->max_draw_calls && calls >= req->max_draw_calls;
+            if (!req->target_binned || final_binned >= req->target_binned || capped || attempt >= 8) break;
+            // short of the target (the in-bounds fraction drifted by more than the margin): top up and redo the exchange
+            per_pass = passes ? (double)final_binned / (double)passes : 0.0;
+            const double left = (double)(req->target_binned - final_binned);
+            draw_passes(std::max<uint64_t>(1, per_pass > 0.0 ? (uint64_t)std::ceil(left / per_pass * 1.01) : req->drawing_passes));
+        }
+        if (stats) {
+            stats->iterations_global = (uint64_t)world * passes * sim_total_particles();
+            stats->binned_global = final_binned;
+            stats->passes = passes; stats->draw_calls = calls; stats->p2p = p2p ? 1 : 0;
+            stats->y0 = (uint32_t)mine_out.y0; stats->y1 = (uint32_t)mine_out.y1;
+            cudaEventElapsedTime(&stats->ms_warmup, b.ev[0], b.ev[1]);
+            cudaEventElapsedTime(&stats->ms_draw, b.ev[1], b.ev[2]);
+            cudaEventElapsedTime(&stats->ms_reduce, b.ev[2], b.ev[3]);
+            cudaEventElapsedTime(&stats->ms_post, b.ev[3], b.ev[4]);
+            cudaEventElapsedTime(&stats->ms_readback, b.ev[4], b.ev[5]);
         }
         return RFK_OK;
     });

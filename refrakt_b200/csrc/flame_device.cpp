@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <list>
 #include <mutex>
 #include <random>
 #include <set>
@@ -101,8 +102,12 @@ struct sim_state {
 sim_state g_sim;
 std::set<flame*> g_active_flames;  // src/flame.hpp:173
 
+// compiled modules by (hash of source text + options): cubin and compile log. Bounded: an animation whose frames change
+// parameter VALUES builds a new value-specialised module per frame (kernel option specialize = 1); the oldest entries go.
+struct cubin_entry { std::string key; std::vector<char> cubin; std::string log; };
 std::mutex g_cache_mutex;
-std::unordered_map<std::string, std::pair<std::vector<char>, std::string>> g_cubin_cache;  // source text + options -> cubin, compile log
+std::list<cubin_entry> g_cubin_cache;  // most recently used first
+constexpr std::size_t kCubinCacheEntries = 24;
 
 }  // namespace
 
@@ -118,10 +123,11 @@ std::vector<char> compile_cubin(const std::string& source, const kernel_options&
     const std::string key = source + "#" + std::to_string(opt.math_mode) + (opt.fmad ? "" : "#M") + "#" + std::to_string(auto_min_blocks);
     {
         std::lock_guard<std::mutex> lock(g_cache_mutex);
-        auto it = g_cubin_cache.find(key);
-        if (it != g_cubin_cache.end()) {
-            if (log_out) *log_out = it->second.second;
-            return it->second.first;
+        for (auto it = g_cubin_cache.begin(); it != g_cubin_cache.end(); ++it) {
+            if (it->key != key) continue;
+            g_cubin_cache.splice(g_cubin_cache.begin(), g_cubin_cache, it);
+            if (log_out) *log_out = it->log;
+            return it->cubin;
         }
     }
     // RFK_SOURCE_DUMP_DIR: keep the generated translation unit on disk under the name the line info refers to
@@ -164,7 +170,8 @@ std::vector<char> compile_cubin(const std::string& source, const kernel_options&
     nvrtcGetCUBIN(prog, cubin.data());
     nvrtcDestroyProgram(&prog);
     std::lock_guard<std::mutex> lock(g_cache_mutex);
-    g_cubin_cache[key] = {cubin, log};
+    g_cubin_cache.push_front(cubin_entry{key, cubin, log});
+    while (g_cubin_cache.size() > kCubinCacheEntries) g_cubin_cache.pop_back();
     return cubin;
 }
 
@@ -818,6 +825,8 @@ std::size_t flame::reference_draw_to_bins(float* bins, std::size_t bins_len, std
 }
 
 bool flame_uses_baked(const flame& f) { return const_cast<flame&>(f).device() && const_cast<flame&>(f).device()->use_baked; }
+
+const unsigned long long* flame_binned_counter_dev(flame& f) { return f.device() ? f.device()->counters : nullptr; }
 
 void flame_copy_particles(flame& f, float* out) {
     if (!f.device() || !f.device()->particles) throw std::runtime_error("no particle buffer (warmup first)");

@@ -33,6 +33,7 @@ void flame_animate_host(flame& f, float tss_width, int temporal_samples, float* 
 void flame_kernel_info(flame& f, const char* kernel, int* regs, int* smem_bytes, int* blocks_per_sm);
 void flame_read_counters(flame& f, unsigned long long* out, int n);
 bool flame_uses_baked(const flame& f);  // the last warmup chose the value-specialised kernels (kernel option specialize)
+const unsigned long long* flame_binned_counter_dev(flame& f);  // device address of the binned-samples counter (counters[0])
 void flame_copy_particles(flame& f, float* out);  // the flame's particle buffer (P x float4), to host
 
 }  // namespace rfk

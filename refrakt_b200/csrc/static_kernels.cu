@@ -2,6 +2,7 @@
 // temporal-sample parameter inflation, density estimation + tonemap.
 #include "static_kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
@@ -73,7 +74,8 @@ __global__ void animate_kernel(const float* __restrict__ fp, float* __restrict__
     if (ts >= temporal_samples) return;
     int half_width = temporal_samples / 2;
     int sample_pos = ts - half_width;
-    float dt = sample_pos / float(half_width) * temporal_sample_width;
+    // one temporal sample: no motion blur (the reference always runs multiples of 32; 0 / 0 here would poison every affine)
+    float dt = half_width ? sample_pos / float(half_width) * temporal_sample_width : 0.0f;
     float* dst = fp_inflated + (size_t)ts * total_params;
     for (int i = 0; i < total_params; i++) dst[i] = fp[i];
     for (int k = 0; k < num_xforms; k++) {
@@ -152,9 +154,12 @@ __global__ void downsample2x_kernel(const float4* __restrict__ in, float4* __res
 
 struct filter_taps { float w[64]; int n; int offset; };
 
-__global__ void spatial_downsample_kernel(const float4* __restrict__ in, float4* __restrict__ out, int W, int H, int ss, const __grid_constant__ filter_taps t) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
+// Output rows [oy0, oy1) of the W x H image; `in` holds the rows [in_y0, ...) of the supersampled image (row slabs of a
+// multi-GPU frame; in_y0 = 0, oy0 = 0, oy1 = H for the whole image); output row y goes to row y - oy0 of `out`.
+__global__ void spatial_downsample_kernel(const float4* __restrict__ in, float4* __restrict__ out, int W, int H, int ss, const __grid_constant__ filter_taps t,
+                                          int oy0, int oy1, int in_y0) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = oy0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= oy1) return;
     const int IW = W * ss, IH = H * ss;
     const int x0 = x * ss - t.offset, y0 = y * ss - t.offset;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -166,13 +171,44 @@ __global__ void spatial_downsample_kernel(const float4* __restrict__ in, float4*
             int sx = x0 + i;
             if (sx < 0 || sx >= IW) continue;
             float w = t.w[i] * t.w[j];
-            float4 v = __ldg(in + (size_t)sy * IW + sx);
+            float4 v = __ldg(in + (size_t)(sy - in_y0) * IW + sx);
             acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y); acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
             wsum += w;
         }
     }
     float inv = wsum > 0.0f ? 1.0f / wsum : 0.0f;
-    out[(size_t)y * W + x] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    out[(size_t)(y - oy0) * W + x] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
+// Sum of the same `count` float4 bins of up to 16 histograms — this GPU's and its peers', mapped over NVLink — in the fixed
+// order src[0] + src[1] + ...: the reduce-scatter of a multi-GPU frame, pulled by the rank that owns the slab
+// (csrc/comm.cpp). Every thread keeps four 128-bit loads per source in flight.
+struct slab_sources { const float4* src[16]; int n; };
+__global__ void __launch_bounds__(256) slab_reduce_kernel(const __grid_constant__ slab_sources srcs, size_t offset, size_t count, float4* __restrict__ out) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < count; i += 4 * stride) {
+        float4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) a[u] = srcs.src[0][offset + i + u * stride];
+        for (int k = 1; k < srcs.n; k++) {
+            float4 b[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) b[u] = srcs.src[k][offset + i + u * stride];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { a[u].x += b[u].x; a[u].y += b[u].y; a[u].z += b[u].z; a[u].w += b[u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) out[i + u * stride] = a[u];
+    }
+    for (; i < count; i += stride) {
+        float4 a = srcs.src[0][offset + i];
+        for (int k = 1; k < srcs.n; k++) {
+            const float4 b = srcs.src[k][offset + i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        out[i] = a;
+    }
 }
 
 __global__ void pack_rgba8_kernel(const float4* __restrict__ in, uchar4* __restrict__ out, size_t count) {
@@ -611,11 +647,39 @@ int spatial_filter_taps(int ss, float filter_radius, float* taps_out) {
 }
 
 void spatial_downsample(const float4* in, float4* out, int W, int H, int ss, float filter_radius, cudaStream_t s) {
+    spatial_downsample_rows(in, out, W, H, ss, filter_radius, 0, H, 0, s);
+}
+
+void spatial_downsample_rows(const float4* in, float4* out, int W, int H, int ss, float filter_radius, int oy0, int oy1, int in_y0, cudaStream_t s) {
+    if (oy1 <= oy0) return;
     filter_taps t{};
     t.n = spatial_filter_taps(ss, filter_radius, t.w);
     t.offset = (t.n - ss) / 2;
-    dim3 block(32, 8), grid((W + 31) / 32, (H + 7) / 8);
-    spatial_downsample_kernel<<<grid, block, 0, s>>>(in, out, W, H, ss, t);
+    dim3 block(32, 8), grid((W + 31) / 32, (oy1 - oy0 + 7) / 8);
+    spatial_downsample_kernel<<<grid, block, 0, s>>>(in, out, W, H, ss, t, oy0, oy1, in_y0);
+}
+
+void spatial_filter_rows(int ss, float filter_radius, int oy0, int oy1, int full_height, int* in_y0, int* in_y1) {
+    filter_taps t{};
+    t.n = spatial_filter_taps(ss, filter_radius, t.w);
+    t.offset = (t.n - ss) / 2;
+    const int lo = oy0 * ss - t.offset, hi = (oy1 - 1) * ss - t.offset + t.n;
+    *in_y0 = lo < 0 ? 0 : lo;
+    *in_y1 = hi > full_height ? full_height : hi;
+}
+
+void slab_reduce(const float4* const* sources, int n_sources, std::size_t offset, std::size_t count, float4* out, cudaStream_t s) {
+    if (!count || n_sources <= 0) return;
+    if (n_sources > 16) throw std::invalid_argument("slab_reduce: more than 16 sources");
+    slab_sources srcs{};
+    srcs.n = n_sources;
+    for (int k = 0; k < n_sources; k++) srcs.src[k] = sources[k];
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const std::size_t want = (count + 4 * 256 - 1) / (4 * 256);
+    const unsigned grid = (unsigned)std::min<std::size_t>(want, (std::size_t)sms * 8);  // eight 256-thread CTAs per SM: a multiple of the SM count
+    slab_reduce_kernel<<<grid, 256, 0, s>>>(srcs, offset, count, out);
 }
 
 void pack_rgba8(const float4* in, uchar4* out, std::size_t count, cudaStream_t s) {

@@ -67,5 +67,13 @@ int spatial_filter_taps(int ss, float filter_radius, float* taps_out);
 // float4 in [0, 1] -> RGBA8, round to nearest (the GL UNORM conversion of buffer_objects.hpp:113-119)
 void pack_rgba8(const float4* in, uchar4* out, std::size_t count, cudaStream_t s);
 void spatial_downsample(const float4* in, float4* out, int W, int H, int ss, float filter_radius, cudaStream_t s);
+// the same for the output rows [oy0, oy1) only, written to rows 0 .. oy1 - oy0 of `out`; `in` starts at row in_y0 of the
+// supersampled image (row slabs of a multi-GPU frame). spatial_filter_rows: the supersampled rows [in_y0, in_y1) those
+// output rows read.
+void spatial_downsample_rows(const float4* in, float4* out, int W, int H, int ss, float filter_radius, int oy0, int oy1, int in_y0, cudaStream_t s);
+void spatial_filter_rows(int ss, float filter_radius, int oy0, int oy1, int full_height, int* in_y0, int* in_y1);
+// out[i] = sources[0][offset + i] + sources[1][offset + i] + ... for i < count (n_sources <= 16; the sources may be peer
+// memory): the pulled reduce-scatter of a multi-GPU frame
+void slab_reduce(const float4* const* sources, int n_sources, std::size_t offset, std::size_t count, float4* out, cudaStream_t s);
 
 }  // namespace rfk::kernels
