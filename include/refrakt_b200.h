@@ -217,6 +217,22 @@ int rfk_flame_screen_affine(const rfk_flame* f, size_t bins_width, size_t bins_h
  * rotation_frequency by degrees * rotation_frequency */
 int rfk_flame_rotate_xforms(rfk_flame* f, float degrees);
 
+/* <motion> children of an xform: motion_info, src/flame.hpp:15-19, :36. The reference declares the map and never fills it
+ * (its parser is commented out, src/flame.cpp:199-210). Parsed here as that block intends: one entry per animated attribute
+ * of the element (a variation, a parameter, weight, color, color_speed, opacity), sharing its motion_frequency and
+ * motion_function; the attribute's value is the amplitude. rfk_flame_apply_motion evaluates them as flam3 does,
+ * field = loaded value + amplitude * f(frequency * time) with f = sin | triangle | hill, and marks the flame for warmup;
+ * it returns the number of fields written. rfk_render --motion applies it per frame (time = frame / fps). */
+typedef struct rfk_motion_info {
+    float freq, amplitude;
+    char function[16];
+    char target[64];
+} rfk_motion_info;
+int rfk_flame_motion_count(const rfk_flame* f, int xform);
+int rfk_flame_get_motion(const rfk_flame* f, int xform, int k, rfk_motion_info* out); /* std::map order = alphabetical by target */
+int rfk_flame_apply_motion(rfk_flame* f, float time_seconds);
+float rfk_motion_function(const char* name, float x);
+
 /* ---- affine helpers: flame::rotate_affine / scale_affine / translate_affine, src/flame.hpp:97-128 ---- */
 void rfk_rotate_affine(const float a[6], float deg, float out[6]);
 void rfk_scale_affine(const float a[6], float scale, float out[6]);

@@ -170,6 +170,7 @@ class Xform:
     color_speed: np.float32 = f32(0)
     rotation_frequency: np.float32 = f32(0)
     opacity: np.float32 = f32(0)
+    motion: Dict[str, tuple] = field(default_factory=dict)  # flame.hpp:36: target -> (freq, function, amplitude); flame.cpp:199-210 as intended
 
 
 @dataclass
@@ -236,6 +237,15 @@ def load_flame_string(text: str, vt: VariationTable) -> Optional[Flame]:
                 elif name == "coefs": x.affine = _parse_strings(val, 6, stod_to_float, f32(0))
                 elif name == "post": x.post = _parse_strings(val, 6, stod_to_float, f32(0))
                 else: bad = True
+            for m in child:  # the commented-out block of flame.cpp:199-210, with the attribute value as the amplitude
+                if m.tag != "motion":
+                    continue
+                freq = f32(strtod_prefix(m.attrib.get("motion_frequency", "")))
+                fn = m.attrib.get("motion_function", "")
+                for name, val in m.attrib.items():
+                    if name not in ("motion_frequency", "motion_function"):
+                        x.motion[name] = (freq, fn, f32(strtod_prefix(val)))
+            x.motion = dict(sorted(x.motion.items()))
             # std::map iterates alphabetically
             x.variations = dict(sorted(x.variations.items()))
             x.var_param = dict(sorted(x.var_param.items()))
@@ -250,6 +260,45 @@ def load_flame_string(text: str, vt: VariationTable) -> Optional[Flame]:
         return None
     f.buffer_map = make_buffer_map(f)
     return f
+
+
+def motion_function(name: str, x) -> np.float32:
+    """flam3's motion functions of the phase x = frequency * time (the reference declares motion_info and never evaluates it)"""
+    import math
+    x = float(f32(x))
+    if name == "sin":
+        return f32(math.sin(2.0 * math.pi * x))
+    if name == "hill":
+        return f32((1.0 - math.cos(2.0 * math.pi * x)) * 0.5)
+    if name == "triangle":
+        fr = math.fmod(x, 1.0)
+        if fr < 0.0:
+            fr += 1.0
+        if fr <= 0.25:
+            return f32(4.0 * fr)
+        if fr <= 0.75:
+            return f32(-4.0 * fr + 2.0)
+        return f32(4.0 * fr - 4.0)
+    return f32(0.0)
+
+
+def apply_motion(f: Flame, base: Flame, time) -> int:
+    """f's animated fields = base's loaded values + amplitude * function(freq * time); returns the fields written"""
+    written = 0
+    pairs = list(zip(f.xforms, base.xforms)) + ([(f.final_xform, base.final_xform)] if f.final_xform is not None else [])
+    for x, b in pairs:
+        for name, (freq, fn, amp) in b.motion.items():
+            delta = f32(amp * motion_function(fn, f32(freq * f32(time))))
+            if name in ("weight", "color", "color_speed", "opacity"):
+                setattr(x, name, f32(getattr(b, name) + delta))
+            elif name in x.variations:
+                x.variations[name] = f32(b.variations[name] + delta)
+            elif name in x.var_param:
+                x.var_param[name] = f32(b.var_param[name] + delta)
+            else:
+                continue
+            written += 1
+    return written
 
 
 # ----------------------------------------------------------------------------------------
@@ -705,6 +754,19 @@ class Oracle:
         H = bins.size // 4 // W
         ss = screen_space_affine(self.flame, W, H)
         return int(self.lib.orc_draw_to_bins(_p(bins, ctypes.c_float), ctypes.c_size_t(W), ctypes.c_size_t(H), _p(ss, ctypes.c_float), num_iter, int(count_xforms)))
+
+    def draw_accumulate(self, W: int, H: int, num_iter: int) -> int:
+        """the passes of draw_to_bins into per-thread histograms that persist until merge_private (bench.py's CPU baseline)"""
+        ss = screen_space_affine(self.flame, W, H)
+        self.lib.orc_draw_accumulate.restype = ctypes.c_ulonglong
+        return int(self.lib.orc_draw_accumulate(ctypes.c_size_t(W), ctypes.c_size_t(H), _p(ss, ctypes.c_float), num_iter))
+
+    def merge_private(self, bins: np.ndarray):
+        assert bins.dtype == np.float32 and bins.flags.c_contiguous
+        self.lib.orc_merge_private(_p(bins, ctypes.c_float))
+
+    def release_private(self):
+        self.lib.orc_release_private()
 
     def xform_picks(self, n):
         out = np.zeros(n, dtype=np.uint64)

@@ -62,6 +62,10 @@ class FrameStats(C.Structure):
                 ("ms_warmup", C.c_float), ("ms_draw", C.c_float), ("ms_post", C.c_float), ("ms_readback", C.c_float)]
 
 
+class MotionInfo(C.Structure):
+    _fields_ = [("freq", C.c_float), ("amplitude", C.c_float), ("function", C.c_char * 16), ("target", C.c_char * 64)]
+
+
 class RowSlab(C.Structure):
     _fields_ = [("y0", C.c_uint32), ("y1", C.c_uint32), ("src_y0", C.c_uint32), ("src_y1", C.c_uint32)]
 
@@ -143,6 +147,10 @@ SIGNATURES = {
     "rfk_flame_xform_counts": (_i, [_vp, C.POINTER(C.c_uint64), _i]),
     "rfk_flame_screen_affine": (_i, [_vp, _sz, _sz, _fpp]),
     "rfk_flame_rotate_xforms": (_i, [_vp, _f]),
+    "rfk_flame_motion_count": (_i, [_vp, _i]),
+    "rfk_flame_get_motion": (_i, [_vp, _i, _i, C.POINTER(MotionInfo)]),
+    "rfk_flame_apply_motion": (_i, [_vp, _f]),
+    "rfk_motion_function": (_f, [_cp, _f]),
     "rfk_rotate_affine": (None, [_fpp, _f, _fpp]),
     "rfk_scale_affine": (None, [_fpp, _f, _fpp]),
     "rfk_translate_affine": (None, [_fpp, _fpp, _fpp]),
@@ -478,6 +486,18 @@ class Flame:
 
     def binned_total(self) -> int: return int(_check(lib().rfk_flame_binned_total(self.handle), "binned_total"))
     def reset_animation(self): _check(lib().rfk_flame_reset_animation(self.handle), "reset_animation")
+    def motion(self, index: int) -> dict:
+        """the <motion> entries of an xform: target -> (frequency, function, amplitude)"""
+        out = {}
+        for k in range(_check(lib().rfk_flame_motion_count(self.handle, index), "motion_count")):
+            m = MotionInfo()
+            _check(lib().rfk_flame_get_motion(self.handle, index, k, C.byref(m)), "get_motion")
+            out[m.target.decode()] = (m.freq, m.function.decode(), m.amplitude)
+        return out
+
+    def apply_motion(self, time_seconds: float) -> int:
+        return int(_check(lib().rfk_flame_apply_motion(self.handle, time_seconds), "apply_motion"))
+
     def rotate_xforms(self, degrees: float): _check(lib().rfk_flame_rotate_xforms(self.handle, degrees), "rotate_xforms")
 
     def xform_counts(self, n: int) -> np.ndarray:

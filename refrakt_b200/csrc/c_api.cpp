@@ -511,6 +511,29 @@ int rfk_flame_rotate_xforms(rfk_flame* f, float degrees) {
     return RFK_OK;
 }
 
+int rfk_flame_motion_count(const rfk_flame* f, int xform) {
+    const flame_xform* x = f ? xform_at(F(f), xform) : nullptr;
+    return x ? (int)x->motion.size() : fail(RFK_E_NOTFOUND, "no such xform");
+}
+int rfk_flame_get_motion(const rfk_flame* f, int xform, int k, rfk_motion_info* out) {
+    const flame_xform* x = (f && out) ? xform_at(F(f), xform) : nullptr;
+    if (!x) return fail(RFK_E_NOTFOUND, "no such xform");
+    if (k < 0 || k >= (int)x->motion.size()) return fail(RFK_E_NOTFOUND, "no such motion entry");
+    auto it = x->motion.begin();
+    std::advance(it, k);
+    std::memset(out, 0, sizeof *out);
+    out->freq = it->second.freq;
+    out->amplitude = it->second.amplitude;
+    std::strncpy(out->function, it->second.function.c_str(), sizeof out->function - 1);
+    std::strncpy(out->target, it->first.c_str(), sizeof out->target - 1);
+    return RFK_OK;
+}
+int rfk_flame_apply_motion(rfk_flame* f, float time_seconds) {
+    if (!f) return fail(RFK_E_INVALID, "null flame");
+    return F(f)->apply_motion(time_seconds);
+}
+float rfk_motion_function(const char* name, float x) { return name ? flame::motion_function(name, x) : 0.0f; }
+
 void rfk_rotate_affine(const float a[6], float deg, float out[6]) {
     flame_xform::affine_t in{a[0], a[1], a[2], a[3], a[4], a[5]};
     auto r = flame::rotate_affine(in, deg);

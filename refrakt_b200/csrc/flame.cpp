@@ -218,6 +218,19 @@ std::unique_ptr<flame> flame::load_flame_string(const std::string& xml_text, con
                     else if (name == "post") xform.post = parse_strings<float, 6>(&value, [](auto& v) { return (float)std::stod(v); });
                     else errors += "Unknown attribute " + name + " in flame " + origin + "\n";
                 }
+                // src/flame.cpp:199-210 (commented out there): every attribute of a <motion> child other than its frequency and
+                // function names an animated field of this xform
+                for (const auto& motion : node.children) {
+                    if (motion.name != "motion") continue;
+                    motion_info m{};
+                    m.freq = xml::as_float(motion.attribute("motion_frequency"));
+                    if (const std::string* fn = motion.attribute("motion_function")) m.function = *fn;
+                    for (const auto& [name, value] : motion.attributes) {
+                        if (name == "motion_frequency" || name == "motion_function") continue;
+                        m.amplitude = xml::as_float(&value);
+                        xform.motion[name] = m;
+                    }
+                }
                 if (node_name == "finalxform") f->final_xform = xform;
                 else f->xforms.push_back(xform);
             } else if (node_name == "color") {
@@ -243,6 +256,47 @@ std::unique_ptr<flame> flame::load_flame_string(const std::string& xml_text, con
     }
     if (!f->do_common_init(vt)) return nullptr;
     return f;
+}
+
+// flam3's motion functions of the phase x = frequency * time (flam3.c, motion_funcs): sin: sin(2 pi x); triangle: a
+// triangle wave through 0 at x = 0 with peaks +-1 at x = 1/4, 3/4; hill: (1 - cos(2 pi x)) / 2.
+float flame::motion_function(const std::string& name, float x) {
+    const double pi = 3.14159265358979323846;
+    if (name == "sin") return (float)std::sin(2.0 * pi * (double)x);
+    if (name == "hill") return (float)((1.0 - std::cos(2.0 * pi * (double)x)) * 0.5);
+    if (name == "triangle") {
+        double fr = std::fmod((double)x, 1.0);
+        if (fr < 0.0) fr += 1.0;
+        if (fr <= 0.25) return (float)(4.0 * fr);
+        if (fr <= 0.75) return (float)(-4.0 * fr + 2.0);
+        return (float)(4.0 * fr - 4.0);
+    }
+    return 0.0f;
+}
+
+int flame::apply_motion(float time) {
+    if (motion_base_.empty()) {
+        motion_base_ = xforms;
+        if (final_xform) motion_base_.push_back(*final_xform);
+    }
+    int written = 0;
+    auto apply = [&](flame_xform& x, const flame_xform& base) {
+        for (const auto& [name, m] : base.motion) {
+            const float delta = m.amplitude * motion_function(m.function, m.freq * time);
+            auto set = [&](float& field, float from) { field = from + delta; written++; };
+            if (name == "weight") set(x.weight, base.weight);
+            else if (name == "color") set(x.color, base.color);
+            else if (name == "color_speed") set(x.color_speed, base.color_speed);
+            else if (name == "opacity") set(x.opacity, base.opacity);
+            else if (auto v = x.variations.find(name); v != x.variations.end()) set(v->second, base.variations.at(name));
+            else if (auto q = x.var_param.find(name); q != x.var_param.end()) set(q->second, base.var_param.at(name));
+            // anything else (a variation the xform does not use: the structure is fixed after load) is ignored
+        }
+    };
+    for (std::size_t i = 0; i < xforms.size() && i < motion_base_.size(); i++) apply(xforms[i], motion_base_[i]);
+    if (final_xform && motion_base_.size() == xforms.size() + 1) apply(*final_xform, motion_base_.back());
+    if (written) needs_update_ = true;
+    return written;
 }
 
 }  // namespace rfk

@@ -17,7 +17,19 @@ namespace rfk {
 class flame_compiler;
 struct flame_device;  // CUDA-side state (flame_device.cpp)
 
-// src/flame.hpp:21-37 (motion_info is parsed nowhere in the reference and is omitted)
+// src/flame.hpp:15-19. The reference declares it and keeps a map of it per xform (:36), but its parser for the <motion>
+// children of an xform is commented out (src/flame.cpp:199-210) and nothing ever reads the map. Here the children are parsed
+// as that block intends — one entry per animated attribute, frequency and function shared by the element — with the
+// attribute's value as the amplitude (the block stores it in `freq`, leaving `amplitude` unset: its bug), and
+// flame::apply_motion evaluates them the way flam3 does: value(t) = loaded value + amplitude * f(frequency * t),
+// f = sin: sin(2 pi x); triangle: 1 - 4 |frac(x + 1/4) - 1/2| ... (see apply_motion); hill: (1 - cos(2 pi x)) / 2.
+struct motion_info {
+    float freq = 0;
+    std::string function;
+    float amplitude = 0;
+};
+
+// src/flame.hpp:21-37
 struct flame_xform {
     using affine_t = std::array<float, 6>;
 
@@ -32,6 +44,8 @@ struct flame_xform {
 
     float rotation_frequency = 0;
     float opacity = 0;
+
+    std::map<std::string, motion_info> motion;  // src/flame.hpp:36; key = the animated attribute (a variation, a parameter, color, ...)
 };
 
 // Float-slot layout of one xform inside fp[] (src/flame.cpp:39-60).
@@ -146,6 +160,11 @@ struct flame {
     // (binding 4); nullptr generates them on the device from `seed`
     static void set_shuffle_buffers(const std::uint32_t* host_tables, std::size_t count, std::uint64_t seed);
     void reset_animation();                                    // src/flame.cpp:332-336
+    // Evaluates every <motion> entry at `time` (seconds) and writes base + amplitude * f(freq * time) into the animated fields;
+    // the base values are the ones load_flame read (kept aside on the first call). Marks the flame as needing warmup.
+    // Returns the number of fields written. No reference counterpart beyond the unused motion map (see motion_info).
+    int apply_motion(float time);
+    static float motion_function(const std::string& name, float x);  // sin / triangle / hill of flam3; unknown names: 0
 
     ~flame();
 
@@ -194,6 +213,7 @@ private:
     std::vector<char> cubin_;
     std::unique_ptr<flame_device> device_;
     bool needs_update_ = true;
+    std::vector<flame_xform> motion_base_;            // xforms (and the final xform last) as loaded, once apply_motion ran
     void rebuild_cuda_source();
 };
 

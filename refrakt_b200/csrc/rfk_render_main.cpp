@@ -19,6 +19,7 @@ static void usage() {
                  "  [--frames N --fps 60] (OUT.png takes a %%d / %%04d frame number) [--deterministic] [--math-mode 0|1|2]\n"
                  "  [--supersample 1] [--filter 1.0] (histogram at supersample x the image size, spatial filter radius in pixels;\n"
                  "   --quality is samples per histogram bin)\n"
+                 "  [--motion] evaluate the genome's <motion> elements at every frame's time (frame / fps)\n"
                  "  [--world N --rank R --comm-file PATH] one process per GPU (--device defaults to R): the N processes render every\n"
                  "   frame together (particle streams sharded, histograms reduce-scattered, rank 0 writes the PNG); rank 0 leaves the\n"
                  "   NCCL id in PATH, the others wait for it. [--frame-parallel]: instead, rank R renders the frames R, R+N, ... alone\n");
@@ -73,7 +74,7 @@ int main(int argc, char** argv) {
     size_t particles = 2048 * 1024, ts = 512;
     float tss_width = 1.2f / 60.0f, fps = 60.0f;
     unsigned long long seed = 0;
-    int device = -1, deterministic = 0, math_mode = -1, world = 1, rank = 0, frame_parallel = 0;
+    int device = -1, deterministic = 0, math_mode = -1, world = 1, rank = 0, frame_parallel = 0, motion = 0;
     std::string comm_file;
     unsigned supersample = 1;
     float filter_radius = 1.0f;
@@ -102,6 +103,7 @@ int main(int argc, char** argv) {
         else if (a == "--rank") rank = std::atoi(next());
         else if (a == "--comm-file") comm_file = next();
         else if (a == "--frame-parallel") frame_parallel = 1;
+        else if (a == "--motion") motion = 1;
         else if (a == "--deterministic") deterministic = 1;
         else if (a == "--math-mode") math_mode = std::atoi(next());
         else { usage(); return 2; }
@@ -144,6 +146,7 @@ int main(int argc, char** argv) {
     for (unsigned frame = 0; frame < frames; frame++) {
         if (frame_parallel && (int)(frame % (unsigned)world) != rank) continue;  // frames round-robin over the ranks, no exchange
         for (; rotated_to < frame; rotated_to++) rfk_flame_rotate_xforms(f, 18.0f / fps);  // DEGREES_PER_SECOND * dt, main.cpp:224; frame by frame, whoever renders it
+        if (motion) rfk_flame_apply_motion(f, (float)frame / fps);  // the genome's <motion> elements at this frame's time
         std::string name;
         frame_name(out, frame, name);
         auto t0 = std::chrono::steady_clock::now();

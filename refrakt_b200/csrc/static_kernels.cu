@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
                                                                      uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
     __shared__ int s_part[DE_THREADS];
     __shared__ float4 s_list[2 * DE_CAP];  // entry e: [2e] = (bx - 1, cy, 2/S, 1/S^2), [2e + 1] = colour * (2/pi)/r^2
-    extern __shared__ unsigned char s_dyn[];  // [nrows][pitch] radius bytes, then 2 * ncnt + 1 list offsets (unsigned short)
+    extern __shared__ __align__(16) unsigned char s_dyn[];  // [nrows][pitch] radius bytes, then 2 * ncnt + 1 list offsets (unsigned short)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx0 = blockIdx.x * DE_TILE_W, ty0 = p.y0 + blockIdx.y * DE_TILE_H;
@@ -302,13 +302,18 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
 
     if (DENSITY) {
         const int R = max(p.estimator_radius, p.estimator_min);
-        // radius-0 sources: out[cy][ox] takes bin (ox + 1, cy). Loaded first (the loads are in flight during A0); a bin that
-        // turns out to have a radius >= 1 is dropped again below.
+        // radius-0 sources: out[cy][ox] takes bin (ox + 1, cy). Loaded after the window scan (whose registers it would
+        // otherwise occupy; the scan has just pulled these sectors into L1 / L2).
+        auto load_radius0 = [&](const unsigned char* rad, int pitch_) {
 #pragma unroll
-        for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
-            const int cy = oy0 + k, bx = ox + 1;
-            if (cy >= p.src_y0 && cy < p.src_y1 && cy < p.y1 && bx < W) acc[k] = __ldg(bin_at(bx, cy));
-        }
+            for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
+                const int cy = oy0 + k, bx = ox + 1;
+                // a bin of the tile's own rows and columns with a radius >= 1 is not a radius-0 source (its footprint always reaches the tile)
+                const bool splat = rad && rad[(R + warp * DE_ROWS_PER_WARP + k) * pitch_ + R + lane] != 0;
+                if (cy >= p.src_y0 && cy < p.src_y1 && cy < p.y1 && bx < W && !splat) acc[k] = __ldg(bin_at(bx, cy));
+            }
+        };
+        if (R < 1) load_radius0(nullptr, 0);
         if (R >= 1) {
             const int win_x0 = tx0 + 1 - R, win_w = DE_TILE_W + 2 * R, nch = (win_w + 31) >> 5, pitch = nch << 5;
             const int win_y0 = ty0 - R, nrows = DE_TILE_H + 2 * R;
@@ -316,45 +321,64 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
             unsigned char* const s_rad = s_dyn;
             unsigned short* const s_off = reinterpret_cast<unsigned short*>(s_dyn + ((nrows * pitch + 15) & ~15));
 
-            // A0: radius byte of every window bin
+            // A0 + A1: radius byte of every window bin and the candidate counts of its (row, chunk) cell, per class. Lean on
+            // purpose — this loop runs for every tile of the image, candidates or not: column validity is one bit per chunk
+            // computed up front, a row is one 64-bit address, the shared-memory stores go through window addresses.
             const float t_any = p.thresholds[1];
+            const unsigned int rad_addr = (unsigned int)__cvta_generic_to_shared(s_rad), off_addr = (unsigned int)__cvta_generic_to_shared(s_off);
+            unsigned int colmask = 0;
+            for (int c = 0; c < nch; c++) {
+                const int col = (c << 5) + lane, bx = win_x0 + col;
+                if (col < win_w && bx >= 0 && bx < W) colmask |= 1u << c;
+            }
+            // radius bytes and counters start at zero; only cells with a candidate are written below
+            {
+                const unsigned int words16 = (unsigned int)((((nrows * pitch + 15) & ~15) + (2 * ncnt + 2) * 2 + 15) >> 4);
+                for (unsigned int i = tid; i < words16; i += DE_THREADS)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(rad_addr + (i << 4)), "r"(0u) : "memory");
+            }
+            __syncthreads();
+            bool any_candidate = false;
             for (int row = warp; row < nrows; row += DE_WARPS) {
                 const int cy = win_y0 + row;
-                const bool row_ok = cy >= p.src_y0 && cy < p.src_y1;
-                for (int c = 0; c < nch; c++) {
-                    const int col = (c << 5) + lane, bx = win_x0 + col;
+                if (cy < p.src_y0 || cy >= p.src_y1) continue;  // outside the image or the slab: empty
+                const float* row_w = &bin_at(win_x0 + lane, cy)->w;  // density of this lane's bin in chunk 0
+                for (int c = 0; c < nch; c++, row_w += 128) {
                     float d = 0.0f;
-                    if (row_ok && col < win_w && bx >= 0 && bx < W) d = __ldg(&bin_at(bx, cy)->w);
-                    int r = 0;
+                    if ((colmask >> c) & 1u) d = __ldg(row_w);
                     const bool cand = d != 0.0f && (p.use_pow || d <= t_any);
-                    if (__any_sync(0xffffffffu, cand)) {
-                        if (p.use_pow) {
-                            if (cand) r = estimator_radius_pow(d, p);
-                        } else {
-                            r = cand ? 1 : 0;
-                            for (int k = 2; k <= R; k++) {  // warp-uniform trip count: until no lane's density is under T[k]
-                                const bool under = cand && d <= p.thresholds[k];
-                                if (!__any_sync(0xffffffffu, under)) break;
-                                r += under ? 1 : 0;
-                            }
+                    if (!__any_sync(0xffffffffu, cand)) continue;  // the common case: dense or empty bins only
+                    int r = 0;
+                    if (p.use_pow) {
+                        if (cand) r = estimator_radius_pow(d, p);
+                    } else {
+                        r = cand ? 1 : 0;
+                        for (int k = 2; k <= R; k++) {  // warp-uniform trip count: until no lane's density is under T[k]
+                            const bool under = cand && d <= p.thresholds[k];
+                            if (!__any_sync(0xffffffffu, under)) break;
+                            r += under ? 1 : 0;
                         }
-                        if (r >= 1 && (bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1)) r = 0;
                     }
-                    s_rad[row * pitch + col] = (unsigned char)r;
+                    const int bx = win_x0 + (c << 5) + lane;
+                    if (r >= 1 && (bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1)) r = 0;
+                    const unsigned int small = __ballot_sync(0xffffffffu, r != 0 && r <= DE_SMALL_R), large = __ballot_sync(0xffffffffu, r > DE_SMALL_R);
+                    if ((small | large) == 0) continue;
+                    any_candidate = true;
+                    const unsigned int cell = (unsigned int)(row * nch + c);
+                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(rad_addr + (cell << 5) + lane), "r"(r) : "memory");
+                    if (lane == 0) {
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off_addr + 2u * cell), "h"((unsigned short)__popc(small)) : "memory");
+                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off_addr + 2u * (cell + (unsigned int)ncnt)), "h"((unsigned short)__popc(large)) : "memory");
+                    }
                 }
             }
-            __syncthreads();
-            // a bin of the tile's own rows and columns with a radius >= 1 is not a radius-0 source (its footprint always reaches the tile)
-#pragma unroll
-            for (int k = 0; k < DE_ROWS_PER_WARP; k++)
-                if (s_rad[(R + warp * DE_ROWS_PER_WARP + k) * pitch + R + lane] != 0) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            // A1: counts per (class, row, chunk)
-            for (int i = warp; i < ncnt; i += DE_WARPS) {
-                const int r = s_rad[(i << 5) + lane];
-                const unsigned int small = __ballot_sync(0xffffffffu, r != 0 && r <= DE_SMALL_R), large = __ballot_sync(0xffffffffu, r > DE_SMALL_R);
-                if (lane == 0) { s_off[i] = (unsigned short)__popc(small); s_off[ncnt + i] = (unsigned short)__popc(large); }
+            // no candidate anywhere in the window (the dense interior of an image, and its empty surroundings): the sums are the
+            // radius-0 copies already loaded
+            if (__syncthreads_or(any_candidate ? 1 : 0) == 0) {
+                load_radius0(nullptr, 0);
+                goto epilogue;
             }
-            __syncthreads();
+            load_radius0(s_rad, pitch);
             // A2: exclusive prefix sum over the 2 * ncnt counters (a window holds fewer than 65536 bins)
             const int n2 = 2 * ncnt;
             {
@@ -400,25 +424,36 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
                 const float oxf = (float)ox, oy0f = (float)oy0;
 
                 for (int base = 0; base < total; base += DE_CAP) {
-                    // A3: write this batch of the list
-                    for (int i = warp; i < n2; i += DE_WARPS) {
-                        const int first = s_off[i], last = s_off[i + 1];
-                        if (last == first || last <= base || first >= base + DE_CAP) continue;  // warp-uniform
-                        const bool large = i >= ncnt;
-                        const int cell = large ? i - ncnt : i;
-                        const int r = s_rad[(cell << 5) + lane];
-                        const bool mine = large ? r > DE_SMALL_R : (r != 0 && r <= DE_SMALL_R);
-                        const unsigned int vote = __ballot_sync(0xffffffffu, mine);
-                        if (mine) {
-                            const int e = first + __popc(vote & ((1u << lane) - 1u)) - base;
-                            if (e >= 0 && e < DE_CAP) {
-                                const int row = cell / nch, c = cell - row * nch;
-                                const int cy = win_y0 + row, bx = win_x0 + (c << 5) + lane;
-                                float4 col = __ldg(bin_at(bx, cy));
-                                const float S = (float)(2 * r + 1), norm = 0.63661977236f / (float)(r * r);  // density_vert.glsl:62
-                                col.x *= norm; col.y *= norm; col.z *= norm; col.w *= norm;
-                                s_list[2 * e] = make_float4((float)(bx - 1), (float)cy, 2.0f / S, 1.0f / (S * S));
-                                s_list[2 * e + 1] = col;
+                    // A3: write this batch of the list. A warp takes a contiguous share of the (class, row, chunk) cells; its lanes look
+                    // at 32 cells at a time and only the cells with entries in this batch are walked.
+                    {
+                        const int share = (n2 + DE_WARPS - 1) / DE_WARPS, c_lo = warp * share, c_hi = min(n2, c_lo + share);
+                        for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
+                            const int mine_cell = c0 + lane;
+                            int first = 0, last = 0;
+                            if (mine_cell < c_hi) { first = s_off[mine_cell]; last = s_off[mine_cell + 1]; }
+                            unsigned int todo = __ballot_sync(0xffffffffu, last > first && last > base && first < base + DE_CAP);
+                            while (todo) {
+                                const int src = __ffs(todo) - 1;
+                                todo &= todo - 1;
+                                const int i = c0 + src, cell_first = __shfl_sync(0xffffffffu, first, src);
+                                const bool large = i >= ncnt;
+                                const int cell = large ? i - ncnt : i;
+                                const int r = s_rad[(cell << 5) + lane];
+                                const bool mine = large ? r > DE_SMALL_R : (r != 0 && r <= DE_SMALL_R);
+                                const unsigned int vote = __ballot_sync(0xffffffffu, mine);
+                                if (mine) {
+                                    const int e = cell_first + __popc(vote & ((1u << lane) - 1u)) - base;
+                                    if (e >= 0 && e < DE_CAP) {
+                                        const int row = cell / nch, c = cell - row * nch;
+                                        const int cy = win_y0 + row, bx = win_x0 + (c << 5) + lane;
+                                        float4 col = __ldg(bin_at(bx, cy));
+                                        const float S = (float)(2 * r + 1), norm = 0.63661977236f / (float)(r * r);  // density_vert.glsl:62
+                                        col.x *= norm; col.y *= norm; col.z *= norm; col.w *= norm;
+                                        s_list[2 * e] = make_float4((float)(bx - 1), (float)cy, 2.0f / S, 1.0f / (S * S));
+                                        s_list[2 * e + 1] = col;
+                                    }
+                                }
                             }
                         }
                     }
@@ -432,8 +467,11 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
                         for (unsigned int at = list0 + 32u * (unsigned int)max(e_lo, 0), end = list0 + 32u * (unsigned int)max(e_hi, 0); at < end; at += 32u) {
                             float4 g;
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "r"(at));
-                            const float nm0 = fmaf(oy0f - g.y, g.z, g.w);                    // n(m) of the warp's first row
-                            const float nm3 = fmaf((float)(DE_ROWS_PER_WARP - 1), g.z, nm0);  // ... and of its last one
+                            // n(m) of every row from m = output row - source row itself (exact in binary32), not from the row's
+                            // offset inside the tile: a pixel's sum must not depend on where the tiling starts (row slabs)
+                            const float m0 = oy0f - g.y;
+                            const float nm0 = fmaf(m0, g.z, g.w);                                        // n(m) of the warp's first row
+                            const float nm3 = fmaf(m0 + (float)(DE_ROWS_PER_WARP - 1), g.z, g.w);        // ... and of its last one
                             if (nm0 > 1.0f || nm3 < -1.0f) continue;  // no row of this warp inside the footprint (warp-uniform)
                             float4 col;
                             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(col.x), "=f"(col.y), "=f"(col.z), "=f"(col.w) : "r"(at));
@@ -441,7 +479,7 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
                             const float one_minus_ci = fmaf(-ni, ni, 1.0f);
 #pragma unroll
                             for (int q = 0; q < DE_ROWS_PER_WARP; q++) {
-                                const float nm = fmaf((float)q, g.z, nm0);
+                                const float nm = q == 0 ? nm0 : (q == DE_ROWS_PER_WARP - 1 ? nm3 : fmaf(m0 + (float)q, g.z, g.w));
                                 fma4(acc[q], col, fmaxf(fmaf(-nm, nm, one_minus_ci), 0.0f));
                             }
                         }
@@ -458,6 +496,7 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
         }
     }
 
+epilogue:
     if (ox >= W) return;
 #pragma unroll
     for (int k = 0; k < DE_ROWS_PER_WARP; k++) {
@@ -513,7 +552,9 @@ static bool density_thresholds(float* host_out, int estimator_radius, int estima
     for (int k = 1; k <= R && k < 102; k++) host_out[k] = INFINITY;
     if (!(estimator_curve > 0.0f)) return false;
     auto radius_of = [&](float d) {
-        int r = (int)((float)estimator_radius / powf(d, estimator_curve));
+        // int(x) of the shader saturates on a GPU; in C++ the conversion of a quotient beyond INT_MAX (tiny densities) is undefined
+        const float q = (float)estimator_radius / powf(d, estimator_curve);
+        int r = q >= 2147483648.0f ? estimator_radius : (q > -2147483648.0f ? (int)q : estimator_min);
         r = r < estimator_radius ? r : estimator_radius;
         return r > estimator_min ? r : estimator_min;
     };
@@ -548,7 +589,7 @@ void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, dens
     // 3.9 KB at R = 11, 67 KB at the maximum R = 100
     const int R = p.estimator_radius > p.estimator_min ? p.estimator_radius : p.estimator_min;
     const size_t nrows = DE_TILE_H + 2 * R, nch = (DE_TILE_W + 2 * R + 31) >> 5;
-    const size_t dyn_bytes = do_density && R >= 1 ? ((nrows * (nch << 5) + 15) & ~size_t(15)) + (2 * nrows * nch + 2) * sizeof(unsigned short) : 0;
+    const size_t dyn_bytes = do_density && R >= 1 ? (((nrows * (nch << 5) + 15) & ~size_t(15)) + (2 * nrows * nch + 2) * sizeof(unsigned short) + 15) & ~size_t(15) : 0;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool configured[64] = {};

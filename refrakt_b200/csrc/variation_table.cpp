@@ -1,9 +1,9 @@
 #include "variation_table.hpp"
 
 #include <algorithm>
+#include <functional>
 #include <regex>
 #include <set>
-#include <stack>
 #include <stdexcept>
 
 #include "textutil.hpp"
@@ -17,23 +17,23 @@ inline bool digit_char(char c) { return c >= '0' && c <= '9'; }
 
 std::string slot_str(int slot) { return "fp[" + std::to_string(slot) + "]"; }  // variation_table.cpp:21
 
-using adj_desc_t = std::map<std::string, std::set<std::string>>;
+// name -> the names its definition mentions
+using dependency_map = std::map<std::string, std::set<std::string>>;
 
-// Depth-first post-order over the precalc dependency graph (variation_table.cpp:25-47).
-void order_recurse(const std::string& vertex, const adj_desc_t& adj, std::map<std::string, bool>& visited, std::stack<std::string>& stack) {
-    visited[vertex] = true;
-    for (const auto& con : adj.at(vertex))
-        if (!visited[con]) order_recurse(con, adj, visited, stack);
-    stack.push(vertex);
-}
-
-std::stack<std::string> get_ordering(const adj_desc_t& adj) {
-    std::stack<std::string> ordering;
-    std::map<std::string, bool> visited;
-    for (auto& [k, v] : adj) visited[k] = false;
-    for (auto& [v, a] : adj)
-        if (!visited[v]) order_recurse(v, adj, visited, ordering);
-    return ordering;
+// The order in which an xform's precalcs (`r`, `rsq`, `phi`, ... of variations.yaml `common`) are declared: every name after
+// the names its own definition uses, alphabetical otherwise — the order the reference's generated text has (it pushes a
+// depth-first walk on a stack and prepends while popping, variation_table.cpp:25-47 and :130-147; the emitted GLSL has to
+// be character-identical, so the order is part of the contract).
+std::vector<std::string> declaration_order(const dependency_map& uses) {
+    std::vector<std::string> order;
+    std::set<std::string> placed;
+    std::function<void(const std::string&)> place = [&](const std::string& name) {
+        if (!placed.insert(name).second) return;
+        for (const std::string& needed : uses.at(name)) place(needed);
+        order.push_back(name);
+    };
+    for (const auto& entry : uses) place(entry.first);
+    return order;
 }
 
 // $cCR -> affine slot C*2+R (variation_table.cpp:49-60); $pCR likewise for post (:62-73).
@@ -86,19 +86,17 @@ std::pair<bool, std::string> make_xform_text(const flame_xform& x, const xform_s
     auto macros = find_macros(xform_result);
     std::erase_if(macros, [&vt](const std::string& name) { return !vt.is_common(name); });
 
-    adj_desc_t macro_adj;
+    dependency_map uses;
     for (auto& m : macros) {
         auto deps = find_macros(vt.common(m));
         for (auto& d : deps)
-            if (vt.is_common(d) && !macro_adj.count(d)) macro_adj[d] = find_macros(vt.common(m));
-        macro_adj[m] = find_macros(vt.common(m));
+            if (vt.is_common(d) && !uses.count(d)) uses[d] = find_macros(vt.common(m));  // (sic: the dependent's set, as variation_table.cpp:133-137 stores it)
+        uses[m] = find_macros(vt.common(m));
     }
 
-    auto order = get_ordering(macro_adj);
-    while (order.size()) {
-        xform_result = "float " + order.top() + " = " + vt.common(order.top()) + ";\n" + xform_result;
-        order.pop();
-    }
+    std::string declarations;
+    for (const std::string& name : declaration_order(uses)) declarations += "float " + name + " = " + vt.common(name) + ";\n";
+    xform_result = declarations + xform_result;
 
     xform_result = affine + xform_result;
     resolve_coefs(xform_result, xmap.affine, 'c');
@@ -113,11 +111,11 @@ std::pair<bool, std::string> make_xform_text(const flame_xform& x, const xform_s
     return {false, xform_result};
 }
 
-void default_replace_macros(std::string& str) {  // variation_table.cpp:174-180
-    str = replace_macro(str, "x", "v.x");
-    str = replace_macro(str, "y", "v.y");
-    str = replace_macro(str, "v", "v.xy");
-    str = replace_macro(str, "result", "result");
+// The substitutions every snippet of variations.yaml gets when the table is loaded: the particle's coordinates by name
+// ($x, $y, $v) and $result, in this order (what variation_table.cpp:174-180 does before anything else sees the text).
+void expand_particle_macros(std::string& text) {
+    static const std::pair<const char*, const char*> table[] = {{"x", "v.x"}, {"y", "v.y"}, {"v", "v.xy"}, {"result", "result"}};
+    for (const auto& [name, value] : table) text = replace_macro(text, name, value);
 }
 
 std::string xform_select_text(const buffer_map_t& map, bool cuda) {  // shaders/templates/xform_select.tpl.glsl
@@ -396,9 +394,9 @@ void flame_compiler::load_text(const std::string& yaml_text) {
             const auto* src_n = def.find("src");
             const auto* res_n = def.find("result");
             std::string src = src_n ? src_n->as_string("") : "";
-            default_replace_macros(src);
+            expand_particle_macros(src);
             std::string result = res_n ? res_n->as_string("") : "";
-            default_replace_macros(result);
+            expand_particle_macros(result);
 
             auto& var = vars_[name];
             var = variation_definition{};
@@ -418,7 +416,7 @@ void flame_compiler::load_text(const std::string& yaml_text) {
     if (const auto* common = defs.find("common"); common && common->is_map()) {
         for (auto& [name, val] : common->entries) {
             std::string src = val.as_string();
-            default_replace_macros(src);
+            expand_particle_macros(src);
             common_[name] = src;
         }
     }

@@ -509,3 +509,41 @@ def test_staging_ring_of_four_chunk_slots_never_aliases(block):
                 assert slots[slot] == want, (block, counts, want)
             prev_reads = reads
             total += c
+
+
+MOTION_GENOME = GENOME_TEMPLATE % """<xform weight="0.5" color="0.2" color_speed="0.5" animate="1" linear="0.7" julian="0.4" julian_power="3" julian_dist="1.1" coefs="0.8 0.1 -0.2 0.7 0.1 0.05" opacity="1">
+  <motion motion_frequency="2" motion_function="sin" julian="0.25" julian_dist="-0.5"/>
+  <motion motion_frequency="0.5" motion_function="triangle" color="0.3" weight="0.2"/>
+ </xform>
+ <xform weight="0.5" color="0.8" color_speed="0.5" animate="0" linear="1" coefs="0.5 0 0 0.5 -0.3 0.2" opacity="1">
+  <motion motion_frequency="1" motion_function="hill" linear="-0.4" swirl="9"/>
+ </xform>
+ <finalxform color="0.5" color_speed="0" linear="1" coefs="1 0 0 1 0 0" opacity="1"><motion motion_frequency="3" motion_function="sin" opacity="-0.5"/></finalxform>"""
+
+
+def test_motion_elements_are_parsed_and_applied(rfk, compiler, vt, oracle_mod):
+    """<motion> children of an xform (motion_info, src/flame.hpp:15-19, :36; the parser src/flame.cpp:199-210 is commented
+    out in the reference): parsed as that block intends, evaluated like flam3; product and oracle agree bit for bit"""
+    f = rfk.Flame.load_flame_string(MOTION_GENOME, compiler)
+    assert f is not None, rfk.Flame.last_error()
+    of = oracle_mod.load_flame_string(MOTION_GENOME, vt)
+    base = oracle_mod.load_flame_string(MOTION_GENOME, vt)
+    assert f.motion(0) == {k: (float(a), b, float(c)) for k, (a, b, c) in of.xforms[0].motion.items()}
+    assert f.motion(0)["julian"] == (2.0, "sin", 0.25) and f.motion(0)["weight"] == (0.5, "triangle", np.float32(0.2))
+    assert f.motion(1).keys() == {"linear", "swirl"} and f.motion(-1) == {"opacity": (3.0, "sin", -0.5)}
+    # a genome without <motion> has none, and the loaded values do not depend on the elements
+    assert rfk.Flame.load_flame(GENOME, compiler).motion(0) == {}
+    assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(of).view(np.uint32))
+    for name in ("sin", "triangle", "hill", "nonsense"):
+        for x in (0.0, 0.1, 0.25, 0.5, 0.8, 1.0, -0.3, 7.625):
+            got = rfk.lib().rfk_motion_function(name.encode(), x)
+            assert np.float32(got) == oracle_mod.motion_function(name, x), (name, x)
+    assert rfk.lib().rfk_motion_function(b"triangle", 0.25) == 1.0 and rfk.lib().rfk_motion_function(b"hill", 0.5) == 1.0
+    for t in (0.0, 1.0 / 60, 0.125, 0.77, 3.5):
+        n = f.apply_motion(t)
+        assert n == oracle_mod.apply_motion(of, base, t) == 6  # swirl is not a variation of xform 1: ignored (structure is fixed)
+        assert f.needs_warmup()
+        assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(of).view(np.uint32)), t
+    assert abs(f.variations(0)["julian"] - (0.4 + 0.25 * np.sin(2 * np.pi * 2 * 3.5))) < 1e-6
+    f.apply_motion(0.0)  # back to the loaded values: the base is kept aside, motion does not accumulate
+    assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(base).view(np.uint32))

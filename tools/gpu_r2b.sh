@@ -1,0 +1,19 @@
+#!/bin/bash
+# round 2: new density kernel, sharded frame on one rank, configs tests; ncu of the density kernel
+tag=${1:-r02b}
+out=gpurun_out
+mkdir -p $out
+timeout 1200 python -m pytest tests/test_sharded_gpu.py tests/test_configs_gpu.py tests/test_render_gpu.py tests/test_fullsize_gpu.py -m gpu -q > $out/pytest_gpu_$tag.log 2>&1
+tail -25 $out/pytest_gpu_$tag.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $out/bench_$tag.json 2> $out/bench_$tag.err
+python - <<PY
+import json
+d=json.loads(open("$out/bench_$tag.json").read().strip().split("\n")[-1])
+print("value", d["value"], "e2e", d["e2e"]["value"], "ms", d["ms_per_step"], "post", d["roofline"].get("post"))
+PY
+tail -3 $out/bench_$tag.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:density_tonemap --launch-skip 3 --launch-count 1 -f -o $out/prof_density_$tag \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/prof_density_$tag.log 2>&1
+tail -2 $out/prof_density_$tag.log
+timeout 300 python tools/radius_stats.py > $out/radius_stats_$tag.jsonl 2>&1
+cat $out/radius_stats_$tag.jsonl | cut -c1-400

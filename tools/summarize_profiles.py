@@ -81,7 +81,10 @@ def report(src, dst, units=None, kernel=None):
                        "dram_bytes_per_launch": num("dram__bytes_read.sum") + num("dram__bytes_write.sum"),
                        "warp_instructions_per_launch": num("smsp__inst_executed.sum"), "units_per_launch": float(units) if units else None,
                        "warp_inst_per_unit": num("smsp__inst_executed.sum") / float(units) if units else None,
-                       "issue_active_pct": float(vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan"))},
+                       "issue_active_pct": float(vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", "nan")),
+                       # L2 reduction sectors of the launch and their share of the sustained peak: sectors / time / share = the peak rate
+                       "red_sectors_per_launch": num("lts__t_sectors_srcunit_tex_op_red.sum") if "lts__t_sectors_srcunit_tex_op_red.sum" in vals else None,
+                       "red_sectors_pct_of_peak": float(vals.get("lts__t_sectors_srcunit_tex_op_red.sum.pct_of_peak_sustained_elapsed", "nan").replace(",", ""))},
                       open(dst.rsplit(".", 1)[0] + ".json", "w"), indent=1)
         if "dram__bytes_read.sum" in vals:
             fh.write("\nDRAM traffic per launch: read %s + write %s (%s).\n" % (vals["dram__bytes_read.sum"], vals["dram__bytes_write.sum"], unit[hdr.index("dram__bytes_read.sum")]))
