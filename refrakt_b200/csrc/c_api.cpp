@@ -738,7 +738,7 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         // once per batch of calls enqueued back to back, sized to stop just short of the target so that the count of calls is
         // the one the call-by-call loop would make.
         auto more = [&]() { return (req->max_draw_calls == 0 || calls < req->max_draw_calls) && (req->target_binned == 0 || binned < req->target_binned); };
-        uint64_t per_call = 0;
+        uint64_t per_call = 0, first_call = 0;
         while (more()) {
             uint32_t batch = 1;
             if (per_call && req->target_binned) {
@@ -759,6 +759,11 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
             calls += batch;
             iterations += (uint64_t)batch * req->drawing_passes * sim_total_particles();
             if (req->target_binned && binned == 0 && calls >= 4) throw std::runtime_error("rfk_render_frame: nothing lands in the histogram");
+            // a genome whose particles overflow one after the other (the reference never resets them, flame.glsl:70) stops
+            // landing samples: the target would never be reached
+            if (first_call == 0) first_call = per_call;
+            if (req->target_binned && binned < req->target_binned && per_call * 1000 < first_call)
+                throw std::runtime_error("rfk_render_frame: the samples stopped landing before the target was reached (the genome's particles overflow and are never reset, as in the reference); render with max_draw_calls instead");
         }
         cuda_ok(cudaEventRecord(b.ev[2], s), "event");
 
@@ -966,7 +971,7 @@ int rfk_render_frame_sharded(rfk_flame* f, const rfk_sharded_request* sreq, uint
         }
         cuda_ok(cudaEventRecord(b.ev[2], s), "event");
 
-        uint64_t final_binned = 0;
+        uint64_t final_binned = 0, binned_before_topup = 0;
         for (int attempt = 0;; attempt++) {
             // ---- reduce-scatter over row slabs with halo; the all-reduce of the counters is also the barrier in front of it ----
             cuda_ok(cudaMemcpyAsync(b.counters, binned_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s), "copy binned counter");
@@ -1030,7 +1035,10 @@ int rfk_render_frame_sharded(rfk_flame* f, const rfk_sharded_request* sreq, uint
             cuda_ok(cudaStreamSynchronize(s), "rfk_render_frame_sharded");
             final_binned = counted;
             const bool capped = req->max_draw_calls && calls >= req->max_draw_calls;
-            if (!req->target_binned || final_binned >= req->target_binned || capped || attempt >= 8) break;
+            if (!req->target_binned || final_binned >= req->target_binned || capped) break;
+            if (attempt >= 8 || (attempt >= 1 && final_binned - binned_before_topup < (req->target_binned - final_binned) / 1000))
+                throw std::runtime_error("rfk_render_frame_sharded: the samples stopped landing before the target was reached (the genome's particles overflow and are never reset, as in the reference); render with max_draw_calls instead");
+            binned_before_topup = final_binned;
             // short of the target (the in-bounds fraction drifted by more than the margin): top up and redo the exchange
             per_pass = passes ? (double)final_binned / (double)passes : 0.0;
             const double left = (double)(req->target_binned - final_binned);

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -250,7 +251,7 @@ __device__ __forceinline__ float4 tonemap_pixel(float4 color, const density_para
 
 constexpr int DE_TILE_W = 32, DE_ROWS_PER_WARP = 4, DE_WARPS = 8, DE_TILE_H = DE_ROWS_PER_WARP * DE_WARPS;
 constexpr int DE_THREADS = DE_WARPS * 32;
-constexpr int DE_CAP = 256;        // candidate-list entries per batch (32 B each)
+constexpr int DE_CAP = 512;        // candidate-list entries per batch (32 B each: 16 KB)
 constexpr int DE_SMALL_R = 3;      // radius classes: 1..3 ("small": the warp's band of source rows is +-3) and above
 
 // Packed FP32 (sm_100 FFMA2: two lanes per issue slot; the kernel is issue bound): acc.xy += c.xy * w, acc.zw += c.zw * w
@@ -281,8 +282,8 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& c, float w) {
 //      small class, +-R for the large one — and accumulates; lanes are output columns.
 // Multi-GPU row slabs (rfk_comm_*): `bins` then holds the source rows [src_y0, src_y1) only and the launch produces the
 // output rows [y0, y1); rows outside [src_y0, src_y1) count as empty (they are outside the image, or not needed).
-template <bool DENSITY, bool TONEMAP>
-__global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
+template <bool DENSITY, bool TONEMAP, int MIN_BLOCKS = 5>
+__global__ void __launch_bounds__(DE_THREADS, MIN_BLOCKS) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
                                                                      uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
     __shared__ int s_part[DE_THREADS];
     __shared__ float4 s_list[2 * DE_CAP];  // entry e: [2e] = (bx - 1, cy, 2/S, 1/S^2), [2e + 1] = colour * (2/pi)/r^2
@@ -339,36 +340,53 @@ __global__ void __launch_bounds__(DE_THREADS, 5) density_tonemap_kernel(const fl
             }
             __syncthreads();
             bool any_candidate = false;
-            for (int row = warp; row < nrows; row += DE_WARPS) {
-                const int cy = win_y0 + row;
-                if (cy < p.src_y0 || cy >= p.src_y1) continue;  // outside the image or the slab: empty
-                const float* row_w = &bin_at(win_x0 + lane, cy)->w;  // density of this lane's bin in chunk 0
-                for (int c = 0; c < nch; c++, row_w += 128) {
-                    float d = 0.0f;
-                    if ((colmask >> c) & 1u) d = __ldg(row_w);
-                    const bool cand = d != 0.0f && (p.use_pow || d <= t_any);
-                    if (!__any_sync(0xffffffffu, cand)) continue;  // the common case: dense or empty bins only
-                    int r = 0;
-                    if (p.use_pow) {
-                        if (cand) r = estimator_radius_pow(d, p);
-                    } else {
-                        r = cand ? 1 : 0;
-                        for (int k = 2; k <= R; k++) {  // warp-uniform trip count: until no lane's density is under T[k]
-                            const bool under = cand && d <= p.thresholds[k];
-                            if (!__any_sync(0xffffffffu, under)) break;
-                            r += under ? 1 : 0;
-                        }
+            // two window rows per trip, all their loads issued before the first is looked at: the scan is a chain of
+            // load -> vote -> branch, and with one load in flight per warp its latency was a tenth of the kernel
+            constexpr int kMaxChunks = 8;  // (32 + 2 * 100 + 31) / 32
+            for (int row0 = warp; row0 < nrows; row0 += 2 * DE_WARPS) {
+                float dv[2][kMaxChunks];
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int row = row0 + rr * DE_WARPS, cy = win_y0 + row;
+                    const bool row_ok = row < nrows && cy >= p.src_y0 && cy < p.src_y1;  // else outside the image or the slab: empty
+                    const float* row_w = &bin_at(win_x0 + lane, row_ok ? cy : p.src_y1 - 1)->w;  // density of this lane's bin in chunk 0
+#pragma unroll
+                    for (int c = 0; c < kMaxChunks; c++) {
+                        dv[rr][c] = 0.0f;
+                        if (c < nch && row_ok && ((colmask >> c) & 1u)) dv[rr][c] = __ldg(row_w + c * 128);
                     }
-                    const int bx = win_x0 + (c << 5) + lane;
-                    if (r >= 1 && (bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1)) r = 0;
-                    const unsigned int small = __ballot_sync(0xffffffffu, r != 0 && r <= DE_SMALL_R), large = __ballot_sync(0xffffffffu, r > DE_SMALL_R);
-                    if ((small | large) == 0) continue;
-                    any_candidate = true;
-                    const unsigned int cell = (unsigned int)(row * nch + c);
-                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(rad_addr + (cell << 5) + lane), "r"(r) : "memory");
-                    if (lane == 0) {
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off_addr + 2u * cell), "h"((unsigned short)__popc(small)) : "memory");
-                        asm volatile("st.shared.u16 [%0], %1;" ::"r"(off_addr + 2u * (cell + (unsigned int)ncnt)), "h"((unsigned short)__popc(large)) : "memory");
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const int row = row0 + rr * DE_WARPS, cy = win_y0 + row;
+#pragma unroll
+                    for (int c = 0; c < kMaxChunks; c++) {
+                        if (c >= nch) break;
+                        const float d = dv[rr][c];
+                        const bool cand = d != 0.0f && (p.use_pow || d <= t_any);
+                        if (!__any_sync(0xffffffffu, cand)) continue;  // the common case: dense or empty bins only
+                        int r = 0;
+                        if (p.use_pow) {
+                            if (cand) r = estimator_radius_pow(d, p);
+                        } else {
+                            r = cand ? 1 : 0;
+                            for (int k = 2; k <= R; k++) {  // warp-uniform trip count: until no lane's density is under T[k]
+                                const bool under = cand && d <= p.thresholds[k];
+                                if (!__any_sync(0xffffffffu, under)) break;
+                                r += under ? 1 : 0;
+                            }
+                        }
+                        const int bx = win_x0 + (c << 5) + lane;
+                        if (r >= 1 && (bx - 1 + r < tx0 || bx - 1 - r > tx0 + DE_TILE_W - 1 || cy + r < ty0 || cy - r > ty0 + DE_TILE_H - 1)) r = 0;
+                        const unsigned int small = __ballot_sync(0xffffffffu, r != 0 && r <= DE_SMALL_R), large = __ballot_sync(0xffffffffu, r > DE_SMALL_R);
+                        if ((small | large) == 0) continue;
+                        any_candidate = true;
+                        const unsigned int cell = (unsigned int)(row * nch + c);
+                        asm volatile("st.shared.u8 [%0], %1;" ::"r"(rad_addr + (cell << 5) + lane), "r"(r) : "memory");
+                        if (lane == 0) {
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(off_addr + 2u * cell), "h"((unsigned short)__popc(small)) : "memory");
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(off_addr + 2u * (cell + (unsigned int)ncnt)), "h"((unsigned short)__popc(large)) : "memory");
+                        }
                     }
                 }
             }
@@ -598,7 +616,12 @@ void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, dens
         cudaFuncSetAttribute(density_tonemap_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         configured[dev] = true;
     }
-    if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
+    static const int min_blocks = [] { const char* e = std::getenv("RFK_DE_MIN_BLOCKS"); return e ? std::atoi(e) : 5; }();  // probe: 6 resident CTAs (40 registers)
+    if (do_density && do_tonemap && min_blocks == 6) {
+        static bool once = false;
+        if (!once) { cudaFuncSetAttribute(density_tonemap_kernel<true, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024); once = true; }
+        density_tonemap_kernel<true, true, 6><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
+    } else if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
     else if (do_density) density_tonemap_kernel<true, false><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
     else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
 }

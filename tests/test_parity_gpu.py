@@ -188,12 +188,20 @@ def _parity_over_genome(rfk, oracle_mod, compiler, vt, xml, n_per_xform, seed):
         err = _rel_err(got, want)
         bad = sane & ~(err <= 1e-5)
         if bad.any():
+            # An outlier is explained (a) by a discontinuity: the oracle at an input nudged by <= 2 ulp agrees within 1e-5; or
+            # (b) by its distance to a pole: the oracle ITSELF moves by `sens` when its input moves by one ulp, and the GPU's
+            # result is within eight such steps of it (tan in popcorn, the denominators of cross / cpow / edisc ...: one ulp of
+            # an intermediate is amplified there in both implementations alike).
             idx = np.nonzero(bad)[0]
             best = np.full(idx.size, np.inf)
+            sens = np.zeros(idx.size)
             for k in (-2, -1, 1, 2):
                 alt, _ = orc.single_step(_nudge(xyz[idx], k), idv[idx], states[idx])
                 best = np.minimum(best, _rel_err(got[idx], alt))
-            unexplained = (best > 1e-5).sum()
+                if abs(k) == 1:
+                    with np.errstate(invalid="ignore"):
+                        sens = np.fmax(sens, _rel_err(alt, want[idx]))
+            unexplained = ((best > 1e-5) & ~(err[idx] <= 8.0 * sens)).sum()
         else:
             unexplained = 0
         names = list((of.final_xform if xid == -1 else of.xforms[xid]).variations)
@@ -201,23 +209,27 @@ def _parity_over_genome(rfk, oracle_mod, compiler, vt, xml, n_per_xform, seed):
     return report
 
 
-# Variations with a pole inside the sampled domain (a denominator or a tangent that crosses zero: sin^2/cos in arch,
-# 1/(1 + e x/r) in conic, 1/(cosh - cos) in foci and coth, 1/cos in ngon, tan in popcorn/tangent/rays, 1/(x^2-y^2) in
-# cross, ...). Next to the pole a 1-ulp difference in an intermediate is amplified without bound, in the oracle as much
-# as on the GPU, so the 1e-5 statistic gets a looser outlier allowance there and the 2-ulp-nudge explanation is not
-# required (measured per-variation table: profiles/r01_variation_parity_mode1.json).
-POLE_VARIATIONS = {"arch", "conic", "foci", "ngon", "cross", "popcorn", "tangent", "rays", "secant2", "perspective", "curl", "mobius",
-                   "bipolar", "edisc", "coth", "cpow", "twintrian", "log", "super_shape", "flower", "spherical", "horseshoe", "spiral",
-                   "hyperbolic", "power", "julian", "juliascope"}
+# Variations with a pole inside the sampled domain (a denominator that crosses zero: sin^2/cos in arch, 1/(1 + e x/r) in
+# conic, 1/(cosh - cos) in foci and coth, 1/cos in ngon, 1/(x^2 - y^2)-like terms in twintrian). Next to the pole a 1-ulp
+# difference in an intermediate is amplified without bound, in the oracle as much as on the GPU. Only the variations the
+# measured per-variation table (profiles/r01_variation_parity_mode1.json, 50 000 vectors each) shows above the 1e-3 rule
+# are listed, each with its measured fraction of vectors outside 1e-5; an xform that mixes some of them may miss 1e-5 on
+# 1.5 x the sum of their fractions (plus the 1e-3 of the rule). Every other variation — julian, juliascope, spherical, log,
+# power ... included — is under the strict rule: >= 99.9 % of the vectors within 1e-5 outright and every outlier explained
+# by a <= 2-ulp nudge of the input.
+POLE_FRACTION = {"foci": 0.01856, "ngon": 0.01356, "arch": 0.00884, "coth": 0.00496, "conic": 0.00366, "twintrian": 0.00156}
+STRICT_OUTSIDE, STRICT_UNEXPLAINED = 1e-3, 2
 
 
 def _check_report(report):
     for xid, (names, frac_bad, unexplained) in report.items():
-        if POLE_VARIATIONS & set(names):
-            assert frac_bad <= 2.5e-2, (xid, names, frac_bad)
+        poles = [n for n in names if n in POLE_FRACTION]
+        if poles:
+            bound = STRICT_OUTSIDE + 1.5 * sum(POLE_FRACTION[n] for n in poles)
+            assert frac_bad <= bound, (xid, names, frac_bad, bound)
         else:
-            assert frac_bad <= 2e-3, (xid, names, frac_bad)
-            assert unexplained <= 2, (xid, names, unexplained)
+            assert frac_bad <= STRICT_OUTSIDE, (xid, names, frac_bad)
+            assert unexplained <= STRICT_UNEXPLAINED, (xid, names, unexplained)
 
 
 @pytest.mark.parametrize("chunk", range(6))

@@ -144,10 +144,20 @@ def test_histogram_statistical_parity(gpu_ready, rfk, flame, oracle_hist, mode):
     weights = flame.copy_flame_data_to_buffer()[[0, 13, 30, 43, 59, 76, 92, 110, 125, 141]]
     draws = total if mode.get("per_lane_xform") else total / 32  # independent selections
     assert np.abs(picks / picks.sum() - weights).max() <= max(1e-3, 4.5 * np.sqrt(0.25 / draws))
-    # colour: mean rgb per unit density agrees
+    # colour: mean rgb per unit density agrees, over the image and per region of an 8 x 8 grid (where the region holds mass)
     c_gpu = bins[..., :3].sum(axis=(0, 1)) / bins[..., 3].sum()
     c_ref = b1[..., :3].sum(axis=(0, 1)) / b1[..., 3].sum()
     assert np.abs(c_gpu - c_ref).max() <= 0.01
+
+    def regions(b, k=8):
+        g = b[: H // k * k, : W // k * k].astype(np.float64).reshape(k, H // k, k, W // k, 4).sum(axis=(1, 3))
+        return g[..., :3] / np.maximum(g[..., 3:4], 1e-9), g[..., 3]
+    rg, _ = regions(bins)
+    r1, m1 = regions(b1)
+    r2, _ = regions(b2)
+    heavy = m1 > 0.004 * m1.sum()
+    assert heavy.sum() >= 8
+    assert np.abs(rg - r1)[heavy].max() <= max(0.015, 2.0 * np.abs(r2 - r1)[heavy].max()), (np.abs(rg - r1)[heavy].max(), np.abs(r2 - r1)[heavy].max())
 
 
 def test_deterministic_mode_is_bit_identical(gpu_ready, rfk, flame):
