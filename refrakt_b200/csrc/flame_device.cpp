@@ -639,6 +639,17 @@ std::vector<float> flame::constant_table(const float* fp) const {
         t[2 * size + i] = 1.0f - fp[i];
         t[3 * size + i] = prod;
     }
+    // The rotated coefficients (a, b, c, d) of an xform that rotates are never read from this table — the kernels take them
+    // from the per-temporal-sample rows (RFK_AFF) — and they change with every frame of an animation (src/main.cpp:383-395):
+    // left out, so that the table, which is also the key of the value-specialised build, stays the same from frame to frame.
+    auto blank = [&](const xform_slots& m) {
+        if (fp[m.rotation_frequency] == 0.0f) return;  // does not rotate: its coefficients are constants like any other slot
+        for (int a = 0; a < 4; a++)
+            for (int q = 0; q < 4; q++)
+                if ((std::size_t)m.affine[a] < size) t[q * size + m.affine[a]] = 0.0f;
+    };
+    for (const auto& m : buffer_map_.xforms) blank(m);
+    if (buffer_map_.final_xform) blank(*buffer_map_.final_xform);
     return t;
 }
 

@@ -186,29 +186,32 @@ __global__ void spatial_downsample_kernel(const float4* __restrict__ in, float4*
 // (csrc/comm.cpp). Every thread keeps four 128-bit loads per source in flight.
 struct slab_sources { const float4* src[16]; int n; };
 __global__ void __launch_bounds__(256) slab_reduce_kernel(const __grid_constant__ slab_sources srcs, size_t offset, size_t count, float4* __restrict__ out) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < count; i += 4 * stride) {
+    // a CTA walks 16 KB pieces (4 x 256 float4, contiguous), grid-strided: every thread has four 128-bit loads per source in
+    // flight and a warp's requests stay inside one 2 KB run of a peer's memory (pieces 4.8 MB apart per thread ran the 2.12 GB
+    // histogram at 250 GB/s per peer)
+    constexpr size_t kPiece = 4 * 256;
+    for (size_t base = (size_t)blockIdx.x * kPiece; base < count; base += (size_t)gridDim.x * kPiece) {
         float4 a[4];
+        bool ok[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) a[u] = srcs.src[0][offset + i + u * stride];
+        for (int u = 0; u < 4; u++) {
+            const size_t i = base + u * 256 + threadIdx.x;
+            ok[u] = i < count;
+            a[u] = ok[u] ? srcs.src[0][offset + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int k = 1; k < srcs.n; k++) {
             float4 b[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) b[u] = srcs.src[k][offset + i + u * stride];
+            for (int u = 0; u < 4; u++) {
+                const size_t i = base + u * 256 + threadIdx.x;
+                b[u] = ok[u] ? srcs.src[k][offset + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int u = 0; u < 4; u++) { a[u].x += b[u].x; a[u].y += b[u].y; a[u].z += b[u].z; a[u].w += b[u].w; }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) out[i + u * stride] = a[u];
-    }
-    for (; i < count; i += stride) {
-        float4 a = srcs.src[0][offset + i];
-        for (int k = 1; k < srcs.n; k++) {
-            const float4 b = srcs.src[k][offset + i];
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        }
-        out[i] = a;
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) out[base + u * 256 + threadIdx.x] = a[u];
     }
 }
 

@@ -56,6 +56,7 @@ def main():
     bins.zero_out()
     flame.warmup(16, TSS)
     flame.draw_to_bins(bins.ptr, W * H, W, 32)
+    out["private_bins_2"] = bins.download(np.float32, (H, W, 4))  # the RNG streams moved on: other samples than the first draw
     r.comm_reduce_histogram(bins.ptr, W * H, 0)  # onto rank 0
     r.comm_barrier()
     if rank == 0:

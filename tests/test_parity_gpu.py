@@ -201,7 +201,12 @@ def _parity_over_genome(rfk, oracle_mod, compiler, vt, xml, n_per_xform, seed):
                 if abs(k) == 1:
                     with np.errstate(invalid="ignore"):
                         sens = np.fmax(sens, _rel_err(alt, want[idx]))
-            unexplained = ((best > 1e-5) & ~(err[idx] <= 8.0 * sens)).sum()
+            open_cases = (best > 1e-5) & ~(err[idx] <= 8.0 * sens)
+            unexplained = int(open_cases.sum())
+            for j in np.nonzero(open_cases)[0][:4]:  # shown when the assertion on the count fails
+                i = idx[j]
+                print("unexplained outlier: xform %d input %r got %r want %r err %.3g nudge-best %.3g sensitivity %.3g" % (
+                    xid, xyz[i].tolist(), got[i, :2].tolist(), want[i, :2].tolist(), err[i], best[j], sens[j]))
         else:
             unexplained = 0
         names = list((of.final_xform if xid == -1 else of.xforms[xid]).variations)

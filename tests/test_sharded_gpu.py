@@ -147,7 +147,8 @@ def test_two_ranks_over_nccl_and_peer_memory(gpu_ready, rfk, compiler, tmp_path)
     want = r0["private_bins"] + r1["private_bins"]  # binary32 addition, as NCCL's sum of two ranks
     assert np.array_equal(r0["allreduced_bins"].view(np.uint32), want.view(np.uint32))
     assert np.array_equal(r1["allreduced_bins"].view(np.uint32), want.view(np.uint32))
-    assert np.array_equal(r0["reduced_bins"].view(np.uint32), want.view(np.uint32))
+    want2 = r0["private_bins_2"] + r1["private_bins_2"]
+    assert np.array_equal(r0["reduced_bins"].view(np.uint32), want2.view(np.uint32)) and not np.array_equal(want2, want)
     assert abs(float(want[..., 3].sum()) - float(r0["binned"][0] + r1["binned"][0])) <= 0.5
 
     # (b) the two data paths drew the same passes from the same seeds: same image up to reduction order
