@@ -107,7 +107,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.25)
 
     def __enter__(self):
         self.thread.start()
@@ -460,6 +460,7 @@ def main():
             t1.record()
             barrier()
             e2e_ms = t0.elapsed_time(t1)
+        launches_timed_region = r.kernel_launch_count() - launches0
         ms = sum(dev_ms)  # device time of the frame without the read-back, this rank
         iters = e2e_iters = its / world  # summed over the ranks below
         binned, calls = st.binned_global / world, st.draw_calls
@@ -493,7 +494,7 @@ def main():
             barrier()
             line_extra["weak"] = {"ms_per_step": w0.elapsed_time(w1) / args.steps, "iterations": wi}
 
-    launches = r.kernel_launch_count() - launches0
+    launches = launches_timed_region if (world > 1 and cfg["mode"] != "animation") else (launches_value if (world == 1 and cfg["mode"] != "animation") else r.kernel_launch_count() - launches0)
     torch.cuda.synchronize()
     draw_ms = [a.elapsed_time(b) for a, b, _ in draw_events]
     draw_binned = [b for _, _, b in draw_events]

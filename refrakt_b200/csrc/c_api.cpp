@@ -655,6 +655,7 @@ struct frame_buffers {
     float4* bins = nullptr; float4* image = nullptr; uchar4* rgba8 = nullptr; float4* small = nullptr;
     size_t bins_n = 0, image_n = 0, rgba8_n = 0, small_n = 0;
     cudaEvent_t ev[5] = {};
+    unsigned long long* host_counter = nullptr;  // pinned: the binned counter of a frame read back together with its image
     void release() {
         cudaFree(bins); cudaFree(image); cudaFree(rgba8); cudaFree(small);
         bins = image = small = nullptr; rgba8 = nullptr;
@@ -739,14 +740,20 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         // the one the call-by-call loop would make.
         auto more = [&]() { return (req->max_draw_calls == 0 || calls < req->max_draw_calls) && (req->target_binned == 0 || binned < req->target_binned); };
         uint64_t per_call = 0, first_call = 0;
-        while (more()) {
+        const bool count_at_the_end = !req->target_binned && !want_hot_map;  // a fixed number of calls: no read-back in between
+        if (count_at_the_end) {
+            for (uint32_t k = 0; k < req->max_draw_calls; k++) fl->draw_to_bins_async(reinterpret_cast<float*>(b.bins), n, W, (int)req->drawing_passes);
+            calls = req->max_draw_calls;
+            iterations = (uint64_t)calls * req->drawing_passes * sim_total_particles();
+        }
+        while (!count_at_the_end && more()) {
             uint32_t batch = 1;
             if (per_call && req->target_binned) {
                 const uint64_t left = req->target_binned - binned;
                 const uint64_t safe = (uint64_t)((double)left / ((double)per_call * 1.01));  // calls that cannot reach the target yet
                 batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(safe, 1), 1u << 20);
-            } else if (per_call) {
-                batch = 1u << 20;
+            } else if (!req->target_binned) {
+                batch = 1u << 20;  // a fixed number of calls: all of them at once, the counter is read once at the end
             }
             if (req->max_draw_calls) batch = std::min(batch, req->max_draw_calls - calls);
             for (uint32_t k = 0; k < batch; k++) {
@@ -786,8 +793,13 @@ int rfk_render_frame(rfk_flame* f, const rfk_frame_request* req, uint8_t* rgba8_
         cuda_ok(cudaEventRecord(b.ev[3], s), "event");
         if (rgba8_out) cuda_ok(cudaMemcpyAsync(rgba8_out, b.rgba8, on * sizeof(uchar4), cudaMemcpyDeviceToHost, s), "read back rgba8");
         if (image_out) cuda_ok(cudaMemcpyAsync(image_out, final_image, on * sizeof(float4), cudaMemcpyDeviceToHost, s), "read back image");
+        if (count_at_the_end) {
+            if (!b.host_counter) cuda_ok(cudaMallocHost(&b.host_counter, sizeof(unsigned long long)), "cudaMallocHost(counter)");
+            cuda_ok(cudaMemcpyAsync(b.host_counter, flame_binned_counter_dev(*fl), sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "read binned counter");
+        }
         cuda_ok(cudaEventRecord(b.ev[4], s), "event");
         cuda_ok(cudaStreamSynchronize(s), "rfk_render_frame");
+        if (count_at_the_end) binned = *b.host_counter;
         if (stats) {
             stats->iterations = iterations; stats->binned = binned; stats->draw_calls = calls;
             cudaEventElapsedTime(&stats->ms_warmup, b.ev[0], b.ev[1]);

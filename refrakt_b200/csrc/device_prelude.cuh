@@ -17,6 +17,8 @@ __shared__ float fp[RFK_TOTAL_PARAMS + 1];
 // issued before the switch; the generated text names them RFK_AFF(xform, component) (compile_flame_cuda).
 __shared__ float4 rfk_aff[RFK_NUM_XFORMS + 1];
 #define RFK_AFF(xform, component) rfk_A.component
+// keeps the optimiser from reasoning across two tests of the same register (the weight-ordered if-chain of dispatch_a)
+#define RFK_OPAQUE(v) asm volatile("" : "+r"(v))
 
 // Packed FP32 (sm_100: FFMA2 / FMUL2 / FADD2, `fma.rn.f32x2`): one instruction does the x and the y lane of a vec2
 // operation — the same FP32 rate as two scalar instructions but ONE issue slot, and the kernels are issue bound

@@ -242,6 +242,8 @@ struct flame_device {
     variant variants[2][2];            // [0][0] stays empty: that is `module` above
     std::vector<float> previous_constants;  // rfk_cfp values of the warmup before the last one (specialize = 2)
     bool use_baked = false;                 // decided by warmup(): the baked variants match the uploaded parameters
+    float* pinned = nullptr;                // pinned staging of warmup()'s uploads: fp[1024], constant table [4096], palette [1024]
+    cudaEvent_t pinned_done = nullptr;
     float4* particles = nullptr;
     float4* swap = nullptr;  // reference pass mode: swap_buffer_
     float* fp = nullptr;
@@ -279,6 +281,8 @@ struct flame_device {
                 if (v.module) driver().ModuleUnload(v.module);
         cudaFree(particles); cudaFree(swap); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
         cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
+        if (pinned_done) { cudaEventSynchronize(pinned_done); cudaEventDestroy(pinned_done); }
+        cudaFreeHost(pinned);
     }
 };
 
@@ -689,12 +693,32 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
     flame_device& d = *device_;
     needs_update_ = false;
 
+    // The parameter block, the constant table and the palette go up through ONE pinned staging buffer owned by the flame:
+    // truly asynchronous copies (a copy from pageable memory makes the driver synchronise the stream first), and warmup
+    // returns without waiting — a frame of an animation is then one host synchronisation, the one that hands over the image.
+    // The event keeps the next warmup from overwriting the staging buffer while these copies are still in flight.
     auto buf = copy_flame_data_to_buffer();
-    cuda_check(cudaMemcpyAsync(d.fp, buf.data(), PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
-    upload_constant_params(*this, buf.data());
-    cuda_check(cudaMemcpyAsync(d.palette, palette.data(), 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
+    d.cfp_staging = constant_table(buf.data());
+    const std::size_t table_floats = std::min(d.cfp_floats, d.cfp_staging.size());
+    if (!d.pinned) {
+        cuda_check(cudaMallocHost(&d.pinned, (PARAM_BUFFER + 4 * PARAM_BUFFER + 256 * 4) * sizeof(float)), "cudaMallocHost(parameter staging)");
+        cuda_check(cudaEventCreateWithFlags(&d.pinned_done, cudaEventDisableTiming), "cudaEventCreate");
+    } else {
+        cuda_check(cudaEventSynchronize(d.pinned_done), "wait for the previous parameter upload");
+    }
+    float* stage_fp = d.pinned, *stage_table = d.pinned + PARAM_BUFFER, *stage_palette = d.pinned + 5 * PARAM_BUFFER;
+    std::memcpy(stage_fp, buf.data(), PARAM_BUFFER * sizeof(float));
+    std::memcpy(stage_table, d.cfp_staging.data(), table_floats * sizeof(float));
+    std::memcpy(stage_palette, palette.data(), 256 * sizeof(float4));
+    cuda_check(cudaMemcpyAsync(d.fp, stage_fp, PARAM_BUFFER * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload fp");
+    if (d.cfp && table_floats) {
+        cuda_check(cudaMemcpyAsync(d.cfp, stage_table, table_floats * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
+        if (float* staged_cfp = d.variants[1][0].cfp)
+            cuda_check(cudaMemcpyAsync(staged_cfp, stage_table, table_floats * sizeof(float), cudaMemcpyHostToDevice, g_sim.stream), "upload constant parameters");
+    }
+    cuda_check(cudaMemcpyAsync(d.palette, stage_palette, 256 * sizeof(float4), cudaMemcpyHostToDevice, g_sim.stream), "upload palette");
+    cuda_check(cudaEventRecord(d.pinned_done, g_sim.stream), "event");
     cuda_check(cudaMemsetAsync(d.counters, 0, 64 * sizeof(unsigned long long), g_sim.stream), "clear counters");
-    // the host arrays above are stack / member storage: finish the copies before returning control
     kernels::animate(d.fp, d.fp_inflated, buffer_map_.size, (int)g_sim.temporal_samples, tss_width, d.anim, d.anim_count, g_sim.stream);
     count_launch(1);
 
@@ -714,8 +738,7 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
     p.num_iter = (int)num_passes;
     void* args[] = {&p};
     launch(warm_fn, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
-    cuda_check(cudaStreamSynchronize(g_sim.stream), "warmup");
-    d.binned_reported = 0;
+    d.binned_reported = 0;  // stream-ordered: the draw calls, read-backs and rfk_synchronize that follow wait for it
     d.warmed = true;
 }
 

@@ -1,6 +1,7 @@
 #include "variation_table.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <regex>
 #include <set>
@@ -155,6 +156,7 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
         ? std::string("vec4 dispatch(vec3 v, int xform){\n").append("switch(xform){\n")
         : std::string("template <bool first_run>\n__device__ __forceinline__ vec4 dispatch_a(vec3 v, int xform, rfk_rng& rs, const float4 rfk_A){\n").append("switch(xform){\n");
     int rf_counter = 0;
+    std::vector<std::pair<int, std::string>> cuda_cases;  // (xform index, body)
 
     for (int i = -1; i < (int)f.xforms.size(); i++) {
         if (i == -1 && !f.final_xform) continue;
@@ -182,8 +184,38 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
             dispatch_invoke = pack_affines(dispatch_invoke);
         }
 
+        if (d == dialect::cuda) cuda_cases.emplace_back(i, dispatch_invoke);
         if (i + 1 == (int)f.xforms.size()) disp_func += "default: {\n" + dispatch_invoke + "\n}}\n";
         else disp_func += "case " + std::to_string(i) + ": {\n" + dispatch_invoke + "\n}\n";
+    }
+    // CUDA dialect: when a few xforms take most of the picks, `dispatch` is a chain of `if (xform == k)` in order of
+    // decreasing weight instead of the switch (whose compare tree + jump table costs ~9 instructions per pick whatever the
+    // weights): E[tests] = sum over the order of position x weight; two instructions per test. The pick is warp-uniform, so
+    // either form is one taken path per warp. Same cases, same text inside them.
+    if (d == dialect::cuda && !f.xforms.empty()) {
+        std::vector<std::pair<double, int>> order;
+        double total = 0.0;
+        for (std::size_t i = 0; i < f.xforms.size(); i++) total += std::max(0.0f, f.xforms[i].weight);
+        for (std::size_t i = 0; i < f.xforms.size(); i++) order.emplace_back(total > 0.0 ? std::max(0.0f, f.xforms[i].weight) / total : 0.0, (int)i);
+        std::stable_sort(order.begin(), order.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+        double expected_tests = 0.0;
+        for (std::size_t k = 0; k < order.size(); k++) expected_tests += order[k].first * (double)std::min(k + 1, order.size() - 1);
+        const char* force = std::getenv("RFK_DISPATCH");  // "switch" / "chain": A/B runs
+        const bool chain_wanted = force ? std::string(force) == "chain" : (f.xforms.size() >= 3 && expected_tests <= 3.5);
+        if (chain_wanted) {
+            std::string chain = "template <bool first_run>\n__device__ __forceinline__ vec4 dispatch_a(vec3 v, int xform, rfk_rng& rs, const float4 rfk_A){\n";
+            auto body_of = [&](int index) -> const std::string& {
+                for (const auto& c : cuda_cases) if (c.first == index) return c.second;
+                throw std::logic_error("dispatch: missing case");
+            };
+            // RFK_OPAQUE between the tests: the optimiser would otherwise fold the chain back into a switch
+            chain += "int rfk_pick = xform;\n";
+            if (f.final_xform) chain += "if (rfk_pick == -1) {\n" + body_of(-1) + "\n}\n";
+            for (std::size_t k = 0; k + 1 < order.size(); k++)
+                chain += "RFK_OPAQUE(rfk_pick);\nif (rfk_pick == " + std::to_string(order[k].second) + ") {\n" + body_of(order[k].second) + "\n}\n";
+            chain += "{\n" + body_of(order.back().second) + "\n}\n";
+            disp_func = chain;
+        }
     }
     if (f.xforms.empty()) disp_func += "default: { return vec4(v.xy, v.z, 0.0" + std::string(d == dialect::cuda ? "f" : "") + "); }}\n";
 

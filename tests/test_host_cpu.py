@@ -547,3 +547,28 @@ def test_motion_elements_are_parsed_and_applied(rfk, compiler, vt, oracle_mod):
     assert abs(f.variations(0)["julian"] - (0.4 + 0.25 * np.sin(2 * np.pi * 2 * 3.5))) < 1e-6
     f.apply_motion(0.0)  # back to the loaded values: the base is kept aside, motion does not accumulate
     assert np.array_equal(f.copy_flame_data_to_buffer().view(np.uint32), oracle_mod.copy_flame_data_to_buffer(base).view(np.uint32))
+
+
+def test_value_specialised_build_compiles_without_a_gpu(rfk, compiler, flame, overlay_compiler, overlay_vt):
+    """kernel option `specialize`: the translation unit with every rfk_cfp[k] replaced by its value (NVRTC, sm_100a)"""
+    src = flame.variant_source(False, True)
+    body = src.split("#define randf() rfk_randf(rs)")[1].split("#undef randf")[0]
+    assert "rfk_cfp[" not in re.sub(r"//[^\n]*", "", body) and "RFK_DIVC(" not in body  # no constant-bank reads left
+    assert "#define RFK_BAKED 1" in src and "#define RFK_HOT_ONLY 1" in src
+    assert "float sum = (0x1.44310ep-6f);" in body  # the first cumulative weight of get_xform_id(), exact
+    assert "RFK_AFF(-1" not in body and "RFK_AFF(4, x)" in body  # the final xform does not rotate: literals; xform 4 does
+    assert "if (rfk_pick == 4) {" in body and body.index("rfk_pick == 4") < body.index("rfk_pick == 5")  # heaviest xform first
+    assert len(flame.variant_cubin(False, True)) > 10000
+    assert "#define RFK_STAGED_BINS 1" in flame.variant_source(True, False)
+    # a genome whose reciprocals include infinities (1 / 0 for unused slots), and a uniform-weight genome (switch, not a chain)
+    stress = rfk.Flame.load_flame_string(stress_genome(overlay_vt), overlay_compiler)
+    assert stress is not None, rfk.Flame.last_error()
+    s2 = stress.variant_source(False, True)
+    assert "switch(xform)" in s2 and len(stress.variant_cubin(False, True)) > 10000
+    # the table behind the build: the rotating affine coefficients are not part of it (one build per animation)
+    f = rfk.Flame.load_flame(GENOME, compiler)
+    before = f.variant_source(False, True)
+    f.rotate_xforms(0.3)
+    assert f.variant_source(False, True) == before
+    f.set_variation(0, "julia", 0.5)
+    assert f.variant_source(False, True) != before
