@@ -336,25 +336,33 @@ def main():
             post_events.append((p0, p1))
 
     def resident_step(record, reduce_to_root=False):
-        """one frame on this GPU with everything on the device; returns (iterations, binned, draw calls)"""
+        """one frame on this GPU with everything on the device; returns (iterations, binned, draw calls). The binned counter
+        (the blocking 8-byte read-back of flame.cpp:329) is read after the first call and then once per batch of calls sized
+        to stop just short of the target — the same calls the call-by-call loop makes, as rfk_render_frame does"""
         flame.warmup(WARMUP_PASSES, TSS_WIDTH)
         bins.zero_()
-        binned, calls = 0, 0
+        binned, calls, per_call = 0, 0, 0
         while (target and binned < target) or (calls_fixed and calls < calls_fixed):
-            if record:
-                e0, e1 = event(), event()
-                e0.record()
-            flame.draw_to_bins_async(bins.data_ptr(), nbins, W, DRAW_PASSES)
-            if record:
-                e1.record()
-            if target or record:
-                total = flame.binned_total()  # blocking 8-byte read-back, as flame.cpp:329
+            if calls_fixed:
+                batch = calls_fixed - calls
+            elif per_call:
+                batch = max(1, int((target - binned) / (per_call * 1.01)))
+            else:
+                batch = 1
+            launched = []
+            for _ in range(batch):
                 if record:
-                    draw_events.append((e0, e1, total - binned))
-                binned = total
-            calls += 1
-        if not target:
-            binned = flame.binned_total()
+                    e0, e1 = event(), event()
+                    e0.record()
+                flame.draw_to_bins_async(bins.data_ptr(), nbins, W, DRAW_PASSES)
+                if record:
+                    e1.record()
+                    launched.append((e0, e1))
+            total = flame.binned_total()
+            per_call = (total - binned) / batch
+            draw_events.extend((a, b, per_call) for a, b in launched)
+            binned = total
+            calls += batch
         if reduce_to_root and world > 1:
             r.comm_reduce_histogram(bins.data_ptr(), nbins, 0)  # the one exchange step of the weak-scaling run (ncclReduce)
         if rank == 0 or not reduce_to_root:

@@ -104,11 +104,9 @@ __device__ __forceinline__ float2 rfk_sample_point(unsigned int i, int bits, flo
 // (t >= 0x34800000). Non-finite positions therefore never bin, where the reference leaves ivec2(floor(NaN)) undefined.
 __device__ __forceinline__ unsigned int rfk_trunc_biased(float p) { return __float_as_uint(__fadd_rz(p, 8388608.0f)) - 0x4B000000u; }
 __device__ __forceinline__ bool rfk_bin_test(float x, float y, float w, const float* ss, int W, int H, unsigned int& cx, unsigned int& cy) {
-    // nested fma, as flame.glsl:79-80 — scalar on purpose: the six coefficients are kernel parameters, which an FFMA reads
-    // straight from the constant bank, where the packed form needs them loaded into register pairs on every iteration
-    const float px = ::fmaf(ss[0], x, ::fmaf(ss[2], y, ss[4])), py = ::fmaf(ss[1], x, ::fmaf(ss[3], y, ss[5]));
-    cx = rfk_trunc_biased(px);
-    cy = rfk_trunc_biased(py);
+    const vec2 pos = rfk_affine(ss[0], ss[1], ss[2], ss[3], ss[4], ss[5], x, y);  // nested fma, as flame.glsl:79-80
+    cx = rfk_trunc_biased(pos.x);
+    cy = rfk_trunc_biased(pos.y);
     return cx < (unsigned int)W && cy < (unsigned int)H && w > 0.0f;
 }
 __device__ __forceinline__ int rfk_bin_of(unsigned int cx, unsigned int cy, int W, int H) { return (int)(((unsigned int)(H - 1) - cy) * (unsigned int)W + cx); }
@@ -235,11 +233,9 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
     const unsigned int ex_both = ex_cur + (unsigned int)__cvta_generic_to_shared(&ex[1][0]);
     auto deal_store = [&]() {
         deal_key = deal_key * 1664525u + 1013904223u;  // CTA-uniform
-        // 64 + 32 bits: (x, y) is already a register pair (the packed arithmetic leaves it as one); a 128-bit store would need
-        // three moves to line x, y and the colour up in a quad first
-        const unsigned int at = ex_cur + rfk_deal_offset(tid16, deal_key);
-        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(at), "f"(x), "f"(y) : "memory");
-        asm volatile("st.shared.f32 [%0+8], %1;" ::"r"(at), "f"(c) : "memory");
+        // one 128-bit store. (Tried: 64 + 32 bits, which saves the three moves that line x, y and the colour up in a quad — two
+        // shared-memory stores per iteration cost more in the MIO queue than the moves cost in issue slots: 1.29 -> 1.38 ms.)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" ::"r"(ex_cur + rfk_deal_offset(tid16, deal_key)), "f"(x), "f"(y), "f"(c) : "memory");
     };
     auto deal_load = [&]() {  // after the barrier that follows deal_store
         float unused;

@@ -1,13 +1,17 @@
 #!/bin/bash
-# multi-GPU pass (gpurun --gpus N): two-rank test, sharded bench lines, the C++ CLI with one process per GPU
+# Multi-GPU pass: the two-rank test, the sharded bench line of every configuration (peer-memory path, and the NCCL path for
+# the 4K frame), the C++ CLI with one process per GPU.
+#   gpurun --gpus 8 --timeout 900 -- 'bash tools/gpu_round_multi.sh 8 r02'
 n=${1:-2}
 tag=${2:-r02f}
 out=gpurun_out
 mkdir -p $out
 nvidia-smi -L > $out/smi_$tag.txt
 nvidia-smi topo -m >> $out/smi_$tag.txt 2>&1
-timeout 900 python -m pytest tests/test_sharded_gpu.py -m gpu -q -k "two_ranks" > $out/pytest_mgpu_$tag.log 2>&1
-tail -30 $out/pytest_mgpu_$tag.log | cut -c1-400
+if [ -z "$SKIP_TESTS" ]; then
+  timeout 900 python -m pytest tests/test_sharded_gpu.py -m gpu -q -k "two_ranks" > $out/pytest_mgpu_$tag.log 2>&1
+  tail -3 $out/pytest_mgpu_$tag.log | cut -c1-400
+fi
 run_bench() {  # config, extra args
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --config $1 $2 \
     > $out/bench_cfg$1_${n}gpu_$tag.json 2> $out/bench_cfg$1_${n}gpu_$tag.err
@@ -20,13 +24,13 @@ except Exception as e:
     print("cfg $1 failed", e); print(open("$out/bench_cfg$1_${n}gpu_$tag.err").read()[-2500:])
 PY
 }
-run_bench 2 "--steps 3 --warmup 3"
+run_bench 2 "--steps 5 --warmup 3"
 NCCL_DEBUG=INFO RFK_COMM_P2P=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --config 2 --steps 3 --warmup 2 --no-weak \
     > $out/bench_cfg2_${n}gpu_nccl_$tag.json 2> $out/bench_cfg2_${n}gpu_nccl_$tag.err
 tail -c 700 $out/bench_cfg2_${n}gpu_nccl_$tag.json; grep -i "NVLS\|P2P/\|via" $out/bench_cfg2_${n}gpu_nccl_$tag.err | head -5
-run_bench 3 "--steps 2 --warmup 1"
-run_bench 4 "--steps 1 --warmup 1"
-run_bench 5 "--steps 2 --warmup 2"
+run_bench 3 "--steps 2 --warmup 3"
+run_bench 4 "--steps 2 --warmup 1"
+run_bench 5 "--steps 3 --warmup 3"
 run_bench 1 "--steps 5 --warmup 3"
 # the C++ CLI, one process per GPU
 rm -f /tmp/rfk_id
