@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RFK_ABI_VERSION 3
+#define RFK_ABI_VERSION 4
 
 enum {
     RFK_OK = 0,
@@ -137,11 +137,15 @@ const char* rfk_flame_cuda_source(const rfk_flame* f); /* the translation unit h
 /* sm_100a cubin of the generated kernels; *size receives the byte count, buf may be NULL to query. Needs no GPU. */
 int rfk_flame_get_cubin(rfk_flame* f, void* buf, size_t buf_len, size_t* size);
 /* The further builds of the same kernels the library makes on first use: `staged` = rfk_draw with the region queues of
- * kernel option staged_bins compiled in; `specialised` = the current parameter values compiled in (kernel option
- * specialize). Translation unit and sm_100a cubin; need no GPU. */
+ * kernel option staged_bins compiled in; `specialised` = 1: the current parameter values compiled in (kernel option
+ * specialize), 2: the same with two particles per thread (kernel option pair_particles). Translation unit and sm_100a
+ * cubin; need no GPU. */
 const char* rfk_flame_variant_source(rfk_flame* f, int staged, int specialised);
 int rfk_flame_get_variant_cubin(rfk_flame* f, int staged, int specialised, void* buf, size_t buf_len, size_t* size);
 int rfk_flame_uses_specialised(const rfk_flame* f); /* 1 when the last warmup chose the value-specialised kernels */
+/* kernel option pair_particles: 0 = generic kernels in use, 1 = the specialised kernels hold two particles per thread, 2 = one;
+ * probe_ms_out (optional) receives the measurement that decided it: ms of the probe launch with one / two particles per thread */
+int rfk_flame_pair_particles_state(const rfk_flame* f, float probe_ms_out[2]);
 
 /* Options of the generated kernels (no reference counterpart). Changing them rebuilds the module. */
 typedef struct rfk_kernel_options {
@@ -172,6 +176,13 @@ typedef struct rfk_kernel_options {
                                kernels only; 1 = warmup rebuilds the specialised kernels (NVRTC, 1-2 s) whenever a value changed;
                                2 = automatic (default): built the second time warmup runs with unchanged values. Same results to
                                rounding: constants fold at compile time with IEEE arithmetic */
+    int32_t pair_particles; /* the value-specialised kernels hold two particles per thread (CTAs of block_width / 2 threads over the
+                               same pool of block_width particles): one xform pick, one walk to its code, one re-deal key and one
+                               barrier per two iterations. 1 (default) = measured: when the specialised kernels are built both forms
+                               run a short warm-up on scratch copies of the particle and RNG buffers and the faster one is kept
+                               (the shipped genome gains 4 %, a genome of twelve heavy xforms would lose 10 %); 2 = always,
+                               0 = never. Ignored (one particle per thread) together with per_lane_xform, warp_aggregate,
+                               deterministic, count_xforms, l2_hints, staged_bins, deal_period > 1 or an explicit min_blocks */
 } rfk_kernel_options;
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* out);
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* in);

@@ -39,7 +39,7 @@ class XformInfo(C.Structure):
 
 class KernelOptions(C.Structure):
     _fields_ = [("math_mode", C.c_int32), ("fmad", C.c_int32), ("per_lane_xform", C.c_int32), ("warp_aggregate", C.c_int32),
-                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32), ("l2_hints", C.c_int32), ("staged_bins", C.c_int32), ("specialize", C.c_int32)]
+                ("deterministic", C.c_int32), ("count_xforms", C.c_int32), ("min_blocks", C.c_int32), ("block_width", C.c_int32), ("deal_period", C.c_int32), ("l2_hints", C.c_int32), ("staged_bins", C.c_int32), ("specialize", C.c_int32), ("pair_particles", C.c_int32)]
 
 
 class HotMapInfo(C.Structure):
@@ -132,6 +132,7 @@ SIGNATURES = {
     "rfk_flame_variant_source": (_cp, [_vp, _i, _i]),
     "rfk_flame_get_variant_cubin": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_sz)]),
     "rfk_flame_uses_specialised": (_i, [_vp]),
+    "rfk_flame_pair_particles_state": (_i, [_vp, _fpp]),
     "rfk_flame_get_options": (_i, [_vp, C.POINTER(KernelOptions)]),
     "rfk_flame_set_options": (_i, [_vp, C.POINTER(KernelOptions)]),
     "rfk_flame_kernel_info": (_i, [_vp, _cp, _ipp, _ipp, _ipp]),
@@ -420,6 +421,12 @@ class Flame:
         buf = C.create_string_buffer(size.value)
         _check(lib().rfk_flame_get_variant_cubin(self.handle, int(staged), int(specialised), buf, size.value, C.byref(size)), "get_variant_cubin")
         return buf.raw
+
+    def pair_particles_state(self):
+        """(state, probe ms): 0 generic kernels, 1 two particles per thread, 2 one; the two probe times that decided it"""
+        ms = np.zeros(2, dtype=np.float32)
+        st = _check(lib().rfk_flame_pair_particles_state(self.handle, _ptr(ms)), "pair_particles_state")
+        return int(st), ms.tolist()
 
     def uses_specialised(self) -> bool: return bool(_check(lib().rfk_flame_uses_specialised(self.handle), "uses_specialised"))
 

@@ -352,7 +352,7 @@ int rfk_flame_get_variant_cubin(rfk_flame* f, int staged, int specialised, void*
             auto fp = fl->copy_flame_data_to_buffer();
             table = fl->constant_table(fp.data());
         }
-        const auto image = fl->variant_cubin(staged != 0, specialised ? &table : nullptr);
+        const auto image = fl->variant_cubin(staged != 0, specialised ? &table : nullptr, specialised == 2);
         *size = image.size();
         if (buf) {
             if (buf_len < image.size()) throw std::invalid_argument("cubin buffer too small");
@@ -370,17 +370,21 @@ const char* rfk_flame_variant_source(rfk_flame* f, int staged, int specialised) 
             auto fp = fl->copy_flame_data_to_buffer();
             table = fl->constant_table(fp.data());
         }
-        t_scratch = fl->variant_source(staged != 0, specialised ? &table : nullptr);
+        t_scratch = fl->variant_source(staged != 0, specialised ? &table : nullptr, specialised == 2);
         return t_scratch.c_str();
     } catch (const std::exception& e) { fail(RFK_E_INVALID, e.what()); return nullptr; }
 }
 
+int rfk_flame_pair_particles_state(const rfk_flame* f, float probe_ms_out[2]) {
+    if (!f) return fail(RFK_E_INVALID, "null flame");
+    return flame_pairs_state(*F(f), probe_ms_out);
+}
 int rfk_flame_uses_specialised(const rfk_flame* f) { return f ? (flame_uses_baked(*F(f)) ? 1 : 0) : fail(RFK_E_INVALID, "null flame"); }
 
 int rfk_flame_get_options(const rfk_flame* f, rfk_kernel_options* o) {
     if (!f || !o) return fail(RFK_E_INVALID, "null argument");
     const auto& k = F(f)->options();
-    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks, k.block_width, k.deal_period, k.l2_hints, k.staged_bins, k.specialize};
+    *o = rfk_kernel_options{k.math_mode, k.fmad, k.per_lane_xform, k.warp_aggregate, k.deterministic, k.count_xforms, k.min_blocks, k.block_width, k.deal_period, k.l2_hints, k.staged_bins, k.specialize, k.pair_particles};
     return RFK_OK;
 }
 int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
@@ -394,6 +398,8 @@ int rfk_flame_set_options(rfk_flame* f, const rfk_kernel_options* i) {
     k.l2_hints = i->l2_hints ? 1 : 0;
     k.staged_bins = i->staged_bins;
     k.specialize = i->specialize;
+    k.pair_particles = i->pair_particles;
+    if (k.pair_particles < 0 || k.pair_particles > 2) return fail(RFK_E_INVALID, "pair_particles must be 0 (never), 1 (measured) or 2 (always)");
     if (k.specialize < 0 || k.specialize > 2) return fail(RFK_E_INVALID, "specialize must be 0 (off), 1 (always) or 2 (automatic)");
     if (k.staged_bins != 0 && k.staged_bins != -1 && (k.staged_bins < 8 || k.staged_bins > 24))
         return fail(RFK_E_INVALID, "staged_bins must be -1 (automatic), 0 (off) or the log2 of the bins per region, 8 to 24");

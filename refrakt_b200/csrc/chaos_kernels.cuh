@@ -442,15 +442,158 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two particles per thread (kernel option pair_particles, the default where no other option asks for the single-particle
+// body): a CTA of RFK_BLOCK / 2 threads owns the same pool of RFK_BLOCK particles; thread t holds the particles of slots
+// t and t + RFK_BLOCK / 2 and their two JSF32 states. One pick, one walk to the xform's case, one fetch of its rotated
+// coefficients, one re-deal key, one barrier and one trip of the loop serve two iterations of the chaos game (~20 of the
+// 135 instructions of an iteration are such per-trip overhead), and the two independent dependency chains overlap each
+// other's MUFU / shared-memory latency. 40 registers per thread at 1536 resident threads: 3072 particles per SM (2048 with
+// one particle per thread). Shipped genome: 135.0 -> 116.7 warp instructions per iteration.
+// The warp's pick now covers 64 particles per iteration instead of 32 (the reference: 256).
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef RFK_PAIRS
+#define RFK_PAIRS 0  // set by the host for the value-specialised build (flame::variant_source); the generic module keeps one particle per thread
+#endif
+#ifndef RFK_PAIRS_MIN_BLOCKS
+#define RFK_PAIRS_MIN_BLOCKS (3072 / RFK_BLOCK)  // 40 registers at 1536 resident threads: the best of 64 / 48 / 40 / 36 / 32 registers measured
+#endif
+#define RFK_PAIRS_AVAILABLE (RFK_PAIRS && !RFK_PER_LANE_XFORM && !RFK_WARP_AGGREGATE && !RFK_DETERMINISTIC && !RFK_COUNT_XFORMS && !RFK_L2_HINTS && !RFK_STAGED_BINS && RFK_DEAL_PERIOD == 1)
+#if RFK_PAIRS_AVAILABLE
+template <bool first_run>
+__device__ __forceinline__ void dispatch2(vec3 v0, vec3 v1, int xform, rfk_rng& rs0, rfk_rng& rs1, vec4& o0, vec4& o1) {
+    dispatch2_a<first_run>(v0, v1, xform, rs0, rs1, rfk_aff[xform + 1], o0, o1);
+}
+
+template <bool DRAW>
+__device__ __forceinline__ void rfk_iterate_pairs(const rfk_iter_params& p) {
+    constexpr unsigned int HALF = RFK_BLOCK / 2;  // threads per CTA
+    __shared__ float4 pal[256];
+    __shared__ float4 ex[2][RFK_BLOCK];
+
+    const unsigned int tid = threadIdx.x;
+    const unsigned int lane = tid & 31u;
+    const unsigned int blocks_per_ts = (unsigned int)p.ppt / RFK_BLOCK;
+    const unsigned int ts = blockIdx.x / blocks_per_ts;
+    const size_t slot0 = (size_t)blockIdx.x * RFK_BLOCK + tid, slot1 = slot0 + HALF;
+
+    rfk_stage_params(p.fp_inflated + (size_t)ts * RFK_TOTAL_PARAMS);
+    if (DRAW) for (int i = tid; i < 256; i += HALF) pal[i] = p.palette[i];
+
+    rfk_rng rs0 = p.rng[slot0], rs1 = p.rng[slot1];
+    float x0, y0, c0, x1, y1, c1;
+    __syncthreads();
+
+    unsigned int binned = 0;
+    int pick_pool = 0, pick_count = 0;
+    const unsigned int tid16 = tid << 4;
+    unsigned int deal_key = rfk_hash32(p.deal_seed ^ (blockIdx.x * 0x9E3779B9u));
+    unsigned int ex_cur = (unsigned int)__cvta_generic_to_shared(&ex[0][0]);
+    const unsigned int ex_both = ex_cur + (unsigned int)__cvta_generic_to_shared(&ex[1][0]);
+    // the bijection j = (slot * a + b) mod RFK_BLOCK of rfk_deal_offset for both slots of the thread: slot1 = slot0 + HALF and
+    // a is odd, so j1 = j0 + HALF mod RFK_BLOCK — the second offset is the first with its top bit flipped
+    auto deal = [&]() {
+        deal_key = deal_key * 1664525u + 1013904223u;  // CTA-uniform
+        const unsigned int off0 = rfk_deal_offset(tid16, deal_key), at0 = ex_cur + off0, at1 = ex_cur + (off0 ^ (HALF << 4));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" ::"r"(at0), "f"(x0), "f"(y0), "f"(c0) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %3};" ::"r"(at1), "f"(x1), "f"(y1), "f"(c1) : "memory");
+        __syncthreads();
+        float unused;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(y0), "=f"(c0), "=f"(unused) : "r"(ex_cur + tid16) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x1), "=f"(y1), "=f"(c1), "=f"(unused) : "r"(ex_cur + tid16 + (HALF << 4)) : "memory");
+        ex_cur = ex_both - ex_cur;
+    };
+
+    if (!DRAW && p.first_run) {
+        // flame.glsl:58-65 for both slots; the draws of a slot come from that slot's generator, in the single-particle order
+        const unsigned int gid0 = (blockIdx.x % blocks_per_ts) * RFK_BLOCK + tid, gid1 = gid0 + HALF;
+        pick_pool = get_xform_id(rfk_randf(rs0));
+        const int xid = __shfl_sync(0xffffffffu, pick_pool, 0);
+        pick_count = 1;
+        const float2 s0 = rfk_sample_point(gid0, p.hammersley_bits, p.hammersley_inv_max), s1 = rfk_sample_point(gid1, p.hammersley_bits, p.hammersley_inv_max);
+        const float r00 = rfk_randf(rs0), r01 = rfk_randf(rs0), r10 = rfk_randf(rs1), r11 = rfk_randf(rs1);
+        const vec2 sc0 = sincos(sqrtf(r01)), sc1 = sincos(sqrtf(r11));
+        const float m0 = r00 * .1f * PI * 2.0f, m1 = r10 * .1f * PI * 2.0f;
+        vec4 q0, q1;
+        dispatch2<true>(vec3(s0.x + m0 * sc0.x, s0.y + m0 * sc0.y, 0.0f), vec3(s1.x + m1 * sc1.x, s1.y + m1 * sc1.y, 0.0f), xid, rs0, rs1, q0, q1);
+        x0 = q0.x; y0 = q0.y; c0 = q0.z; x1 = q1.x; y1 = q1.y; c1 = q1.z;
+        deal();
+    } else {
+        const float4 a = p.particles[slot0], b = p.particles[slot1];
+        x0 = a.x; y0 = a.y; c0 = a.z; x1 = b.x; y1 = b.y; c1 = b.z;
+    }
+
+    auto bin = [&](float fx, float fy, float fc, float fw) {  // flame.glsl:78-86
+        unsigned int cx, cy;
+        if (rfk_bin_test(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, cx, cy)) {
+            const int idx = rfk_bin_of(cx, cy, p.bin_w, p.bin_h);
+            const unsigned int prow = (unsigned int)__cvta_generic_to_shared(&pal[rfk_palette_index(fc)]);
+            float4 col;
+            asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(col.x), "=f"(col.y) : "r"(prow));
+            asm volatile("ld.volatile.shared.f32 %0, [%1+8];" : "=f"(col.z) : "r"(prow));
+            col.w = fw;
+            rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, col.w);
+            binned++;
+        }
+    };
+
+    for (int it = 0; it < p.num_iter;) {
+        if ((pick_count & 31) == 0) pick_pool = get_xform_id(rfk_randf(rs0));
+        int pick_lane = pick_count & 31;
+        const int block_len = ::min(32 - pick_lane, p.num_iter - it);
+        pick_count += block_len;
+        const int pick_lane_end = pick_lane + block_len;
+        for (; pick_lane != pick_lane_end; ++pick_lane) {
+            const int xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane);
+            __builtin_assume(xid >= 0 && xid < (RFK_NUM_XFORMS > 0 ? RFK_NUM_XFORMS : 1));
+            vec4 r0, r1;
+            dispatch2<false>(vec3(x0, y0, c0), vec3(x1, y1, c1), xid, rs0, rs1, r0, r1);
+            x0 = r0.x; y0 = r0.y; c0 = r0.z; x1 = r1.x; y1 = r1.y; c1 = r1.z;  // flame.glsl:72
+            if (DRAW) {
+#if RFK_HAS_FINAL
+                vec4 q0, q1;  // src/flame.cpp:23: result = dispatch(result.xyz, -1) * vec4(1, 1, 1, result.w)
+                dispatch2<false>(vec3(r0.x, r0.y, r0.z), vec3(r1.x, r1.y, r1.z), -1, rs0, rs1, q0, q1);
+                bin(q0.x, q0.y, q0.z, q0.w * r0.w);
+                bin(q1.x, q1.y, q1.z, q1.w * r1.w);
+#else
+                bin(r0.x, r0.y, r0.z, r0.w);
+                bin(r1.x, r1.y, r1.z, r1.w);
+#endif
+            }
+            deal();
+        }
+        it += block_len;
+    }
+
+    p.particles[slot0] = make_float4(x0, y0, c0, 0.0f);
+    p.particles[slot1] = make_float4(x1, y1, c1, 0.0f);
+    p.rng[slot0] = rs0;  // flame.glsl:89
+    p.rng[slot1] = rs1;
+    if (DRAW) {
+        for (int o = 16; o > 0; o >>= 1) binned += __shfl_xor_sync(0xffffffffu, binned, o);
+        if (lane == 0 && binned) atomicAdd(p.counters, (unsigned long long)binned);
+    }
+}
+#endif  // RFK_PAIRS_AVAILABLE
+
 #ifndef RFK_DRAW_ONLY
 #define RFK_DRAW_ONLY 0  // 1: the module holds rfk_draw alone (the staged kernels of the automatic mode, built on first use)
 #endif
+#if RFK_PAIRS_AVAILABLE
+// same names, half the threads per CTA (the host reads RFK_PAIRS back from the options it compiled with)
+extern "C" __global__ void __launch_bounds__(RFK_BLOCK / 2, RFK_PAIRS_MIN_BLOCKS) rfk_draw(const __grid_constant__ rfk_iter_params p) { rfk_iterate_pairs<true>(p); }
+#else
 extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_draw(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<true>(p); }
+#endif
 #ifndef RFK_HOT_ONLY
 #define RFK_HOT_ONLY 0   // 1: rfk_warm, rfk_draw and rfk_single_step only (the value-specialised build of kernel option `specialize`)
 #endif
 #if !RFK_DRAW_ONLY
+#if RFK_PAIRS_AVAILABLE
+extern "C" __global__ void __launch_bounds__(RFK_BLOCK / 2, RFK_PAIRS_MIN_BLOCKS) rfk_warm(const __grid_constant__ rfk_iter_params p) { rfk_iterate_pairs<false>(p); }
+#else
 extern "C" __global__ void RFK_LAUNCH_BOUNDS rfk_warm(const __grid_constant__ rfk_iter_params p) { rfk_iterate_body<false>(p); }
+#endif
 
 #if !RFK_HOT_ONLY
 // The reference's own dispatch structure, restated for the GPU: shaders/flame.glsl:41-90 as ONE iteration per launch

@@ -89,6 +89,12 @@ struct kernel_options {
                                   // 0 = off (one module per genome structure, as the reference's one shader per genome);
                                   // 1 = rebuilt by warmup() whenever a value changed; 2 = automatic (default): built the second time
                                   // warmup() runs with unchanged values (stills, animations, benchmarks), generic kernels meanwhile
+    int pair_particles = 1;       // value-specialised build only: two particles per thread (CTAs of block_width / 2 threads over the same
+                                  // pool of block_width particles): one pick, one walk to the xform's case, one re-deal key and one
+                                  // barrier per two iterations. 1 (default) = measured: when the specialised kernels are built, both
+                                  // forms run a short warm-up on scratch copies of the particle and RNG buffers and the faster one is
+                                  // kept (genomes with many heavy xforms lose with pairs); 2 = always; 0 = never. Not with
+                                  // per_lane_xform, warp_aggregate, deterministic, count_xforms, l2_hints, staged_bins, deal_period > 1
     bool operator==(const kernel_options&) const = default;
 };
 
@@ -186,8 +192,9 @@ struct flame {
     const kernel_options& options() const { return options_; }
     // the translation unit of a kernel variant: `staged` compiles rfk_draw's region queues in (rfk_draw alone); `baked`, when
     // not null, holds the 4 * size constants of rfk_cfp[] and replaces every rfk_cfp[k] of the text with its value
-    std::string variant_source(bool staged, const std::vector<float>* baked) const;
-    std::vector<char> variant_cubin(bool staged, const std::vector<float>* baked) const;
+    std::string variant_source(bool staged, const std::vector<float>* baked, bool pairs = false) const;
+    bool pairs_allowed() const;  // the options admit the two-particles-per-thread build of the value-specialised kernels
+    std::vector<char> variant_cubin(bool staged, const std::vector<float>* baked, bool pairs = false) const;
     std::vector<float> constant_table(const float* fp) const;  // the contents of rfk_cfp[] for the parameter buffer `fp`
     // Rebuilds the CUDA module with new options (the structure of the genome is fixed
     // after load, only values change without a rebuild: src/flame.hpp, main.cpp:335-369).

@@ -240,6 +240,9 @@ struct flame_device {
         std::vector<float> values;     // baked variants: the constants compiled in
     };
     variant variants[2][2];            // [0][0] stays empty: that is `module` above
+    variant paired;                    // baked, unstaged, two particles per thread (kernel option pair_particles)
+    int pairs_state = 0;               // 0 = not measured for the current baked values, 1 = the paired build is the faster one, 2 = it is not
+    float pairs_ms[2] = {0.0f, 0.0f};  // the measurement: ms of the probe launch, one particle per thread / two
     std::vector<float> previous_constants;  // rfk_cfp values of the warmup before the last one (specialize = 2)
     bool use_baked = false;                 // decided by warmup(): the baked variants match the uploaded parameters
     float* pinned = nullptr;                // pinned staging of warmup()'s uploads: fp[1024], constant table [4096], palette [1024]
@@ -279,6 +282,7 @@ struct flame_device {
         for (auto& row : variants)
             for (auto& v : row)
                 if (v.module) driver().ModuleUnload(v.module);
+        if (paired.module) driver().ModuleUnload(paired.module);
         cudaFree(particles); cudaFree(swap); cudaFree(fp); cudaFree(fp_inflated); cudaFree(palette);
         cudaFree(counters); cudaFree(fixed_bins); cudaFree(anim);
         if (pinned_done) { cudaEventSynchronize(pinned_done); cudaEventDestroy(pinned_done); }
@@ -420,7 +424,8 @@ static std::string float_literal(float v) {
 //          cumulative weights of get_xform_id() fold into compare immediates, and selects on parameters
 //          (`rfk_cfp[n] == 0 ? ... : ...`) fold away. The four rotated affine coefficients of every xform differ between
 //          temporal samples and stay in shared memory (fp[k]).
-std::string flame::variant_source(bool staged, const std::vector<float>* baked) const {
+std::string flame::variant_source(bool staged, const std::vector<float>* baked, bool pairs) const {
+    if (pairs && (!baked || staged)) throw std::invalid_argument("variant_source: the paired kernels exist in the value-specialised, unstaged build only");
     std::string source = cuda_source_;
     if (staged) {
         const std::string off = "#define RFK_STAGED_BINS 0\n", on = "#define RFK_STAGED_BINS 1\n#define RFK_DRAW_ONLY 1\n";
@@ -433,7 +438,8 @@ std::string flame::variant_source(bool staged, const std::vector<float>* baked) 
         const std::size_t decl = source.find(decl_head);
         if (decl == std::string::npos) throw std::runtime_error("variant_source: no rfk_cfp declaration in the generated text");
         const std::size_t decl_end = source.find('\n', decl);
-        source.replace(decl, decl_end - decl, "#define RFK_BAKED 1  // rfk_cfp[] compiled in as literals\n#define RFK_HOT_ONLY 1");
+        source.replace(decl, decl_end - decl, std::string("#define RFK_BAKED 1  // rfk_cfp[] compiled in as literals\n#define RFK_HOT_ONLY 1") +
+                                                  (pairs ? "\n#define RFK_PAIRS 1" + std::string(std::getenv("RFK_PAIRS_MIN_BLOCKS") ? std::string("\n#define RFK_PAIRS_MIN_BLOCKS ") + std::getenv("RFK_PAIRS_MIN_BLOCKS") : "") : ""));
         // `e RFK_DIVC(n, r)` (device_prelude.cuh) names its slots inside a macro: expanded here, so the pass below sees them
         for (std::size_t at = source.find("RFK_DIVC("); at != std::string::npos; at = source.find("RFK_DIVC(", at + 1)) {
             std::size_t j = at + 9, comma = source.find(',', j), close = source.find(')', j);
@@ -483,8 +489,14 @@ std::string flame::variant_source(bool staged, const std::vector<float>* baked) 
     return source;
 }
 
-std::vector<char> flame::variant_cubin(bool staged, const std::vector<float>* baked) const {
-    return compile_with_bounds(variant_source(staged, baked), options_);
+bool flame::pairs_allowed() const {
+    const kernel_options& o = options_;
+    return o.pair_particles && !o.per_lane_xform && !o.warp_aggregate && !o.deterministic && !o.count_xforms && !o.l2_hints && o.staged_bins <= 0 &&
+           o.deal_period == 1 && o.min_blocks == 0;
+}
+
+std::vector<char> flame::variant_cubin(bool staged, const std::vector<float>* baked, bool pairs) const {
+    return compile_with_bounds(variant_source(staged, baked, pairs), options_);
 }
 
 void flame::reset_animation() { needs_update_ = true; }
@@ -558,13 +570,14 @@ static void ensure_module(flame& f) {
 }
 
 // builds (on first use) and returns a further variant of the kernels; a baked variant whose values are stale is rebuilt
-static flame_device::variant& ensure_variant(flame& f, bool staged, bool baked) {
+static flame_device::variant& ensure_variant(flame& f, bool staged, bool baked, bool pairs = false) {
     flame_device& d = *f.device();
-    flame_device::variant& v = d.variants[staged][baked];
+    flame_device::variant& v = pairs ? d.paired : d.variants[staged][baked];
     if (v.module && (!baked || v.values == d.cfp_staging)) return v;
     const auto& api = driver();
     if (v.module) { api.ModuleUnload(v.module); v = flame_device::variant{}; }
-    const std::vector<char> image = f.variant_cubin(staged, baked ? &d.cfp_staging : nullptr);
+    if (baked && !staged) d.pairs_state = 0;  // new values: measure again
+    const std::vector<char> image = f.variant_cubin(staged, baked ? &d.cfp_staging : nullptr, pairs);
     cu_check(api.ModuleLoadData(&v.module, image.data()), "cuModuleLoadData(variant)");
     cu_check(api.ModuleGetFunction(&v.draw, v.module, "rfk_draw"), "rfk_draw(variant)");
     if (!staged) {
@@ -688,6 +701,57 @@ static rfk_iter_params_host base_params(flame& f) {
     return p;
 }
 
+// Kernel option pair_particles = 1: which of the two value-specialised builds — one particle per thread, or two — is the
+// faster one for this genome is MEASURED once per build: both run rfk_warm (first-run pass + 24 iterations, no histogram) on
+// scratch copies of the particle and RNG buffers, CUDA-event timed; nothing the render reads or writes is touched, so a run
+// is the same with and without the measurement. (Shipped genome: the paired build is 3.7 % faster; the 12-xform stress
+// genome: 10 % slower — its xform bodies, inlined twice, no longer fit the instruction cache.)
+static void choose_pairs(flame& f) {
+    flame_device& d = *f.device();
+    const kernel_options& o = f.options();
+    if (d.pairs_state != 0) return;
+    if (!f.pairs_allowed()) { d.pairs_state = 2; return; }
+    if (o.pair_particles == 2) { ensure_variant(f, false, true, true); d.pairs_state = 1; return; }
+    flame_device::variant* candidates[2] = {&ensure_variant(f, false, true, false), &ensure_variant(f, false, true, true)};
+    d.pairs_state = 0;  // (ensure_variant resets it when it rebuilds)
+    const std::size_t P = g_sim.total_particles;
+    float4* particles = nullptr;
+    uint4* rng = nullptr;
+    cudaEvent_t ev[2][2] = {};
+    float ms[2] = {0.0f, 0.0f};
+    try {
+        cuda_check(cudaMalloc(&particles, P * sizeof(float4)), "cudaMalloc(tuning scratch)");
+        cuda_check(cudaMalloc(&rng, P * sizeof(uint4)), "cudaMalloc(tuning scratch)");
+        for (auto& pair : ev) for (auto& e : pair) cuda_check(cudaEventCreate(&e), "cudaEventCreate");
+        const unsigned int deal_counter = d.deal_counter;
+        for (int round = 0; round < 2; round++) {  // round 0 loads the code, round 1 is timed
+            for (int k = 0; k < 2; k++) {
+                cuda_check(cudaMemcpyAsync(rng, g_sim.rng, P * sizeof(uint4), cudaMemcpyDeviceToDevice, g_sim.stream), "copy rng states");
+                rfk_iter_params_host p = base_params(f);
+                p.particles = particles;
+                p.rng = rng;
+                p.first_run = 1;
+                p.num_iter = 24;
+                void* args[] = {&p};
+                cuda_check(cudaEventRecord(ev[k][0], g_sim.stream), "event");
+                launch(candidates[k]->warm, (unsigned)(P / o.block_width), k ? o.block_width / 2 : o.block_width, args);
+                cuda_check(cudaEventRecord(ev[k][1], g_sim.stream), "event");
+            }
+        }
+        d.deal_counter = deal_counter;
+        cuda_check(cudaStreamSynchronize(g_sim.stream), "pair_particles measurement");
+        for (int k = 0; k < 2; k++) cuda_check(cudaEventElapsedTime(&ms[k], ev[k][0], ev[k][1]), "event time");
+    } catch (...) {
+        cudaFree(particles); cudaFree(rng);
+        for (auto& pair : ev) for (auto& e : pair) if (e) cudaEventDestroy(e);
+        throw;
+    }
+    cudaFree(particles); cudaFree(rng);
+    for (auto& pair : ev) for (auto& e : pair) cudaEventDestroy(e);
+    d.pairs_state = ms[1] < ms[0] ? 1 : 2;
+    d.pairs_ms[0] = ms[0]; d.pairs_ms[1] = ms[1];
+}
+
 void flame::warmup(std::size_t num_passes, float tss_width) {
     ensure_buffers(*this);
     flame_device& d = *device_;
@@ -731,13 +795,21 @@ void flame::warmup(std::size_t num_passes, float tss_width) {
     const bool have_match = d.variants[0][1].module && d.variants[0][1].values == d.cfp_staging;
     d.use_baked = !d.cfp_staging.empty() && (options_.specialize == 1 || (options_.specialize == 2 && (seen_before || have_match)));
     d.previous_constants = d.cfp_staging;
-    CUfunction warm_fn = d.use_baked ? ensure_variant(*this, false, true).warm : d.warm;
+    CUfunction warm_fn = d.warm;
+    bool pairs = false;
+    if (d.use_baked) {
+        ensure_variant(*this, false, true);  // (re)built here when the values changed: the measurement below starts over
+        choose_pairs(*this);
+        pairs = d.pairs_state == 1;
+        warm_fn = ensure_variant(*this, false, true, pairs).warm;
+    }
 
     rfk_iter_params_host p = base_params(*this);
     p.first_run = 1;
     p.num_iter = (int)num_passes;
     void* args[] = {&p};
-    launch(warm_fn, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
+    const unsigned warm_threads = pairs ? options_.block_width / 2 : options_.block_width;
+    launch(warm_fn, (unsigned)(g_sim.total_particles / options_.block_width), warm_threads, args);
     d.binned_reported = 0;  // stream-ordered: the draw calls, read-backs and rfk_synchronize that follow wait for it
     d.warmed = true;
 }
@@ -858,6 +930,13 @@ std::size_t flame::reference_draw_to_bins(float* bins, std::size_t bins_len, std
     return (std::size_t)delta;
 }
 
+int flame_pairs_state(const flame& f, float ms_out[2]) {
+    flame_device* d = const_cast<flame&>(f).device();
+    if (!d) return 0;
+    if (ms_out) { ms_out[0] = d->pairs_ms[0]; ms_out[1] = d->pairs_ms[1]; }
+    return d->use_baked ? d->pairs_state : 0;
+}
+
 bool flame_uses_baked(const flame& f) { return const_cast<flame&>(f).device() && const_cast<flame&>(f).device()->use_baked; }
 
 const unsigned long long* flame_binned_counter_dev(flame& f) { return f.device() ? f.device()->counters : nullptr; }
@@ -901,7 +980,8 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
     }
     int stage_regions = 0, stage_shift = options_.staged_bins > 0 ? options_.staged_bins : 0;
     const bool baked = d.use_baked && !d.cfp_staging.empty();
-    CUfunction draw_fn = baked ? ensure_variant(*this, false, true).draw : d.draw;
+    bool pairs = baked && d.pairs_state == 1;
+    CUfunction draw_fn = baked ? ensure_variant(*this, false, true, pairs).draw : d.draw;
     if (options_.staged_bins < 0 && !d.stage_unavailable && !options_.deterministic && !options_.warp_aggregate && !options_.l2_hints &&
         W * H * sizeof(float4) >= (std::size_t(1) << 29)) {
         // automatic: a histogram of 512 MiB or more (four times the L2) is drawn through the queues, in at most 64 regions of
@@ -911,6 +991,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         while (((W * H + (std::size_t(1) << shift) - 1) >> shift) > 64) shift++;
         if (shift <= 24) {  // a record holds 24 bits of bin index
             draw_fn = ensure_variant(*this, true, baked).draw;
+            pairs = false;
             stage_shift = shift;
         }
     }
@@ -961,7 +1042,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
             }
         }
         if (d.stage_unavailable) {
-            draw_fn = baked ? ensure_variant(*this, false, true).draw : d.draw;
+            draw_fn = baked ? ensure_variant(*this, false, true, pairs = baked && d.pairs_state == 1).draw : d.draw;
             stage_shift = 0;
         }
     }
@@ -977,7 +1058,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         p.stage_regions = stage_regions;
     }
     void* args[] = {&p};
-    launch(draw_fn, (unsigned)(g_sim.total_particles / options_.block_width), options_.block_width, args);
+    launch(draw_fn, (unsigned)(g_sim.total_particles / options_.block_width), pairs ? options_.block_width / 2 : options_.block_width, args);
     if (stage_regions) {
         kernels::stage_accumulate(d.stage_records, d.stage_cursors, d.stage_fill, p.stage_capacity, p.stage_region_shift, stage_regions, d.palette, p.bins,
                                   W * H, g_sim.stream);

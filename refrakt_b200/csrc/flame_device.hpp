@@ -32,7 +32,9 @@ void flame_bucket_index(flame& f, int n, const float* xyzw, const float ss_affin
 void flame_animate_host(flame& f, float tss_width, int temporal_samples, float* out);
 void flame_kernel_info(flame& f, const char* kernel, int* regs, int* smem_bytes, int* blocks_per_sm);
 void flame_read_counters(flame& f, unsigned long long* out, int n);
-bool flame_uses_baked(const flame& f);  // the last warmup chose the value-specialised kernels (kernel option specialize)
+bool flame_uses_baked(const flame& f);
+// kernel option pair_particles: 0 = generic kernels in use / not measured, 1 = two particles per thread, 2 = one; ms_out = the measurement
+int flame_pairs_state(const flame& f, float ms_out[2]);  // the last warmup chose the value-specialised kernels (kernel option specialize)
 const unsigned long long* flame_binned_counter_dev(flame& f);  // device address of the binned-samples counter (counters[0])
 void flame_copy_particles(flame& f, float* out);  // the flame's particle buffer (P x float4), to host
 

@@ -285,7 +285,9 @@ __device__ __forceinline__ void fma4(float4& acc, const float4& c, float w) {
 //      small class, +-R for the large one — and accumulates; lanes are output columns.
 // Multi-GPU row slabs (rfk_comm_*): `bins` then holds the source rows [src_y0, src_y1) only and the launch produces the
 // output rows [y0, y1); rows outside [src_y0, src_y1) count as empty (they are outside the image, or not needed).
-template <bool DENSITY, bool TONEMAP, int MIN_BLOCKS = 5>
+// MAX_CHUNKS: compile-time bound of the 32-column chunks per window row, (32 + 2R + 31) / 32 — 2 up to radius 16 (the usual
+// 9..11), 4 up to 48, 8 up to 100: the window scan's loops over the chunks unroll to exactly that many loads
+template <bool DENSITY, bool TONEMAP, int MAX_CHUNKS = 8, int MIN_BLOCKS = 5>
 __global__ void __launch_bounds__(DE_THREADS, MIN_BLOCKS) density_tonemap_kernel(const float4* __restrict__ bins, float4* __restrict__ out_f4,
                                                                      uchar4* __restrict__ out_rgba8, const __grid_constant__ density_params p) {
     __shared__ int s_part[DE_THREADS];
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(DE_THREADS, MIN_BLOCKS) density_tonemap_kernel
             bool any_candidate = false;
             // two window rows per trip, all their loads issued before the first is looked at: the scan is a chain of
             // load -> vote -> branch, and with one load in flight per warp its latency was a tenth of the kernel
-            constexpr int kMaxChunks = 8;  // (32 + 2 * 100 + 31) / 32
+            constexpr int kMaxChunks = MAX_CHUNKS;
             for (int row0 = warp; row0 < nrows; row0 += 2 * DE_WARPS) {
                 float dv[2][kMaxChunks];
 #pragma unroll
@@ -615,16 +617,15 @@ void density_tonemap(const float4* bins, float4* out_f4, uchar4* out_rgba8, dens
     cudaGetDevice(&dev);
     static bool configured[64] = {};
     if (dev >= 0 && dev < 64 && !configured[dev]) {  // per device: the opt-in is a property of the function on that device
-        cudaFuncSetAttribute(density_tonemap_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        cudaFuncSetAttribute(density_tonemap_kernel<true, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);  // radius above 48 only
         cudaFuncSetAttribute(density_tonemap_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         configured[dev] = true;
     }
-    static const int min_blocks = [] { const char* e = std::getenv("RFK_DE_MIN_BLOCKS"); return e ? std::atoi(e) : 5; }();  // probe: 6 resident CTAs (40 registers)
-    if (do_density && do_tonemap && min_blocks == 6) {
-        static bool once = false;
-        if (!once) { cudaFuncSetAttribute(density_tonemap_kernel<true, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024); once = true; }
-        density_tonemap_kernel<true, true, 6><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
-    } else if (do_density && do_tonemap) density_tonemap_kernel<true, true><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
+    if (do_density && do_tonemap) {
+        if (nch <= 2) density_tonemap_kernel<true, true, 2><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
+        else if (nch <= 4) density_tonemap_kernel<true, true, 4><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
+        else density_tonemap_kernel<true, true, 8><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
+    }
     else if (do_density) density_tonemap_kernel<true, false><<<grid, block, dyn_bytes, s>>>(bins, out_f4, out_rgba8, p);
     else density_tonemap_kernel<false, true><<<grid, block, 0, s>>>(bins, out_f4, out_rgba8, p);
 }

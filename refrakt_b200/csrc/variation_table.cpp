@@ -188,11 +188,18 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
         if (i + 1 == (int)f.xforms.size()) disp_func += "default: {\n" + dispatch_invoke + "\n}}\n";
         else disp_func += "case " + std::to_string(i) + ": {\n" + dispatch_invoke + "\n}\n";
     }
-    // CUDA dialect: when a few xforms take most of the picks, `dispatch` is a chain of `if (xform == k)` in order of
-    // decreasing weight instead of the switch (whose compare tree + jump table costs ~9 instructions per pick whatever the
-    // weights): E[tests] = sum over the order of position x weight; two instructions per test. The pick is warp-uniform, so
-    // either form is one taken path per warp. Same cases, same text inside them.
-    if (d == dialect::cuda && !f.xforms.empty()) {
+    // CUDA dialect. Every xform's text becomes a function of its own, rfk_xform_<k> (k = m1 for the final xform), and two
+    // dispatchers call them: dispatch_a(v, xform, ...) for one particle and dispatch2_a(v0, v1, xform, ...) for the two
+    // particles a thread of the paired kernels holds — one pick, one walk to the case, the case applied twice.
+    // When a few xforms take most of the picks the walk is a chain of `if (xform == k)` in order of decreasing weight instead
+    // of a switch (whose compare tree + jump table costs ~9 instructions per pick whatever the weights): E[tests] = sum over
+    // the order of position x weight, two instructions per test. The pick is warp-uniform, so either form is one taken path
+    // per warp. Same cases, same text inside them.
+    if (d == dialect::cuda) {
+        auto fn_name = [](int index) { return index < 0 ? std::string("rfk_xform_m1") : "rfk_xform_" + std::to_string(index); };
+        std::string functions;
+        for (const auto& c : cuda_cases)
+            functions += "template <bool first_run>\n__device__ __forceinline__ vec4 " + fn_name(c.first) + "(vec3 v, rfk_rng& rs, const float4 rfk_A){\n" + c.second + "\n}\n";
         std::vector<std::pair<double, int>> order;
         double total = 0.0;
         for (std::size_t i = 0; i < f.xforms.size(); i++) total += std::max(0.0f, f.xforms[i].weight);
@@ -202,22 +209,35 @@ std::string emit(const flame& f, const flame_compiler& vt, dialect d) {
         for (std::size_t k = 0; k < order.size(); k++) expected_tests += order[k].first * (double)std::min(k + 1, order.size() - 1);
         const char* force = std::getenv("RFK_DISPATCH");  // "switch" / "chain": A/B runs
         const bool chain_wanted = force ? std::string(force) == "chain" : (f.xforms.size() >= 3 && expected_tests <= 3.5);
-        if (chain_wanted) {
-            std::string chain = "template <bool first_run>\n__device__ __forceinline__ vec4 dispatch_a(vec3 v, int xform, rfk_rng& rs, const float4 rfk_A){\n";
-            auto body_of = [&](int index) -> const std::string& {
-                for (const auto& c : cuda_cases) if (c.first == index) return c.second;
-                throw std::logic_error("dispatch: missing case");
-            };
-            // RFK_OPAQUE between the tests: the optimiser would otherwise fold the chain back into a switch
-            chain += "int rfk_pick = xform;\n";
-            if (f.final_xform) chain += "if (rfk_pick == -1) {\n" + body_of(-1) + "\n}\n";
-            for (std::size_t k = 0; k + 1 < order.size(); k++)
-                chain += "RFK_OPAQUE(rfk_pick);\nif (rfk_pick == " + std::to_string(order[k].second) + ") {\n" + body_of(order[k].second) + "\n}\n";
-            chain += "{\n" + body_of(order.back().second) + "\n}\n";
-            disp_func = chain;
-        }
+        // `one` / `two`: the statement that applies case k to one particle / to both
+        auto one = [&](int k) { return "return " + fn_name(k) + "<first_run>(v, rs, rfk_A);"; };
+        auto two = [&](int k) { return "o0 = " + fn_name(k) + "<first_run>(v0, rs0, rfk_A); o1 = " + fn_name(k) + "<first_run>(v1, rs1, rfk_A); return;"; };
+        auto walk = [&](auto&& apply, const std::string& nothing) {
+            std::string w;
+            if (f.xforms.empty()) {
+                if (f.final_xform) w += "if (xform == -1) { " + apply(-1) + " }\n";
+                return w + nothing + "\n";
+            }
+            if (chain_wanted) {
+                // RFK_OPAQUE between the tests: the optimiser would otherwise fold the chain back into a switch
+                w += "int rfk_pick = xform;\n";
+                if (f.final_xform) w += "if (rfk_pick == -1) { " + apply(-1) + " }\n";
+                for (std::size_t k = 0; k + 1 < order.size(); k++)
+                    w += "RFK_OPAQUE(rfk_pick);\nif (rfk_pick == " + std::to_string(order[k].second) + ") { " + apply(order[k].second) + " }\n";
+                return w + "{ " + apply(order.back().second) + " }\n";
+            }
+            w += "switch(xform){\n";
+            if (f.final_xform) w += "case -1: { " + apply(-1) + " }\n";
+            for (int i = 0; i + 1 < (int)f.xforms.size(); i++) w += "case " + std::to_string(i) + ": { " + apply(i) + " }\n";
+            return w + "default: { " + apply((int)f.xforms.size() - 1) + " }}\n";
+        };
+        disp_func = functions +
+                    "template <bool first_run>\n__device__ __forceinline__ vec4 dispatch_a(vec3 v, int xform, rfk_rng& rs, const float4 rfk_A){\n" +
+                    walk(one, "return vec4(v.xy, v.z, 0.0f);") + "}\n" +
+                    "template <bool first_run>\n__device__ __forceinline__ void dispatch2_a(vec3 v0, vec3 v1, int xform, rfk_rng& rs0, rfk_rng& rs1, const float4 rfk_A, vec4& o0, vec4& o1){\n" +
+                    walk(two, "o0 = vec4(v0.xy, v0.z, 0.0f); o1 = vec4(v1.xy, v1.z, 0.0f); return;");
     }
-    if (f.xforms.empty()) disp_func += "default: { return vec4(v.xy, v.z, 0.0" + std::string(d == dialect::cuda ? "f" : "") + "); }}\n";
+    if (f.xforms.empty() && d == dialect::glsl) disp_func += "default: { return vec4(v.xy, v.z, 0.0); }}\n";
 
     std::string xid_func = xform_select_text(buf_map, d == dialect::cuda);
 

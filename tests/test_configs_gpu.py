@@ -193,13 +193,31 @@ def test_specialised_kernels_draw_the_same_histogram(gpu_ready, rfk, compiler, o
     W, H, P, TS, passes = 320, 180, 256 * 16 * 32, 32, 64
     g0, n0 = _gpu_bins(rfk, f, W, H, P, TS, passes, 1, seed=5, specialize=0)
     assert not f.uses_specialised()
-    g1, n1 = _gpu_bins(rfk, f, W, H, P, TS, passes, 1, seed=5, specialize=1)
+    g1, n1 = _gpu_bins(rfk, f, W, H, P, TS, passes, 1, seed=5, specialize=1, pair_particles=0)
     assert f.uses_specialised()
     assert abs(n0 - n1) <= 1e-4 * n0
     assert _norm_l1(_pooled(g0), _pooled(g1)) <= 2e-3
     a, na = _oracle_bins(oracle, W, H, P, TS, passes, 1, 0, 41)
     b, nb = _oracle_bins(oracle, W, H, P, TS, passes, 1, P, 42)
-    assert _norm_l1(_pooled(g1), _pooled(a)) <= max(0.02, 1.5 * _norm_l1(_pooled(a), _pooled(b)))
+    self_l1 = _norm_l1(_pooled(a), _pooled(b))
+    assert _norm_l1(_pooled(g1), _pooled(a)) <= max(0.02, 1.5 * self_l1)
+    # two particles per thread (the default of the specialised build): other picks for the same seeds, the same measure
+    g2, n2 = _gpu_bins(rfk, f, W, H, P, TS, passes, 1, seed=5, specialize=1, pair_particles=2)
+    assert f.uses_specialised() and f.pair_particles_state()[0] == 1
+    total = P * passes
+    assert abs(n2 / total - na / total) <= 0.002 * na / total + 3e-4 + abs(na - nb) / total
+    assert abs(g2[..., 3].sum() - n2) <= 1e-3 * n2
+    assert _norm_l1(_pooled(g2), _pooled(a)) <= max(0.02, 1.5 * self_l1)
+    cg, _ = _colour_by_region(g2)
+    ca, ma = _colour_by_region(a)
+    cb, _ = _colour_by_region(b)
+    heavy = ma > 0.005 * ma.sum()
+    assert np.abs(cg - ca)[heavy].max() <= max(0.02, 2.0 * np.abs(cb - ca)[heavy].max())
+    # pair_particles = 1: measured; whichever way it goes, the state and the two probe times are reported
+    f.set_options(pair_particles=1)
+    f.warmup(4, TSS)
+    state, ms = f.pair_particles_state()
+    assert state in (1, 2) and ms[0] > 0 and ms[1] > 0 and (state == 1) == (ms[1] < ms[0])
     # automatic mode: generic on the first warmup with these values, specialised from the second on; an edit goes back to generic
     f.set_options(specialize=2)
     x = f.xform(2)

@@ -19,7 +19,7 @@ def test_abi_exports_every_declared_symbol(rfk):
     for name in sorted(declared):
         assert hasattr(lib, name), "library does not export " + name
     assert declared == set(rfk.SIGNATURES), declared ^ set(rfk.SIGNATURES)
-    assert lib.rfk_abi_version() == 3
+    assert lib.rfk_abi_version() == 4
     out = subprocess.run(["nm", "-D", "--defined-only", rfk.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     exported = set(re.findall(r"\bT (rfk_[a-z0-9_]+)", out))
     assert declared <= exported
@@ -559,6 +559,8 @@ def test_value_specialised_build_compiles_without_a_gpu(rfk, compiler, flame, ov
     assert "RFK_AFF(-1" not in body and "RFK_AFF(4, x)" in body  # the final xform does not rotate: literals; xform 4 does
     assert "if (rfk_pick == 4) {" in body and body.index("rfk_pick == 4") < body.index("rfk_pick == 5")  # heaviest xform first
     assert len(flame.variant_cubin(False, True)) > 10000
+    assert "#define RFK_PAIRS 1" in flame.variant_source(False, 2) and "#define RFK_PAIRS 1" not in src  # two particles per thread
+    assert len(flame.variant_cubin(False, 2)) > 10000
     assert "#define RFK_STAGED_BINS 1" in flame.variant_source(True, False)
     # a genome whose reciprocals include infinities (1 / 0 for unused slots), and a uniform-weight genome (switch, not a chain)
     stress = rfk.Flame.load_flame_string(stress_genome(overlay_vt), overlay_compiler)

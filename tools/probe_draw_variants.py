@@ -17,8 +17,8 @@ FIX = os.path.join(ROOT, "tests", "fixtures")
 P, TS, W, H = 2048 * 1024, 512, 3840, 2160
 
 
-def measure(flame, name, spec, calls=12):
-    flame.set_options(specialize=spec)
+def measure(flame, name, spec, calls=12, pairs=1):
+    flame.set_options(specialize=spec, pair_particles=pairs)
     r.set_sim_parameters(P, TS, 1024, seed=0)
     flame.warmup(16, 1.2 / 60)
     bins = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
@@ -32,7 +32,7 @@ def measure(flame, name, spec, calls=12):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / calls
     binned = flame.binned_total()
-    rec = dict(genome=name, specialize=spec, uses_specialised=flame.uses_specialised(), ms_per_call=ms, giter_s=P * 128 / ms / 1e6,
+    rec = dict(genome=name, specialize=spec, pair_particles=pairs, uses_specialised=flame.uses_specialised(), pair_state=flame.pair_particles_state(), ms_per_call=ms, giter_s=P * 128 / ms / 1e6,
                in_bounds=binned / (P * 128 * (calls + 1)), **flame.kernel_info("rfk_draw"))
     print(json.dumps(rec), flush=True)
     d = bins.view(H, W, 4)[..., 3].double().view(H // 8, 8, W // 8, 8).sum(dim=(1, 3))
@@ -53,9 +53,15 @@ def main():
     stress = r.Flame.load_flame_string(stress_genome(_Table(compiler)), compiler)
     assert shipped is not None and stress is not None, r.Flame.last_error()
     for name, flame in (("electricsheep.247.11256", shipped), ("stress247", stress)):
+        if "--pairs-only" in sys.argv:
+            measure(flame, name, 1, pairs=1)
+            continue
         a = measure(flame, name, 0)
-        b = measure(flame, name, 1)
-        print(json.dumps(dict(genome=name, pooled_l1_generic_vs_specialised=float(0.5 * np.abs(a - b).sum()))), flush=True)
+        b = measure(flame, name, 1, pairs=0)
+        c = measure(flame, name, 1, pairs=2)
+        measure(flame, name, 1, pairs=1)  # measured choice
+        print(json.dumps(dict(genome=name, pooled_l1_generic_vs_specialised=float(0.5 * np.abs(a - b).sum()),
+                              pooled_l1_single_vs_pairs=float(0.5 * np.abs(b - c).sum()))), flush=True)
 
 
 if __name__ == "__main__":
