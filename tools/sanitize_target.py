@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import refrakt_b200 as r  # noqa: E402
 
-FIX = os.path.join(ROOT, "tests", "fixtures")
+FIX = os.path.join(ROOT, "refrakt_b200", "data")
 compiler = r.FlameCompiler(os.path.join(FIX, "variations.yaml"))
 flame = r.Flame.load_flame(os.path.join(FIX, "electricsheep.247.11256.flam3"), compiler)
 assert flame is not None, r.Flame.last_error()
@@ -18,7 +18,8 @@ assert flame is not None, r.Flame.last_error()
 P, TS = 256 * 32, 16
 r.set_sim_parameters(P, TS, 16, seed=3)
 W, H = 96, 54
-modes = [dict(), dict(warp_aggregate=1), dict(per_lane_xform=1), dict(deterministic=1), dict(count_xforms=1),
+modes = [dict(specialize=0), dict(specialize=1, pair_particles=0), dict(specialize=1, pair_particles=2), dict(specialize=1, pair_particles=1),
+         dict(warp_aggregate=1), dict(per_lane_xform=1), dict(deterministic=1), dict(count_xforms=1),
          dict(block_width=128), dict(block_width=512), dict(deal_period=4), dict(math_mode=0), dict(math_mode=2)]
 base = flame.options()
 defaults = {k: getattr(base, k) for k, _ in base._fields_}
@@ -72,6 +73,32 @@ bins = r.DeviceBuffer(W * H * 16)
 bins.zero_out()
 n = flame.reference_draw_to_bins(bins.ptr, W * H, W, 3, shuffle_ids=np.arange(6, dtype=np.uint32) % 8)
 print("reference pass mode binned", n)
+
+# round 2: density estimation over row slabs (and a large radius), the sharded frame on a one-rank communicator (NCCL data path)
+bins_h = np.zeros((H, W, 4), dtype=np.float32)
+rng = np.random.default_rng(1)
+bins_h[..., 3] = (rng.random((H, W)) < 0.2) * rng.integers(1, 60, (H, W))
+bins_h[..., :3] = rng.random((H, W, 3)) * bins_h[..., 3:4]
+post = flame.post_params()
+for radius, world in ((11, 3), (40, 2), (0, 2)):
+    post.estimator_radius = radius
+    for rank in range(world):
+        sl = r.comm_row_slab(H, radius, rank, world)
+        rows = np.ascontiguousarray(bins_h[H - sl.src_y1: H - sl.src_y0])
+        d_rows, d_out = r.DeviceBuffer(rows.nbytes), r.DeviceBuffer((sl.y1 - sl.y0) * W * 16)
+        d_rows.upload(rows)
+        r.density_tonemap_rows(d_rows.ptr, d_out.ptr, None, W, H, post, sl.y0, sl.y1, sl.src_y0, sl.src_y1, sl.y0)
+        d_out.download(np.float32, (sl.y1 - sl.y0, W, 4))
+        d_rows.free(); d_out.free()
+    print("density over row slabs: radius", radius, "ranks", world)
+try:
+    r.comm_init(r.comm_unique_id(), 0, 1)
+    for ss in (1, 2):
+        img8, imgf, st = flame.render_frame_sharded(W, H, max_draw_calls=2, drawing_passes=4, warmup_passes=3, supersample=ss, want_image=True)
+        print("sharded frame on one rank: supersample", ss, "binned", st.binned_global, "p2p", st.p2p)
+    r.comm_destroy()
+except r.RefraktError as e:
+    print("sharded frame skipped:", e)
 
 print("seed", r.seed_rng_states(1024, 0)[-1], "hammersley", r.make_sample_points(512)[-1], "shuffle", r.make_shuffle_buffers(512, 2, 1)[0, :4])
 print("launches", r.kernel_launch_count())
