@@ -372,6 +372,9 @@ int rfk_set_rng_states(const uint32_t* states, size_t first, size_t count); /* h
 
 /* ---- output: the reference's screenshot (src/main.cpp:590-593, stbi_write_png of get_pixels()) ---- */
 int rfk_write_png(const char* path, const uint8_t* rgba8, size_t width, size_t height); /* host pixels, rows top to bottom */
+/* the float frame (rfk_render_frame's image_out; the reference keeps RGBA32F textures, main.cpp:218-219, and saves 8 bits):
+ * OpenEXR, scanline, uncompressed, four 32-bit float channels */
+int rfk_write_exr(const char* path, const float* rgba32f, size_t width, size_t height);
 
 /* ---- reference pass mode: the reference's own dispatch structure on the GPU (flame.cpp:252-280, :317-325 driving
  * flame.glsl:41-90: ONE iteration per launch on a (PPT/256, TS) grid, particle and RNG state through global memory, one

@@ -185,6 +185,7 @@ SIGNATURES = {
     "rfk_import_rng_states": (_i, [_cp, _cp]),
     "rfk_set_rng_states": (_i, [_upp, _sz, _sz]),
     "rfk_write_png": (_i, [_cp, _vp, _sz, _sz]),
+    "rfk_write_exr": (_i, [_cp, _vp, _sz, _sz]),
     "rfk_set_shuffle_buffers": (_i, [_upp, _sz, C.c_uint64]),
     "rfk_flame_reference_warmup": (_i, [_vp, _sz, _f, _upp]),
     "rfk_flame_reference_draw_to_bins": (C.c_int64, [_vp, _vp, _sz, _sz, _i, _upp]),
@@ -755,6 +756,13 @@ def write_png(path: str, rgba8: np.ndarray):
     rgba8 = np.ascontiguousarray(rgba8, dtype=np.uint8)
     h, w = rgba8.shape[:2]
     _check(lib().rfk_write_png(path.encode(), rgba8.ctypes.data, w, h), "write_png")
+
+
+def write_exr(path: str, rgba32f: np.ndarray):
+    """the float frame as an uncompressed scanline OpenEXR file; rgba32f is H x W x 4 float32, rows top to bottom"""
+    rgba32f = np.ascontiguousarray(rgba32f, dtype=np.float32)
+    h, w = rgba32f.shape[:2]
+    _check(lib().rfk_write_exr(path.encode(), rgba32f.ctypes.data, w, h), "write_exr")
 
 
 def copy_rng_states(first: int, count: int) -> np.ndarray:

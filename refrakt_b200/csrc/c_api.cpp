@@ -1177,6 +1177,14 @@ int rfk_write_png(const char* path, const uint8_t* rgba8, size_t width, size_t h
     } catch (const std::exception& e) { return fail(RFK_E_INVALID, e.what()); }
 }
 
+int rfk_write_exr(const char* path, const float* rgba, size_t width, size_t height) {
+    try {
+        if (!path || !rgba) return fail(RFK_E_INVALID, "rfk_write_exr: null argument");
+        write_exr_rgba32f(path, rgba, width, height);
+        return RFK_OK;
+    } catch (const std::exception& e) { return fail(RFK_E_INVALID, e.what()); }
+}
+
 // ---- reference pass mode ----
 int rfk_set_shuffle_buffers(const uint32_t* tables, size_t count, uint64_t seed) {
     return guarded([&]() -> int { flame::set_shuffle_buffers(tables, count, seed); return RFK_OK; });

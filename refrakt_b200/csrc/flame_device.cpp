@@ -650,12 +650,20 @@ std::vector<float> flame::constant_table(const float* fp) const {
     const std::size_t size = std::min<std::size_t>(std::max(1, buffer_map_.size), PARAM_BUFFER);
     std::vector<float> t(4 * size);
     for (std::size_t i = 0; i < size; i++) {
-        volatile float prod = i ? fp[i - 1] * fp[i] : 0.0f;  // rounded to binary32, like the device's FMUL
         t[i] = fp[i];
         t[size + i] = 1.0f / fp[i];
+    }
+    // the blend constants exist at the colour-speed slots only (anywhere else they would tie the table — the key of the
+    // value-specialised build — to neighbouring slots for nothing, e.g. the translation e to the rotating coefficient d)
+    auto blend = [&](const xform_slots& m) {
+        const std::size_t i = (std::size_t)m.color_speed;
+        if (i == 0 || i >= size) return;
+        volatile float prod = fp[i - 1] * fp[i];  // rounded to binary32, like the device's FMUL
         t[2 * size + i] = 1.0f - fp[i];
         t[3 * size + i] = prod;
-    }
+    };
+    for (const auto& m : buffer_map_.xforms) blend(m);
+    if (buffer_map_.final_xform) blend(*buffer_map_.final_xform);
     // The rotated coefficients (a, b, c, d) of an xform that rotates are never read from this table — the kernels take them
     // from the per-temporal-sample rows (RFK_AFF) — and they change with every frame of an animation (src/main.cpp:383-395):
     // left out, so that the table, which is also the key of the value-specialised build, stays the same from frame to frame.

@@ -19,6 +19,7 @@ static void usage() {
                  "  [--frames N --fps 60] (OUT.png takes a %%d / %%04d frame number) [--deterministic] [--math-mode 0|1|2]\n"
                  "  [--supersample 1] [--filter 1.0] (histogram at supersample x the image size, spatial filter radius in pixels;\n"
                  "   --quality is samples per histogram bin)\n"
+                 "  [--exr OUT.exr] also write the float frame (OpenEXR, uncompressed 32-bit float RGBA; same %%d rule as --out)\n"
                  "  [--motion] evaluate the genome's <motion> elements at every frame's time (frame / fps)\n"
                  "  [--world N --rank R --comm-file PATH] one process per GPU (--device defaults to R): the N processes render every\n"
                  "   frame together (particle streams sharded, histograms reduce-scattered, rank 0 writes the PNG); rank 0 leaves the\n"
@@ -75,7 +76,7 @@ int main(int argc, char** argv) {
     float tss_width = 1.2f / 60.0f, fps = 60.0f;
     unsigned long long seed = 0;
     int device = -1, deterministic = 0, math_mode = -1, world = 1, rank = 0, frame_parallel = 0, motion = 0;
-    std::string comm_file;
+    std::string comm_file, exr;
     unsigned supersample = 1;
     float filter_radius = 1.0f;
     for (int i = 1; i < argc; i++) {
@@ -104,6 +105,7 @@ int main(int argc, char** argv) {
         else if (a == "--comm-file") comm_file = next();
         else if (a == "--frame-parallel") frame_parallel = 1;
         else if (a == "--motion") motion = 1;
+        else if (a == "--exr") exr = next();
         else if (a == "--deterministic") deterministic = 1;
         else if (a == "--math-mode") math_mode = std::atoi(next());
         else { usage(); return 2; }
@@ -138,6 +140,7 @@ int main(int argc, char** argv) {
     }
 
     std::vector<uint8_t> pixels((size_t)width * height * 4);
+    std::vector<float> image;
     rfk_frame_request req{};
     req.width = width; req.height = height; req.warmup_passes = warmup; req.drawing_passes = passes; req.tss_width = tss_width;
     req.target_binned = (uint64_t)quality * width * height * supersample * supersample; req.max_draw_calls = 0; req.scale_constant_exp = 4.0f;
@@ -165,7 +168,12 @@ int main(int argc, char** argv) {
             continue;
         }
         rfk_frame_stats st{};
-        if (rfk_render_frame(f, &req, pixels.data(), nullptr, &st) != RFK_OK) die("render_frame");
+        if (!exr.empty() && image.empty()) image.resize((size_t)width * height * 4);
+        if (rfk_render_frame(f, &req, pixels.data(), exr.empty() ? nullptr : image.data(), &st) != RFK_OK) die("render_frame");
+        if (!exr.empty()) {
+            std::string exr_name;
+            if (!frame_name(exr, frame, exr_name) || rfk_write_exr(exr_name.c_str(), image.data(), width, height) != RFK_OK) die("write_exr");
+        }
         double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (rfk_write_png(name.c_str(), pixels.data(), width, height) != RFK_OK) die("write_png");
         std::printf("{\"frame\": %u, \"file\": \"%s\", \"iterations\": %llu, \"binned\": %llu, \"draw_calls\": %u, \"ms\": %.3f, \"ms_draw\": %.3f, \"ms_post\": %.3f, \"giter_per_s\": %.2f}\n",

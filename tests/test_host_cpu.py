@@ -574,3 +574,37 @@ def test_value_specialised_build_compiles_without_a_gpu(rfk, compiler, flame, ov
     assert f.variant_source(False, True) == before
     f.set_variation(0, "julia", 0.5)
     assert f.variant_source(False, True) != before
+
+
+def test_exr_writer_round_trip(rfk, tmp_path):
+    """rfk_write_exr: scanline OpenEXR 2, uncompressed, FLOAT channels A B G R — read back here by the file layout"""
+    import struct
+    rng = np.random.default_rng(3)
+    W, H = 37, 11
+    img = rng.random((H, W, 4)).astype(np.float32) * 4 - 1
+    path = str(tmp_path / "frame.exr")
+    rfk.write_exr(path, img)
+    raw = open(path, "rb").read()
+    assert raw[:8] == bytes([0x76, 0x2F, 0x31, 0x01, 2, 0, 0, 0])
+    pos, attrs = 8, {}
+    while raw[pos] != 0:
+        name_end = raw.index(b"\0", pos); type_end = raw.index(b"\0", name_end + 1)
+        size = struct.unpack_from("<i", raw, type_end + 1)[0]
+        attrs[raw[pos:name_end].decode()] = (raw[name_end + 1:type_end].decode(), raw[type_end + 5:type_end + 5 + size])
+        pos = type_end + 5 + size
+    pos += 1
+    assert attrs["compression"] == ("compression", b"\0") and attrs["lineOrder"][1] == b"\0"
+    assert struct.unpack("<4i", attrs["dataWindow"][1]) == (0, 0, W - 1, H - 1) == struct.unpack("<4i", attrs["displayWindow"][1])
+    names = [c for c in attrs["channels"][1].split(b"\0") if len(c) == 1 and c.isalpha()]
+    assert names == [b"A", b"B", b"G", b"R"]
+    offsets = struct.unpack_from("<%dQ" % H, raw, pos)
+    got = np.zeros_like(img)
+    for y, off in enumerate(offsets):
+        yy, nbytes = struct.unpack_from("<ii", raw, off)
+        assert yy == y and nbytes == 16 * W
+        planes = np.frombuffer(raw, dtype="<f4", count=4 * W, offset=off + 8).reshape(4, W)
+        got[y, :, 3], got[y, :, 2], got[y, :, 1], got[y, :, 0] = planes
+    assert np.array_equal(got.view(np.uint32), img.view(np.uint32))
+    assert len(raw) == offsets[-1] + 8 + 16 * W
+    with pytest.raises(rfk.RefraktError):
+        rfk.write_exr(str(tmp_path / "no_such_dir" / "x.exr"), img)
