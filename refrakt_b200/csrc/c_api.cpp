@@ -678,9 +678,13 @@ struct sharded_buffers {
     unsigned long long* counters = nullptr;  // [0] binned samples of all ranks, [1] barrier token
     uint64_t generation = 0;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t counted = nullptr;                // the first call's count has reached host_counter
+    unsigned long long* host_counter = nullptr;   // pinned
     void release() {
         comm::release_peers();
         cudaFree(bins); cudaFree(slab); cudaFree(image); cudaFree(small); cudaFree(rows8); cudaFree(full8); cudaFree(full_image); cudaFree(counters);
+        if (host_counter) cudaFreeHost(host_counter);
+        host_counter = nullptr;
         bins = slab = image = small = full_image = nullptr; rows8 = full8 = nullptr; counters = nullptr;
         bins_n = slab_n = image_n = small_n = rows8_n = full8_n = full_image_n = 0;
         generation++;
@@ -955,14 +959,6 @@ int rfk_render_frame_sharded(rfk_flame* f, const rfk_sharded_request* sreq, uint
         const unsigned long long* binned_dev = flame_binned_counter_dev(*fl);
         uint64_t passes = 0, binned_global = 0;
         uint32_t calls = 0;
-        auto global_binned = [&]() -> uint64_t {  // sum over the ranks of the binned counters; blocks
-            cuda_ok(cudaMemcpyAsync(b.counters, binned_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s), "copy binned counter");
-            comm::barrier_sum(reinterpret_cast<std::uint64_t*>(b.counters), 1, s);
-            unsigned long long v = 0;
-            cuda_ok(cudaMemcpyAsync(&v, b.counters, sizeof v, cudaMemcpyDeviceToHost, s), "read binned counter");
-            cuda_ok(cudaStreamSynchronize(s), "read binned counter");
-            return v;
-        };
         auto draw_passes = [&](uint64_t count) {
             while (count) {
                 if (req->max_draw_calls && calls >= req->max_draw_calls) return;
@@ -975,16 +971,29 @@ int rfk_render_frame_sharded(rfk_flame* f, const rfk_sharded_request* sreq, uint
         if (!req->target_binned) {
             draw_passes((uint64_t)req->max_draw_calls * req->drawing_passes);
         } else {
-            // a first call on every rank measures what a pass lands; the rest is enqueued without a host round trip
+            // a first call on every rank measures what a pass lands. Its count travels to the host behind an event while the GPU
+            // already works on the passes that cannot overshoot whatever the count turns out to be (a pass lands at most one
+            // sample per particle, so target / (world * particles) passes are always safe); the remainder is sized from the count
+            // and enqueued behind them: no bubble on the device, and no host round trip after the last draw call either.
             const uint64_t even_share = (req->target_binned / ((uint64_t)world * sim_total_particles())) + 1;  // passes if every iteration binned
             draw_passes(std::min<uint64_t>(req->drawing_passes, std::max<uint64_t>(1, even_share / 2)));
-            binned_global = global_binned();
-            if (binned_global < req->target_binned) {
-                // the rest in one go, with a 0.2 % margin; the draw calls stay in flight — the exchange below does not wait for
-                // their count, which is read together with the image (a shortfall, rare, costs one more round there)
-                per_pass = passes ? (double)binned_global / (double)passes : 0.0;
-                const double left = (double)(req->target_binned - binned_global);
-                draw_passes(per_pass > 0.0 ? std::max<uint64_t>(1, (uint64_t)std::ceil(left / per_pass * 1.002)) : req->drawing_passes);
+            const uint64_t first_passes = passes;
+            if (!b.host_counter) cuda_ok(cudaMallocHost(&b.host_counter, sizeof(unsigned long long)), "cudaMallocHost(counter)");
+            if (!b.counted) cuda_ok(cudaEventCreateWithFlags(&b.counted, cudaEventDisableTiming), "cudaEventCreate");
+            cuda_ok(cudaMemcpyAsync(b.counters + 2, binned_dev, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s), "copy binned counter");
+            comm::barrier_sum(reinterpret_cast<std::uint64_t*>(b.counters + 2), 1, s);
+            cuda_ok(cudaMemcpyAsync(b.host_counter, b.counters + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "read binned counter");
+            cuda_ok(cudaEventRecord(b.counted, s), "event");
+            if (even_share - 1 > passes) draw_passes(even_share - 1 - passes);
+            cuda_ok(cudaEventSynchronize(b.counted), "read binned counter");
+            binned_global = *b.host_counter;
+            per_pass = first_passes ? (double)binned_global / (double)first_passes : 0.0;
+            if (per_pass > 0.0) {
+                // 0.2 % margin; a shortfall (rare) is found when the count is read together with the image and costs one more round
+                const uint64_t wanted = (uint64_t)std::ceil((double)req->target_binned / per_pass * 1.002);
+                if (wanted > passes) draw_passes(wanted - passes);
+            } else if (binned_global < req->target_binned) {
+                draw_passes(req->drawing_passes);
             }
         }
         cuda_ok(cudaEventRecord(b.ev[2], s), "event");

@@ -38,6 +38,9 @@ __device__ __forceinline__ vec4 dispatch(vec3 v, int xform, rfk_rng& rs) {
     return dispatch_a<first_run>(v, xform, rs, rfk_aff[xform + 1]);
 }
 
+#ifndef RFK_EXPERIMENT
+#define RFK_EXPERIMENT 0  // timing builds of tools/gpu_probe_l1tex.sh (paired rfk_draw only)
+#endif
 struct rfk_iter_params {
     float4* particles;                  // [P] (x, y, colour, 0): pos_in/pos_out of buffers.glsl:1-9
     uint4* rng;                         // [P] JSF32 state per thread slot (random.glsl:1-4)
@@ -527,12 +530,28 @@ __device__ __forceinline__ void rfk_iterate_pairs(const rfk_iter_params& p) {
         unsigned int cx, cy;
         if (rfk_bin_test(fx, fy, fw, p.ss_affine, p.bin_w, p.bin_h, cx, cy)) {
             const int idx = rfk_bin_of(cx, cy, p.bin_w, p.bin_h);
+#if RFK_EXPERIMENT == 1  // timing only: rows forced into distinct bank groups per quarter warp = the cost of eight swizzled copies
+            const unsigned int prow = (unsigned int)__cvta_generic_to_shared(&pal[(rfk_palette_index(fc) & ~7u) | (lane & 7u)]);
+            float4 col;
+            asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(col.x), "=f"(col.y), "=f"(col.z), "=f"(col.w) : "r"(prow));
+#elif RFK_EXPERIMENT == 2  // timing only: one 128-bit load of the random row
+            const unsigned int prow = (unsigned int)__cvta_generic_to_shared(&pal[rfk_palette_index(fc)]);
+            float4 col;
+            asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(col.x), "=f"(col.y), "=f"(col.z), "=f"(col.w) : "r"(prow));
+#elif RFK_EXPERIMENT == 3  // timing only: no palette
+            float4 col = make_float4(fc, fc, fc, fw);
+#else
             const unsigned int prow = (unsigned int)__cvta_generic_to_shared(&pal[rfk_palette_index(fc)]);
             float4 col;
             asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(col.x), "=f"(col.y) : "r"(prow));
             asm volatile("ld.volatile.shared.f32 %0, [%1+8];" : "=f"(col.z) : "r"(prow));
+#endif
             col.w = fw;
+#if RFK_EXPERIMENT == 4  // timing only: no reduction (the palette row is still read: the loads are volatile)
+            if (col.x == -1.0f) rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, col.w);
+#else
             rfk_red_add_v4(p.bins + idx, col.x, col.y, col.z, col.w);
+#endif
             binned++;
         }
     };

@@ -312,6 +312,7 @@ void flame::rebuild_cuda_source() {
     s += "#define RFK_COUNT_XFORMS " + std::to_string(options_.count_xforms ? 1 : 0) + "\n";
     s += "#define RFK_L2_HINTS " + std::to_string(options_.l2_hints ? 1 : 0) + "\n";
     s += "#define RFK_STAGED_BINS " + std::to_string(options_.staged_bins > 0 ? 1 : 0) + "\n";
+    if (const char* e = std::getenv("RFK_EXPERIMENT")) s += "#define RFK_EXPERIMENT " + std::string(e) + "\n";  // timing builds of tools/gpu_probe_l1tex.sh
     // min_blocks 0 = automatic (flame::cubin): 2048 resident threads per SM (32 registers) unless that spills, else 1536
     // (40 registers) — tools/probe_min_blocks.py; -1 = leave the register budget to the compiler
     if (options_.min_blocks > 0) s += "#define RFK_LAUNCH_BOUNDS __launch_bounds__(RFK_BLOCK, " + std::to_string(options_.min_blocks) + ")\n";
@@ -996,6 +997,7 @@ void flame::draw_to_bins_async(float* bins, std::size_t bins_len, std::size_t bi
         // at least 2^22 bins (64 MB, half the L2; measured best on the 2.12 GB histogram of config 3). The crossover was measured
         // (profiles/r01_staged_threshold_probe.json): 299 MB direct 1.89 ms per call / queued 3.16; 531 MB 3.64 / 3.21; 944 MB 5.37 / 3.23
         int shift = 22;
+        if (const char* e = std::getenv("RFK_STAGE_SHIFT")) shift = std::max(8, std::min(24, std::atoi(e)));  // tuning runs
         while (((W * H + (std::size_t(1) << shift) - 1) >> shift) > 64) shift++;
         if (shift <= 24) {  // a record holds 24 bits of bin index
             draw_fn = ensure_variant(*this, true, baked).draw;

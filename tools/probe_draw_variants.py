@@ -54,7 +54,7 @@ def main():
     assert shipped is not None and stress is not None, r.Flame.last_error()
     for name, flame in (("electricsheep.247.11256", shipped), ("stress247", stress)):
         if "--pairs-only" in sys.argv:
-            measure(flame, name, 1, pairs=1)
+            measure(flame, name, 1, pairs=2)
             continue
         a = measure(flame, name, 0)
         b = measure(flame, name, 1, pairs=0)

@@ -64,6 +64,13 @@ for kw, max_bytes in ((dict(staged_bins=8), None), (dict(staged_bins=8), 21 * 40
 os.environ.pop("RFK_STAGE_MAX_BYTES", None)
 flame.set_options(**defaults)
 
+# region queues inside a frame (rfk_render_frame, several draw calls)
+for passes in (4, 40):
+    flame.set_options(staged_bins=8)
+    img, stats = flame.render_frame(W, H, max_draw_calls=3, drawing_passes=passes, warmup_passes=3)
+    print("queued frame: passes", passes, "binned", stats.binned)
+flame.set_options(**defaults)
+
 img, stats = flame.render_frame(W, H, max_draw_calls=1, drawing_passes=4, warmup_passes=3, supersample=2, filter_radius=0.75)
 print("supersampled frame", img.shape, stats.binned)
 
