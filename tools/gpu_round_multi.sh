@@ -24,14 +24,21 @@ except Exception as e:
     print("cfg $1 failed", e); print(open("$out/bench_cfg$1_${n}gpu_$tag.err").read()[-2500:])
 PY
 }
-run_bench 2 "--steps 5 --warmup 3"
-NCCL_DEBUG=INFO RFK_COMM_P2P=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --config 2 --steps 3 --warmup 2 --no-weak \
-    > $out/bench_cfg2_${n}gpu_nccl_$tag.json 2> $out/bench_cfg2_${n}gpu_nccl_$tag.err
-tail -c 700 $out/bench_cfg2_${n}gpu_nccl_$tag.json; grep -i "NVLS\|P2P/\|via" $out/bench_cfg2_${n}gpu_nccl_$tag.err | head -5
-run_bench 3 "--steps 2 --warmup 3"
-run_bench 4 "--steps 2 --warmup 1"
-run_bench 5 "--steps 3 --warmup 3"
-run_bench 1 "--steps 5 --warmup 3"
+what=${WHAT:-"2 nccl 3 4 5 1 cli"}   # which parts to run
+for w in $what; do
+  case $w in
+    2) run_bench 2 "--steps 5 --warmup 3" ;;
+    nccl)
+      NCCL_DEBUG=INFO RFK_COMM_P2P=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --config 2 --steps 3 --warmup 2 --no-weak \
+          > $out/bench_cfg2_${n}gpu_nccl_$tag.json 2> $out/bench_cfg2_${n}gpu_nccl_$tag.err
+      tail -c 700 $out/bench_cfg2_${n}gpu_nccl_$tag.json; grep -i "NVLS\|P2P/\|via" $out/bench_cfg2_${n}gpu_nccl_$tag.err | head -5 ;;
+    3) run_bench 3 "--steps 2 --warmup 3" ;;
+    4) run_bench 4 "--steps 2 --warmup 1" ;;
+    5) run_bench 5 "--steps 3 --warmup 3" ;;
+    1) run_bench 1 "--steps 5 --warmup 3" ;;
+  esac
+done
+case " $what " in *" cli "*) ;; *) ls -la $out | tail -3; exit 0 ;; esac
 # the C++ CLI, one process per GPU
 rm -f /tmp/rfk_id
 for r in $(seq 1 $((n-1))); do
