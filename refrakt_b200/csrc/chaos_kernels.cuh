@@ -452,7 +452,7 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
 // coefficients, one re-deal key, one barrier and one trip of the loop serve two iterations of the chaos game (~20 of the
 // 135 instructions of an iteration are such per-trip overhead), and the two independent dependency chains overlap each
 // other's MUFU / shared-memory latency. 40 registers per thread at 1536 resident threads: 3072 particles per SM (2048 with
-// one particle per thread). Shipped genome: 135.0 -> 116.7 warp instructions per iteration.
+// one particle per thread). Shipped genome: 135.0 -> 121.6 warp instructions per iteration.
 // The warp's pick now covers 64 particles per iteration instead of 32 (the reference: 256).
 // ---------------------------------------------------------------------------------------------------------------------
 #ifndef RFK_PAIRS
