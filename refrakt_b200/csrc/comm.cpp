@@ -40,7 +40,10 @@ const nccl_api& nccl() {
             a.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (a.handle) break;
         }
-        if (!a.handle) throw std::runtime_error("multi-GPU: libnccl.so.2 cannot be loaded (set RFK_NCCL_LIBRARY): " + std::string(dlerror() ? dlerror() : ""));
+        if (!a.handle) {
+            const char* why = dlerror();  // one call: it clears the message
+            throw std::runtime_error("multi-GPU: libnccl.so.2 cannot be loaded (set RFK_NCCL_LIBRARY): " + std::string(why ? why : ""));
+        }
         auto get = [&](const char* sym, auto& fn) {
             void* p = dlsym(a.handle, sym);
             if (!p) throw std::runtime_error(std::string("multi-GPU: NCCL symbol missing: ") + sym);
