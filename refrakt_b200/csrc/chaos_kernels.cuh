@@ -281,6 +281,8 @@ __device__ __forceinline__ void rfk_iterate_body(const rfk_iter_params& p) {
       for (; it < block_end; ++it) {
         const int xid = get_xform_id(rfk_randf(rs));
 #else
+      // (the pick and the coefficients of the next iteration fetched one iteration ahead, as rfk_iterate_pairs does: -1 % on
+      // the shipped genome, +0.6 % / +4 % on the stress genome's specialised / generic build at 32 registers — not here)
       for (; pick_lane != pick_lane_end; ++pick_lane) {
         const int xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane);
 #endif
@@ -562,11 +564,28 @@ __device__ __forceinline__ void rfk_iterate_pairs(const rfk_iter_params& p) {
         const int block_len = ::min(32 - pick_lane, p.num_iter - it);
         pick_count += block_len;
         const int pick_lane_end = pick_lane + block_len;
+#if RFK_EXPERIMENT == 7  // A/B: the pick and the coefficients fetched at the top of the iteration that uses them
         for (; pick_lane != pick_lane_end; ++pick_lane) {
             const int xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane);
             __builtin_assume(xid >= 0 && xid < (RFK_NUM_XFORMS > 0 ? RFK_NUM_XFORMS : 1));
             vec4 r0, r1;
             dispatch2<false>(vec3(x0, y0, c0), vec3(x1, y1, c1), xid, rs0, rs1, r0, r1);
+#else
+        // the pick of an iteration and the rotated coefficients of its xform are fetched one iteration ahead, right after the
+        // dispatch: the shuffle and the shared-memory load then complete while the iteration bins and re-deals, instead of
+        // standing between the barrier and the first arithmetic of the next one (1.208 -> 1.195 ms per call on the shipped
+        // genome, 2.28 -> 2.20 on the stress genome; RFK_EXPERIMENT=7 is the old order)
+        int xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane);
+        __builtin_assume(xid >= 0 && xid < (RFK_NUM_XFORMS > 0 ? RFK_NUM_XFORMS : 1));
+        float4 coeff = rfk_aff[xid + 1];
+        while (pick_lane != pick_lane_end) {
+            vec4 r0, r1;
+            dispatch2_a<false>(vec3(x0, y0, c0), vec3(x1, y1, c1), xid, rs0, rs1, coeff, r0, r1);
+            ++pick_lane;
+            xid = __shfl_sync(0xffffffffu, pick_pool, pick_lane & 31);  // past the block's end: lane 0's pick, not used
+            __builtin_assume(xid >= 0 && xid < (RFK_NUM_XFORMS > 0 ? RFK_NUM_XFORMS : 1));
+            coeff = rfk_aff[xid + 1];
+#endif
             x0 = r0.x; y0 = r0.y; c0 = r0.z; x1 = r1.x; y1 = r1.y; c1 = r1.z;  // flame.glsl:72
             if (DRAW) {
 #if RFK_HAS_FINAL

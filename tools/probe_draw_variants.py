@@ -17,23 +17,26 @@ FIX = os.path.join(ROOT, "tests", "fixtures")
 P, TS, W, H = 2048 * 1024, 512, 3840, 2160
 
 
+PASSES = int(os.environ.get("PROBE_PASSES", "128"))  # iterations per draw call
+
+
 def measure(flame, name, spec, calls=12, pairs=1):
     flame.set_options(specialize=spec, pair_particles=pairs)
     r.set_sim_parameters(P, TS, 1024, seed=0)
     flame.warmup(16, 1.2 / 60)
     bins = torch.zeros(W * H * 4, dtype=torch.float32, device="cuda")
-    flame.draw_to_bins(bins.data_ptr(), W * H, W, 128)
+    flame.draw_to_bins(bins.data_ptr(), W * H, W, PASSES)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(calls):
-        flame.draw_to_bins_async(bins.data_ptr(), W * H, W, 128)
+        flame.draw_to_bins_async(bins.data_ptr(), W * H, W, PASSES)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / calls
     binned = flame.binned_total()
-    rec = dict(genome=name, specialize=spec, pair_particles=pairs, uses_specialised=flame.uses_specialised(), pair_state=flame.pair_particles_state(), ms_per_call=ms, giter_s=P * 128 / ms / 1e6,
-               in_bounds=binned / (P * 128 * (calls + 1)), **flame.kernel_info("rfk_draw"))
+    rec = dict(genome=name, specialize=spec, pair_particles=pairs, uses_specialised=flame.uses_specialised(), pair_state=flame.pair_particles_state(), ms_per_call=ms, passes=PASSES, giter_s=P * PASSES / ms / 1e6,
+               in_bounds=binned / (P * PASSES * (calls + 1)), **flame.kernel_info("rfk_draw"))
     print(json.dumps(rec), flush=True)
     d = bins.view(H, W, 4)[..., 3].double().view(H // 8, 8, W // 8, 8).sum(dim=(1, 3))
     return (d / d.sum()).cpu().numpy()
