@@ -560,6 +560,7 @@ def test_value_specialised_build_compiles_without_a_gpu(rfk, compiler, flame, ov
     assert "if (rfk_pick == 4) {" in body and body.index("rfk_pick == 4") < body.index("rfk_pick == 5")  # heaviest xform first
     assert len(flame.variant_cubin(False, True)) > 10000
     assert "#define RFK_PAIRS 1" in flame.variant_source(False, 2) and "#define RFK_PAIRS 1" not in src  # two particles per thread
+    assert src.count("#define RFK_EXPERIMENT") == 1 and "#define RFK_EXPERIMENT 0" in src  # timing builds only on request (environment)
     assert len(flame.variant_cubin(False, 2)) > 10000
     assert "#define RFK_STAGED_BINS 1" in flame.variant_source(True, False)
     # a genome whose reciprocals include infinities (1 / 0 for unused slots), and a uniform-weight genome (switch, not a chain)
