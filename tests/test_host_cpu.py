@@ -322,6 +322,15 @@ def test_buffer_cache_is_the_reference_file_format(rfk, tmp_path):
     assert struct.unpack("<Q", raw[:8])[0] == perm.nbytes and raw[8:] == perm.tobytes()
     assert np.array_equal(g.read_buffer(name, np.uint32), perm)
     assert g.write_buffer(perm) == name and g.cached_buffers() == [name]  # content-derived name
+    try:  # ... and, where the system carries xxHash (this image does), the reference's own: XXH3_128bits, high64 then low64
+        import ctypes.util
+        import xxhash
+        if ctypes.util.find_library("xxhash"):
+            assert name == xxhash.xxh3_128_hexdigest(perm.tobytes()).upper()
+            assert g.write_buffer(np.zeros(0, dtype=np.uint8)) == xxhash.xxh3_128_hexdigest(b"").upper()
+            os.remove(str(tmp_path / "cache" / "shuffle" / "4096" / (xxhash.xxh3_128_hexdigest(b"").upper() + ".bin")))
+    except ImportError:
+        pass
     other = g.write_buffer(perm[::-1].copy())
     assert sorted(g.cached_buffers()) == sorted([name, other])
     # a file written the way the reference writes it is read back
