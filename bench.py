@@ -180,7 +180,7 @@ def cpu_reference_run(cfg_id, steps, warmup, sample_passes=24, one_thread_probe=
         t3 = time.perf_counter()
         if s >= warmup:
             rows.append((t1 - t0, t2 - t1, t3 - t2))
-    chaos_s = sum(x[0] for x in rows) / len(rows)
+    chaos_s = min(x[0] for x in rows)  # the best step: the host cores are shared with other tenants of the box
     merge_s = sum(x[1] for x in rows) / len(rows)
     post_s = sum(x[2] for x in rows) / len(rows)
     iters = P * (1 + WARMUP_PASSES + sample_passes)
@@ -195,7 +195,7 @@ def cpu_reference_run(cfg_id, steps, warmup, sample_passes=24, one_thread_probe=
         orc.set_threads(threads)
     orc.release_private()
     sample = ("per step: warmup(16) + %d drawn passes of P=%d particles (TS=%d) into the %dx%d histogram = %d iterations on %d OpenMP threads, then merge of the private "
-              "histograms, density estimation + tonemap; chaos game, merge and post timed separately; not scaled") % (sample_passes, P, TS, W, H, iters, threads)
+              "histograms, density estimation + tonemap; chaos game, merge and post timed separately (%d untimed + %d timed steps, chaos game: the fastest); not scaled") % (sample_passes, P, TS, W, H, iters, threads, warmup, steps)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "threads": threads, "host_cores": cores,
             "one_thread_value": one_thread, "speedup_over_one_thread": (rate / one_thread) if one_thread else None,
             "chaos_seconds_per_step": chaos_s, "merge_ms": merge_s * 1e3, "post_ms": post_s * 1e3, "iterations_per_step": iters}
@@ -587,7 +587,7 @@ def main():
             line["roofline"] = roof
         if not args.no_cpu_baseline and world == 1:
             try:
-                base = cpu_reference_run(args.config, 1, 0, sample_passes=16)
+                base = cpu_reference_run(args.config, 2, 1, sample_passes=16)  # one untimed step: the private histograms are allocated and touched there
                 line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "threads", "one_thread_value", "speedup_over_one_thread", "merge_ms", "post_ms")}
             except Exception as e:  # the bench line must still print
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
